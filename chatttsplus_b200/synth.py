@@ -1,0 +1,192 @@
+"""Seeded synthetic checkpoints with the reference's state-dict key layout.
+
+No ChatTTS checkpoint exists offline (``checkpoints/`` is git-ignored and the pipeline
+downloads from the hub at first run), so parity tests, ``smoke()`` and ``bench.py`` all run on weights made
+here: real shapes, reference key names (SURVEY.md appendix A.3 = the module structure of
+chattts_plus/models/gpt.py:43-77, dvae.py:129-168,203-241 and the vocos config in
+configs/infer/chattts_plus.yaml:46-66), ``torch.Generator``-seeded so every box regenerates the same tensors.
+The same dicts are bound to the CUDA kernels and to the oracle.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, Optional
+
+import torch
+
+
+@dataclass
+class GPTConfig:
+    hidden_size: int = 768
+    intermediate_size: int = 3072
+    num_attention_heads: int = 12
+    num_hidden_layers: int = 20
+    num_audio_tokens: int = 626
+    num_text_tokens: int = 21178
+    num_vq: int = 4
+    rms_norm_eps: float = 1e-6
+    rope_theta: float = 10000.0
+    max_position_embeddings: int = 4096
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden_size // self.num_attention_heads
+
+
+@dataclass
+class DVAEConfig:
+    """Decoder side of the DVAE. Defaults = ``dvae_decode`` (Decoder.pt) in configs/infer/chattts_plus.yaml."""
+    dim: int = 384            # out_conv input channels == decoder odim
+    idim: int = 384
+    odim: int = 384
+    hidden: int = 512
+    n_layer: int = 12
+    bn_dim: int = 128
+    kernel: int = 7
+    dilation: int = 2
+    n_mels: int = 100
+    # GFSQ (only for the codes->mel model, ``dvae_encode`` / DVAE_full.pt)
+    vq: bool = False
+    vq_dim: int = 1024
+    vq_levels: tuple = (5, 5, 5, 5)
+    vq_G: int = 2
+    vq_R: int = 2
+
+    @staticmethod
+    def codes_model() -> "DVAEConfig":
+        return DVAEConfig(dim=512, idim=512, odim=512, hidden=256, n_layer=12, bn_dim=128, vq=True)
+
+
+@dataclass
+class VocosConfig:
+    input_channels: int = 100
+    dim: int = 512
+    intermediate_dim: int = 1536
+    num_layers: int = 8
+    n_fft: int = 1024
+    hop_length: int = 256
+
+
+def _gen(seed: int) -> torch.Generator:
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    return g
+
+
+def _n(g, *shape, std=1.0, mean=0.0):
+    return torch.randn(*shape, generator=g, dtype=torch.float32) * std + mean
+
+
+def _u(g, *shape, lo=0.0, hi=1.0):
+    return torch.rand(*shape, generator=g, dtype=torch.float32) * (hi - lo) + lo
+
+
+def make_gpt_state(cfg: GPTConfig = GPTConfig(), seed: int = 1234, head_gain: float = 4.0) -> Dict[str, torch.Tensor]:
+    """``GPT.pt``-shaped state dict (keys as loaded strictly by reference gpt.py:84-85)."""
+    g = _gen(seed)
+    H, I = cfg.hidden_size, cfg.intermediate_size
+    sd: Dict[str, torch.Tensor] = {}
+    for l in range(cfg.num_hidden_layers):
+        p = f"gpt.layers.{l}."
+        sd[p + "input_layernorm.weight"] = 1.0 + _n(g, H, std=0.1)
+        sd[p + "post_attention_layernorm.weight"] = 1.0 + _n(g, H, std=0.1)
+        for nm in ("q_proj", "k_proj", "v_proj", "o_proj"):
+            sd[p + f"self_attn.{nm}.weight"] = _n(g, H, H, std=0.02)
+        # keys sharper than HF init so attention is not uniform (exercises the softmax)
+        sd[p + "self_attn.q_proj.weight"] *= 3.0
+        sd[p + "self_attn.k_proj.weight"] *= 3.0
+        sd[p + "mlp.gate_proj.weight"] = _n(g, I, H, std=0.02)
+        sd[p + "mlp.up_proj.weight"] = _n(g, I, H, std=0.02)
+        sd[p + "mlp.down_proj.weight"] = _n(g, H, I, std=0.02)
+    sd["gpt.norm.weight"] = 1.0 + _n(g, H, std=0.1)
+    for q in range(cfg.num_vq):
+        sd[f"emb_code.{q}.weight"] = _n(g, cfg.num_audio_tokens, H, std=0.5)
+    sd["emb_text.weight"] = _n(g, cfg.num_text_tokens, H, std=1.0)
+    v = _n(g, cfg.num_text_tokens, H, std=0.02)
+    sd["head_text.parametrizations.weight.original0"] = v.norm(dim=1, keepdim=True) * head_gain
+    sd["head_text.parametrizations.weight.original1"] = v
+    for q in range(cfg.num_vq):
+        v = _n(g, cfg.num_audio_tokens, H, std=0.02)
+        sd[f"head_code.{q}.parametrizations.weight.original0"] = v.norm(dim=1, keepdim=True) * head_gain
+        sd[f"head_code.{q}.parametrizations.weight.original1"] = v
+    return sd
+
+
+def _convnext(sd, g, prefix, dim, inter, kernel, gamma_lo, gamma_hi):
+    sd[prefix + "dwconv.weight"] = _n(g, dim, 1, kernel, std=kernel ** -0.5)
+    sd[prefix + "dwconv.bias"] = _n(g, dim, std=0.05)
+    sd[prefix + "norm.weight"] = 1.0 + _n(g, dim, std=0.1)
+    sd[prefix + "norm.bias"] = _n(g, dim, std=0.05)
+    sd[prefix + "pwconv1.weight"] = _n(g, inter, dim, std=dim ** -0.5)
+    sd[prefix + "pwconv1.bias"] = _n(g, inter, std=0.05)
+    sd[prefix + "pwconv2.weight"] = _n(g, dim, inter, std=inter ** -0.5)
+    sd[prefix + "pwconv2.bias"] = _n(g, dim, std=0.05)
+    sd[prefix + "gamma"] = _u(g, dim, lo=gamma_lo, hi=gamma_hi)
+
+
+def make_dvae_state(cfg: DVAEConfig = DVAEConfig(), seed: int = 4321) -> Dict[str, torch.Tensor]:
+    """``Decoder.pt`` / decode-side ``DVAE_full.pt`` state dict (reference dvae.py:129-168,203-241)."""
+    g = _gen(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    sd["coef"] = _u(g, 1, cfg.n_mels, 1, lo=0.5, hi=1.5)
+    sd["decoder.conv_in.0.weight"] = _n(g, cfg.bn_dim, cfg.idim, 3, std=(3 * cfg.idim) ** -0.5)
+    sd["decoder.conv_in.0.bias"] = _n(g, cfg.bn_dim, std=0.05)
+    sd["decoder.conv_in.2.weight"] = _n(g, cfg.hidden, cfg.bn_dim, 3, std=(3 * cfg.bn_dim) ** -0.5)
+    sd["decoder.conv_in.2.bias"] = _n(g, cfg.hidden, std=0.05)
+    for l in range(cfg.n_layer):
+        _convnext(sd, g, f"decoder.decoder_block.{l}.", cfg.hidden, cfg.hidden * 4, cfg.kernel, 0.05, 0.3)
+    sd["decoder.conv_out.weight"] = _n(g, cfg.odim, cfg.hidden, 1, std=cfg.hidden ** -0.5)
+    sd["out_conv.weight"] = _n(g, cfg.n_mels, cfg.dim, 3, std=(3 * cfg.dim) ** -0.5)
+    if cfg.vq:
+        # GroupedResidualFSQ: one ResidualFSQ per group, each with project_in (dim/G -> len(levels)) and
+        # project_out (len(levels) -> dim/G); only project_out is used by get_output_from_indices.
+        gd = cfg.vq_dim // cfg.vq_G
+        nl = len(cfg.vq_levels)
+        for gi in range(cfg.vq_G):
+            sd[f"vq_layer.quantizer.rvqs.{gi}.project_in.weight"] = _n(g, nl, gd, std=gd ** -0.5)
+            sd[f"vq_layer.quantizer.rvqs.{gi}.project_in.bias"] = _n(g, nl, std=0.05)
+            sd[f"vq_layer.quantizer.rvqs.{gi}.project_out.weight"] = _n(g, gd, nl, std=0.5)
+            sd[f"vq_layer.quantizer.rvqs.{gi}.project_out.bias"] = _n(g, gd, std=0.05)
+    return sd
+
+
+def make_vocos_state(cfg: VocosConfig = VocosConfig(), seed: int = 9876) -> Dict[str, torch.Tensor]:
+    """``Vocos.pt``-shaped state dict (vocos package module names: backbone.embed / norm / convnext.N /
+    final_layer_norm, head.out, head.istft.window)."""
+    g = _gen(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    C, D = cfg.input_channels, cfg.dim
+    sd["backbone.embed.weight"] = _n(g, D, C, 7, std=(7 * C) ** -0.5)
+    sd["backbone.embed.bias"] = _n(g, D, std=0.05)
+    sd["backbone.norm.weight"] = 1.0 + _n(g, D, std=0.1)
+    sd["backbone.norm.bias"] = _n(g, D, std=0.05)
+    for l in range(cfg.num_layers):
+        _convnext(sd, g, f"backbone.convnext.{l}.", D, cfg.intermediate_dim, 7, 0.05, 0.25)
+    sd["backbone.final_layer_norm.weight"] = 1.0 + _n(g, D, std=0.1)
+    sd["backbone.final_layer_norm.bias"] = _n(g, D, std=0.05)
+    sd["head.out.weight"] = _n(g, cfg.n_fft + 2, D, std=0.6 * D ** -0.5)
+    sd["head.out.bias"] = _n(g, cfg.n_fft + 2, std=0.3)
+    # log-magnitudes centred so that |S| ~ 1e-2 .. 1 (waveform amplitude O(0.1), like real speech)
+    sd["head.out.bias"][: cfg.n_fft // 2 + 1] -= 2.5
+    sd["head.istft.window"] = torch.hann_window(cfg.n_fft, periodic=True, dtype=torch.float32)
+    return sd
+
+
+def make_lora_state(cfg: GPTConfig = GPTConfig(), r: int = 8, seed: int = 777) -> Dict[str, torch.Tensor]:
+    """peft-adapter-shaped tensors (keys as written by peft ``save_pretrained`` for a LlamaModel wrapped in
+    PeftModel: base_model.model.layers.N.self_attn.{q,k,v,o}_proj.lora_{A,B}.weight)."""
+    g = _gen(seed)
+    H = cfg.hidden_size
+    sd = {}
+    for l in range(cfg.num_hidden_layers):
+        for nm in ("q_proj", "k_proj", "v_proj", "o_proj"):
+            p = f"base_model.model.layers.{l}.self_attn.{nm}."
+            sd[p + "lora_A.weight"] = _n(g, r, H, std=0.02)
+            sd[p + "lora_B.weight"] = _n(g, H, r, std=0.02)
+    return sd
+
+
+def make_spk_stat(seed: int = 2468, dim: int = 768) -> torch.Tensor:
+    """``spk_stat.pt``: ``[2*dim]`` = (std, mean) halves (reference chattts_plus_pipeline.py:140-145)."""
+    g = _gen(seed)
+    return torch.cat([_u(g, dim, lo=0.5, hi=2.0), _n(g, dim, std=1.0)])
