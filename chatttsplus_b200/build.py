@@ -1,0 +1,79 @@
+"""Build libctp.so (hand-written sm_100a CUDA + the C ABI) in-tree with nvcc.
+
+    python -m chatttsplus_b200.build [--force]
+
+nvcc cross-compiles for sm_100a without a GPU.  The shared object lands in chatttsplus_b200/_C/ (git-ignored,
+but shipped to the GPU box with the tree).
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT_DIR = os.path.join(HERE, "_C")
+LIB = os.path.join(OUT_DIR, "libctp.so")
+SOURCES = ["ctp_capi_core.cu", "gemm.cu", "gpt.cu", "voc.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc() -> str:
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
+            return c
+    return "nvcc"
+
+
+def _digest() -> str:
+    h = hashlib.sha256()
+    for root in (CSRC, os.path.join(HERE, "..", "include")):
+        for fn in sorted(os.listdir(root)):
+            if fn.endswith((".cu", ".cuh", ".h")):
+                with open(os.path.join(root, fn), "rb") as f:
+                    h.update(fn.encode())
+                    h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OUT_DIR, exist_ok=True)
+    stamp = os.path.join(OUT_DIR, "build.stamp")
+    dig = _digest()
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
+        return LIB
+    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    objs = []
+    procs = []
+    for s in srcs:
+        o = os.path.join(OUT_DIR, os.path.basename(s) + ".o")
+        objs.append(o)
+        cmd = [_nvcc(), *NVCC_FLAGS, "-c", s, "-o", o]
+        if verbose:
+            cmd.insert(1, "-Xptxas")
+            cmd.insert(2, "-v")
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode:
+            print(out)
+        if p.returncode:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    link = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
+    r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode:
+        print(r.stdout)
+        raise RuntimeError("link failed")
+    with open(stamp, "w") as f:
+        f.write(dig)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

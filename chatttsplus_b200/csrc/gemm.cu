@@ -1,0 +1,118 @@
+// Host side of the tcgen05 GEMM: tensor-map construction (driver entry point resolved at run time, so the
+// library links against nothing but the static CUDA runtime) and launch dispatch over the N-tile width.
+#include "gemm.cuh"
+#include "../../include/ctp.h"
+
+#include <cudaTypedefs.h>
+#include <mutex>
+#include <stdlib.h>
+
+namespace ctp {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static std::once_flag g_once;
+static int g_init_status = 0;
+static uint32_t g_desc[4] = {1, 64, 2, 2};  // LBO>>4, SBO>>4, layout type, K-advance per UMMA_K (in 16-byte units)
+
+template <int BN>
+static cudaError_t set_smem_attr() {
+    return cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::TOTAL);
+}
+
+int gemm_init() {
+    std::call_once(g_once, [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+            ctp_set_error("cuTensorMapEncodeTiled not available: %s", cudaGetErrorString(e));
+            g_init_status = CTP_ERR_NO_DEVICE;
+            return;
+        }
+        g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+        if (const char* d = getenv("CTP_DESC")) {  // bring-up diagnostics only
+            unsigned a, b, c, e;
+            if (sscanf(d, "%u,%u,%u,%u", &a, &b, &c, &e) == 4) { g_desc[0] = a; g_desc[1] = b; g_desc[2] = c; g_desc[3] = e; }
+        }
+        cudaError_t a = set_smem_attr<32>();
+        if (a == cudaSuccess) a = set_smem_attr<64>();
+        if (a == cudaSuccess) a = set_smem_attr<128>();
+        if (a == cudaSuccess) a = set_smem_attr<256>();
+        if (a != cudaSuccess) {
+            ctp_set_error("cudaFuncSetAttribute(gemm smem): %s", cudaGetErrorString(a));
+            g_init_status = CTP_ERR_CUDA;
+        }
+    });
+    return g_init_status;
+}
+
+int make_tmap_kmajor(CUtensorMap* out, const void* base, long long rows, long long K, long long ld_elems, int box_rows) {
+    int st = gemm_init();
+    if (st) return st;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ((ld_elems * 2) & 15) != 0) {
+        ctp_set_error("tensor map: base %p / row pitch %lld elements must be 16-byte aligned", base, ld_elems);
+        return CTP_ERR_INVALID;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)(ld_elems * 2)};
+    cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        ctp_set_error("cuTensorMapEncodeTiled failed (%d): rows=%lld K=%lld ld=%lld box_rows=%d", (int)r, rows, K, ld_elems,
+                      box_rows);
+        return CTP_ERR_CUDA;
+    }
+    return CTP_OK;
+}
+
+template <int BN>
+static int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, long long a_rows, long long b_rows, long long K,
+                     int split_k, const GemmEpilogue& epi, cudaStream_t stream) {
+    GemmShape shp;
+    shp.k_blocks = (int)((K + GEMM_BK - 1) / GEMM_BK);
+    shp.desc_lbo = g_desc[0]; shp.desc_sbo = g_desc[1]; shp.desc_layout = g_desc[2]; shp.desc_kadv = g_desc[3];
+    if (split_k < 1) split_k = 1;
+    if (split_k > shp.k_blocks) split_k = shp.k_blocks;
+    if (split_k > 1 && !(epi.atomic && !epi.out_f16)) {
+        ctp_set_error("gemm: split_k > 1 needs fp32 atomic output");
+        return CTP_ERR_INVALID;
+    }
+    dim3 grid((unsigned)((b_rows + BN - 1) / BN), (unsigned)((a_rows + GEMM_BM - 1) / GEMM_BM), (unsigned)split_k);
+    gemm_tcgen05_kernel<BN><<<grid, GEMM_THREADS, GemmSmem<BN>::TOTAL, stream>>>(tmA, tmB, shp, epi);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        ctp_set_error("gemm launch failed: %s", cudaGetErrorString(e));
+        return CTP_ERR_CUDA;
+    }
+    return CTP_OK;
+}
+
+int gemm_launch_maps(const CUtensorMap& tmA, const CUtensorMap& tmB, long long a_rows, long long b_rows, long long K,
+                     int block_n, int split_k, const GemmEpilogue& epi, cudaStream_t stream) {
+    int st = gemm_init();
+    if (st) return st;
+    switch (block_n) {
+        case 32: return launch_bn<32>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream);
+        case 64: return launch_bn<64>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream);
+        case 128: return launch_bn<128>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream);
+        case 256: return launch_bn<256>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream);
+        default: ctp_set_error("gemm: unsupported block_n %d", block_n); return CTP_ERR_INVALID;
+    }
+}
+
+int gemm_launch(const GemmLaunch& g, cudaStream_t stream) {
+    CUtensorMap tmA, tmB;
+    int st = make_tmap_kmajor(&tmA, g.A, g.a_rows, g.K, g.lda, GEMM_BM);
+    if (st) return st;
+    st = make_tmap_kmajor(&tmB, g.B, g.b_rows, g.K, g.ldb, g.block_n);
+    if (st) return st;
+    return gemm_launch_maps(tmA, tmB, g.a_rows, g.b_rows, g.K, g.block_n, g.split_k, g.epi, stream);
+}
+
+}  // namespace ctp

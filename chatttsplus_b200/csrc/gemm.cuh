@@ -1,0 +1,254 @@
+// tcgen05 + TMA GEMM for sm_100a:  D[Mrows, Ncols] = sum_k A[Mrows,k] * B[Ncols,k]   (both operands K-major fp16)
+//
+//   * one 128 x BN output tile per CTA, K in blocks of 64 (one 128-byte swizzle row), STAGES-deep TMA ring
+//   * warp 4 lane 0: TMA producer; warp 5 lane 0: tcgen05.mma issuer (accumulator in TMEM, fp32);
+//     warps 0-3: epilogue (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+//   * split-K over gridDim.z with fp32 atomic accumulation (decode path: the weight stream is spread over SMs)
+//   * "swap" orientation: the M operand is the weight matrix [features, K] and the N operand the (few) tokens, so
+//     a batch-32 decode step still fills the 128-row MMA (rows = output features, columns = batch rows).
+//
+// Operand tiles in shared memory use the 128B-swizzled K-major canonical layout (see ctp_common.cuh).
+#pragma once
+#include "ctp_common.cuh"
+
+namespace ctp {
+
+struct GemmEpilogue {
+    void* out;               // fp32 or fp16, element (t, f) at out[t*ldo + f]
+    long long ldo;
+    int out_f16;             // 1: __half output, 0: float
+    int atomic;              // 1: atomicAdd into fp32 out (split-K or residual accumulate)
+    int swap;                // 0: tile rows = tokens t, tile cols = features f;  1: rows = f, cols = t
+    int act_gelu;            // exact-erf GELU after bias
+    const float* bias;       // [F] or null
+    const float* gamma;      // [F] or null (applied after activation)
+    const float* residual;   // fp32 [T][ldr] or null (added last)
+    long long ldr;
+    const unsigned char* row_valid;  // [T] or null: invalid tokens are written as 0
+    int T, F;                // logical extents (bounds for partial tiles)
+};
+
+struct GemmShape {
+    int k_blocks;  // ceil(K / 64)
+    // shared-memory matrix descriptor fields (defaults = 128B-swizzled K-major canonical layout); overridable through
+    // the CTP_DESC environment variable for bring-up diagnostics only
+    uint32_t desc_lbo, desc_sbo, desc_layout, desc_kadv;
+};
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+template <int BN>
+struct GemmSmem {
+    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
+    static constexpr int B_BYTES = BN * GEMM_BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    // <= 200 KB of operand ring; leaves room for the barrier block and 1 KB alignment slack under 227 KB
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+};
+
+template <int BN>
+__device__ __forceinline__ void gemm_epilogue_store(const GemmEpilogue& e, int row_g, int col_g0, const float (&acc)[32],
+                                                    bool add_bias) {
+    // row_g: global index along the M operand; col_g0..+31: along the N operand
+    if (!e.swap) {
+        const int t = row_g;
+        if (t >= e.T) return;
+        const bool valid = e.row_valid ? (e.row_valid[t] != 0) : true;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int f = col_g0 + j;
+            float x = acc[j];
+            if (f < e.F) {
+                if (e.bias && add_bias) x += e.bias[f];
+                if (e.act_gelu) x = gelu_erf(x);
+                if (e.gamma) x *= e.gamma[f];
+                if (e.residual && add_bias) x += e.residual[(long long)t * e.ldr + f];
+            }
+            v[j] = valid ? x : 0.0f;
+        }
+        if (e.out_f16) {
+            __half* o = reinterpret_cast<__half*>(e.out) + (long long)t * e.ldo + col_g0;
+            if (col_g0 + 32 <= e.F && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    __half2 h0 = __floats2half2_rn(v[j], v[j + 1]);
+                    __half2 h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
+                    __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]);
+                    __half2 h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
+                    uint4 pk;
+                    pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                    pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                    pk.z = *reinterpret_cast<uint32_t*>(&h2);
+                    pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                    *reinterpret_cast<uint4*>(o + j) = pk;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (col_g0 + j < e.F) o[j] = __float2half_rn(v[j]);
+            }
+        } else {
+            float* o = reinterpret_cast<float*>(e.out) + (long long)t * e.ldo + col_g0;
+            if (e.atomic) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (col_g0 + j < e.F) atomicAdd(o + j, v[j]);
+            } else if (col_g0 + 32 <= e.F && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (col_g0 + j < e.F) o[j] = v[j];
+            }
+        }
+    } else {
+        // rows are features: consecutive lanes hold consecutive f for a fixed token -> coalesced along f
+        const int f = row_g;
+        if (f >= e.F) return;
+        const float b = (e.bias && add_bias) ? e.bias[f] : 0.0f;
+        const float g = e.gamma ? e.gamma[f] : 1.0f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int t = col_g0 + j;
+            if (t >= e.T) break;
+            float x = acc[j] + b;
+            if (e.act_gelu) x = gelu_erf(x);
+            x *= g;
+            if (e.residual && add_bias) x += e.residual[(long long)t * e.ldr + f];
+            if (e.row_valid && !e.row_valid[t]) x = 0.0f;
+            if (e.out_f16) {
+                reinterpret_cast<__half*>(e.out)[(long long)t * e.ldo + f] = __float2half_rn(x);
+            } else {
+                float* o = reinterpret_cast<float*>(e.out) + (long long)t * e.ldo + f;
+                if (e.atomic) atomicAdd(o, x);
+                else *o = x;
+            }
+        }
+    }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmShape shp, const GemmEpilogue epi) {
+    using S = GemmSmem<BN>;
+    constexpr int STAGES = S::STAGES;
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment for the 128B-swizzle atoms
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* ring = smem;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* accum_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN;
+    const int m0 = blockIdx.y * GEMM_BM;
+    const int nsplit = gridDim.z;
+    const int kb0 = (int)(((long long)shp.k_blocks * blockIdx.z) / nsplit);
+    const int kb1 = (int)(((long long)shp.k_blocks * (blockIdx.z + 1)) / nsplit);
+    const int nkb = kb1 - kb0;
+
+    if (warp == 4 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 5) tmem_alloc<TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (i / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* a = ring + s * S::STAGE_BYTES;
+                uint8_t* b = a + S::A_BYTES;
+                mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
+                tma_load_2d(&tmA, &full_bar[s], a, (kb0 + i) * GEMM_BK, m0);
+                tma_load_2d(&tmB, &full_bar[s], b, (kb0 + i) * GEMM_BK, n0);
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, BN);
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (i / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(ring + s * S::STAGE_BYTES);
+                const uint64_t da = make_kmajor_desc(a_addr, shp.desc_lbo, shp.desc_sbo, shp.desc_layout);
+                const uint64_t db = make_kmajor_desc(a_addr + S::A_BYTES, shp.desc_lbo, shp.desc_sbo, shp.desc_layout);
+#pragma unroll
+                for (int k = 0; k < GEMM_BK / 16; ++k) {
+                    // advance 16 fp16 = 32 bytes along K inside the swizzle row: +2 in the (addr>>4) field
+                    umma_f16(tmem_base, da + (uint64_t)(shp.desc_kadv * k), db + (uint64_t)(shp.desc_kadv * k), idesc,
+                             (i > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above retire
+            }
+            umma_commit(accum_bar);  // accumulator complete
+        }
+    } else {
+        // epilogue warps 0..3: TMEM lanes [32*warp, 32*warp+32)
+        if (nkb > 0) {
+            mbar_wait(accum_bar, 0);
+            tc_fence_after();
+            const int row_g = m0 + warp * 32 + lane;
+            const bool add_bias = (blockIdx.z == 0);
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                float acc[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, acc);
+                gemm_epilogue_store<BN>(epi, row_g, n0 + c, acc, add_bias);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------------------
+// K-major fp16 matrix [rows, K] with row pitch `ld` elements -> 2-D tensor map, box = 64 x box_rows, 128B swizzle.
+// Overlapping rows (ld < K, used for the k3/k7 convolutions as im2col windows) are legal: strides only need to be
+// multiples of 16 bytes.
+int make_tmap_kmajor(CUtensorMap* out, const void* base, long long rows, long long K, long long ld_elems, int box_rows);
+
+struct GemmLaunch {
+    const void* A; long long a_rows; long long lda;   // M operand
+    const void* B; long long b_rows; long long ldb;   // N operand
+    long long K;
+    int block_n;   // 32, 64, 128, 256
+    int split_k;
+    GemmEpilogue epi;
+};
+int gemm_launch(const GemmLaunch& g, cudaStream_t stream);
+// Variant with prebuilt tensor maps (decode path: maps are created once at bind time).
+int gemm_launch_maps(const CUtensorMap& tmA, const CUtensorMap& tmB, long long a_rows, long long b_rows, long long K,
+                     int block_n, int split_k, const GemmEpilogue& epi, cudaStream_t stream);
+int gemm_init();  // resolves cuTensorMapEncodeTiled, sets max dynamic smem attributes
+
+}  // namespace ctp

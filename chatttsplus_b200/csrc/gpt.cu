@@ -1,0 +1,551 @@
+// GPT decoder handle: weight binding, prefill, decode step, sampler, device-resident generate loop.
+// C-ABI entry points are declared in include/ctp.h (each cites the reference interface it replaces).
+#include "gemm.cuh"
+#include "gpt_kernels.cuh"
+
+#include <map>
+#include <math.h>
+#include <string.h>
+#include <vector>
+
+using namespace ctp;
+
+namespace {
+
+struct LayerMaps {
+    CUtensorMap wqkv, wo, wgu, wdown;
+};
+
+struct ActMaps {  // activation operands (N side) for one N-tile width
+    CUtensorMap xn, attn, hmid;
+};
+
+struct GraphKey {
+    int B, nsplit;
+    bool operator<(const GraphKey& o) const { return B != o.B ? B < o.B : nsplit < o.nsplit; }
+};
+
+}  // namespace
+
+struct ctp_gpt {
+    ctp_gpt_cfg cfg{};
+    ctp_gpt_weights w{};
+    bool bound = false;
+    int dev = 0;
+
+    // device workspace (rows = max(max_batch, prefill tokens))
+    long long ws_rows = 0;
+    float* x = nullptr;        // [rows][H] residual stream
+    __half* xn = nullptr;      // [rows][H]
+    float* acc_qkv = nullptr;  // [rows][3H]
+    __half* attn = nullptr;    // [rows][H]
+    float* acc_gu = nullptr;   // [rows][2I]
+    __half* hmid = nullptr;    // [rows][I]
+    float* x_last = nullptr;   // [maxB][H] (prefill: gathered last positions)
+    float* hidden = nullptr;   // [maxB][H]
+    float* logits = nullptr;   // [maxB][num_vq*num_audio]
+    __half* kv = nullptr;      // [L][2][maxB][nH][maxS][64]
+    float* attn_part = nullptr;
+    int* attn_cnt = nullptr;
+    int* pad_len = nullptr;    // [maxB]
+    float* inv_freq = nullptr; // [32]
+    GenState* st = nullptr;    // device
+    GenState* st_pin = nullptr;  // pinned host mirror for polling
+    int max_splits = 16;
+
+    std::vector<LayerMaps> lmaps;
+    CUtensorMap head_map{};
+    ActMaps act32{}, act64{};
+    // decode activation maps point at the first max_batch rows of xn / attn / hmid
+    std::map<GraphKey, cudaGraphExec_t> graphs;
+    cudaStream_t cap_stream = nullptr;
+
+    // host mirror of the generation state
+    int B = 0, cur_len = 0, step = 0, max_new = 0;
+    bool have_bufs = false;
+
+    size_t kv_plane_elems() const { return (size_t)cfg.max_batch * cfg.n_heads * cfg.max_seq * HEAD_DIM; }
+    __half* kplane(int l) const { return kv + (size_t)(2 * l) * kv_plane_elems(); }
+    __half* vplane(int l) const { return kv + (size_t)(2 * l + 1) * kv_plane_elems(); }
+};
+
+static int ensure_workspace(ctp_gpt* h, long long rows) {
+    if (rows < 64) rows = 64;  // decode activation tensor maps always span 64 rows (widest N tile)
+    if (rows <= h->ws_rows) return CTP_OK;
+    const int H = h->cfg.hidden, I = h->cfg.inter;
+    cudaFree(h->x); cudaFree(h->xn); cudaFree(h->acc_qkv); cudaFree(h->attn); cudaFree(h->acc_gu); cudaFree(h->hmid);
+    h->x = nullptr; h->xn = nullptr; h->acc_qkv = nullptr; h->attn = nullptr; h->acc_gu = nullptr; h->hmid = nullptr;
+    h->ws_rows = 0;
+    CTP_CUDA_OK(cudaMalloc(&h->x, sizeof(float) * rows * H));
+    CTP_CUDA_OK(cudaMalloc(&h->xn, sizeof(__half) * rows * H));
+    CTP_CUDA_OK(cudaMalloc(&h->acc_qkv, sizeof(float) * rows * 3 * H));
+    CTP_CUDA_OK(cudaMalloc(&h->attn, sizeof(__half) * rows * H));
+    CTP_CUDA_OK(cudaMalloc(&h->acc_gu, sizeof(float) * rows * 2 * I));
+    CTP_CUDA_OK(cudaMalloc(&h->hmid, sizeof(__half) * rows * I));
+    CTP_CUDA_OK(cudaMemset(h->xn, 0, sizeof(__half) * rows * H));
+    CTP_CUDA_OK(cudaMemset(h->attn, 0, sizeof(__half) * rows * H));
+    CTP_CUDA_OK(cudaMemset(h->hmid, 0, sizeof(__half) * rows * I));
+    h->ws_rows = rows;
+    // decode activation maps depend on the buffer addresses
+    const int mb = 64;  // rows past the live batch hold zeros/stale data; their output columns are masked
+    int st;
+    for (int bn : {32, 64}) {
+        ActMaps& am = (bn == 32) ? h->act32 : h->act64;
+        if ((st = make_tmap_kmajor(&am.xn, h->xn, mb, H, H, bn))) return st;
+        if ((st = make_tmap_kmajor(&am.attn, h->attn, mb, H, H, bn))) return st;
+        if ((st = make_tmap_kmajor(&am.hmid, h->hmid, mb, I, I, bn))) return st;
+    }
+    // captured graphs hold the old pointers
+    for (auto& kvp : h->graphs) cudaGraphExecDestroy(kvp.second);
+    h->graphs.clear();
+    return CTP_OK;
+}
+
+extern "C" ctp_status ctp_gpt_create(ctp_gpt** out, const ctp_gpt_cfg* cfg) {
+    CTP_REQUIRE(out && cfg, "ctp_gpt_create: null argument");
+    CTP_REQUIRE(cfg->n_heads * HEAD_DIM == cfg->hidden, "head_dim must be 64 (hidden %d, heads %d)", cfg->hidden, cfg->n_heads);
+    CTP_REQUIRE(cfg->hidden % 64 == 0 && cfg->hidden <= 1024 && cfg->inter % 64 == 0, "hidden/inter must be multiples of 64, hidden <= 1024");
+    CTP_REQUIRE(cfg->n_heads * 32 <= 1024, "too many heads");
+    CTP_REQUIRE(cfg->max_batch >= 1 && cfg->max_batch <= 64, "max_batch must be in [1,64]");
+    CTP_REQUIRE(cfg->num_vq >= 1 && cfg->num_vq <= MAX_VQ, "num_vq must be in [1,%d]", MAX_VQ);
+    CTP_REQUIRE(cfg->max_seq >= 2, "max_seq too small");
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        ctp_set_error("no CUDA device: libctp has no CPU fallback");
+        return CTP_ERR_NO_DEVICE;
+    }
+    ctp_status ds = ctp_device_check(dev);
+    if (ds != CTP_OK) return ds;
+    int gi = gemm_init();
+    if (gi) return (ctp_status)gi;
+    ctp_gpt* h = new ctp_gpt();
+    h->cfg = *cfg;
+    h->dev = dev;
+    const int H = cfg->hidden, mb = cfg->max_batch;
+    const size_t kv_elems = (size_t)cfg->n_layers * 2 * h->kv_plane_elems();
+#define CK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { ctp_set_error("%s -> %s", #expr, cudaGetErrorString(_e)); ctp_gpt_destroy(h); return CTP_ERR_CUDA; } } while (0)
+    CK(cudaMalloc(&h->kv, kv_elems * sizeof(__half)));
+    CK(cudaMemset(h->kv, 0, kv_elems * sizeof(__half)));
+    CK(cudaMalloc(&h->x_last, sizeof(float) * mb * H));
+    CK(cudaMalloc(&h->hidden, sizeof(float) * mb * H));
+    const size_t lg = (size_t)mb * std::max(cfg->num_vq * cfg->num_audio, 1);
+    CK(cudaMalloc(&h->logits, sizeof(float) * lg));
+    CK(cudaMalloc(&h->attn_part, sizeof(float) * (size_t)mb * cfg->n_heads * h->max_splits * 66));
+    CK(cudaMalloc(&h->attn_cnt, sizeof(int) * mb * cfg->n_heads));
+    CK(cudaMemset(h->attn_cnt, 0, sizeof(int) * mb * cfg->n_heads));
+    CK(cudaMalloc(&h->pad_len, sizeof(int) * mb));
+    CK(cudaMemset(h->pad_len, 0, sizeof(int) * mb));
+    CK(cudaMalloc(&h->inv_freq, sizeof(float) * 32));
+    CK(cudaMalloc(&h->st, sizeof(GenState)));
+    CK(cudaMemset(h->st, 0, sizeof(GenState)));
+    CK(cudaMallocHost(&h->st_pin, sizeof(GenState)));
+    CK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    {
+        // llama.py:98 — inv_freq = 1 / base^(2i/d), evaluated in fp32 like torch does
+        float f[32];
+        for (int i = 0; i < 32; ++i) f[i] = 1.0f / powf(cfg->rope_theta, (float)(2 * i) / (float)HEAD_DIM);
+        CK(cudaMemcpy(h->inv_freq, f, sizeof(f), cudaMemcpyHostToDevice));
+    }
+#undef CK
+    int st = ensure_workspace(h, mb);
+    if (st) { ctp_gpt_destroy(h); return (ctp_status)st; }
+    *out = h;
+    return CTP_OK;
+}
+
+extern "C" void ctp_gpt_destroy(ctp_gpt* h) {
+    if (!h) return;
+    for (auto& kvp : h->graphs) cudaGraphExecDestroy(kvp.second);
+    cudaFree(h->x); cudaFree(h->xn); cudaFree(h->acc_qkv); cudaFree(h->attn); cudaFree(h->acc_gu); cudaFree(h->hmid);
+    cudaFree(h->x_last); cudaFree(h->hidden); cudaFree(h->logits); cudaFree(h->kv); cudaFree(h->attn_part);
+    cudaFree(h->attn_cnt); cudaFree(h->pad_len); cudaFree(h->inv_freq); cudaFree(h->st);
+    if (h->st_pin) cudaFreeHost(h->st_pin);
+    if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+    delete h;
+}
+
+extern "C" ctp_status ctp_gpt_bind_weights(ctp_gpt* h, const ctp_gpt_weights* w) {
+    CTP_REQUIRE(h && w, "bind: null argument");
+    CTP_REQUIRE(w->wqkv && w->wo && w->wgu && w->wdown && w->ln1 && w->ln2 && w->norm_f && w->emb_code && w->head_code,
+                "bind: missing weight pointer");
+    const ctp_gpt_cfg& c = h->cfg;
+    const long long H = c.hidden, I = c.inter;
+    h->lmaps.resize(c.n_layers);
+    int st;
+    for (int l = 0; l < c.n_layers; ++l) {
+        LayerMaps& m = h->lmaps[l];
+        const __half* wqkv = (const __half*)w->wqkv + (size_t)l * 3 * H * H;
+        const __half* wo = (const __half*)w->wo + (size_t)l * H * H;
+        const __half* wgu = (const __half*)w->wgu + (size_t)l * 2 * I * H;
+        const __half* wd = (const __half*)w->wdown + (size_t)l * H * I;
+        if ((st = make_tmap_kmajor(&m.wqkv, wqkv, 3 * H, H, H, GEMM_BM))) return (ctp_status)st;
+        if ((st = make_tmap_kmajor(&m.wo, wo, H, H, H, GEMM_BM))) return (ctp_status)st;
+        if ((st = make_tmap_kmajor(&m.wgu, wgu, 2 * I, H, H, GEMM_BM))) return (ctp_status)st;
+        if ((st = make_tmap_kmajor(&m.wdown, wd, H, I, I, GEMM_BM))) return (ctp_status)st;
+    }
+    if ((st = make_tmap_kmajor(&h->head_map, w->head_code, (long long)c.num_vq * c.num_audio, H, H, GEMM_BM))) return (ctp_status)st;
+    h->w = *w;
+    h->bound = true;
+    // weights are baked into captured graphs as tensor maps
+    for (auto& kvp : h->graphs) cudaGraphExecDestroy(kvp.second);
+    h->graphs.clear();
+    return CTP_OK;
+}
+
+extern "C" ctp_status ctp_gpt_embed_prompt(ctp_gpt* h, int32_t B, int32_t L0, const int32_t* ids, const uint8_t* text_mask,
+                                           float* emb_out, ctp_stream stream) {
+    CTP_REQUIRE(h && h->bound, "embed_prompt: weights not bound");
+    CTP_REQUIRE(h->w.emb_text, "embed_prompt: emb_text not bound");
+    CTP_REQUIRE(B >= 1 && L0 >= 1 && ids && text_mask && emb_out, "embed_prompt: bad argument");
+    k_embed_prompt<<<B * L0, 256, 0, (cudaStream_t)stream>>>(ids, text_mask, (const __half*)h->w.emb_text,
+                                                             (const __half*)h->w.emb_code, emb_out, h->cfg.hidden,
+                                                             h->cfg.num_vq, h->cfg.num_audio);
+    CTP_CUDA_OK(cudaGetLastError());
+    return CTP_OK;
+}
+
+// ---- shared launch helpers ------------------------------------------------------------------------------
+static GemmEpilogue epi_swap_atomic(float* out, long long ldo, int T, int F) {
+    GemmEpilogue e{};
+    e.out = out; e.ldo = ldo; e.out_f16 = 0; e.atomic = 1; e.swap = 1; e.T = T; e.F = F;
+    return e;
+}
+
+static int split_for(int k_blocks, int m_tiles, int target_ctas = 148) {
+    int s = target_ctas / m_tiles;
+    if (s < 1) s = 1;
+    if (s > k_blocks) s = k_blocks;
+    return s;
+}
+
+#define LAUNCH_OK() do { cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { ctp_set_error("%s:%d launch: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); return CTP_ERR_CUDA; } } while (0)
+
+// heads: logits[b][q*A + a] = hidden_n[b] . head_code[q*A + a]   (gpt.py:424-439; weight_norm folded at bind)
+static int launch_heads(ctp_gpt* h, int B, cudaStream_t s) {
+    const ctp_gpt_cfg& c = h->cfg;
+    const int F = c.num_vq * c.num_audio;
+    const int bn = B <= 32 ? 32 : 64;
+    const ActMaps& am = bn == 32 ? h->act32 : h->act64;
+    const int m_tiles = (F + GEMM_BM - 1) / GEMM_BM;
+    GemmEpilogue e = epi_swap_atomic(h->logits, F, B, F);
+    return gemm_launch_maps(h->head_map, am.xn, F, B, c.hidden, bn, split_for(c.hidden / 64, m_tiles), e, s);
+}
+
+// One decode trunk step for B sequences (ids_ext == nullptr -> codes of the previous sample step).
+static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, cudaStream_t s) {
+    const ctp_gpt_cfg& c = h->cfg;
+    const int H = c.hidden, I = c.inter;
+    const int bn = B <= 32 ? 32 : 64;
+    const ActMaps& am = bn == 32 ? h->act32 : h->act64;
+    int st;
+    for (int l = 0; l < c.n_layers; ++l) {
+        NormArgs na{};
+        na.x = h->x; na.w = h->w.ln1 + (size_t)l * H; na.xn = h->xn; na.H = H; na.eps = c.rms_eps;
+        na.zero_buf = h->acc_qkv; na.zero_n = 3 * H;
+        if (l == 0) { na.st = h->st; na.ids_ext = ids_ext; na.emb_code = (const __half*)h->w.emb_code; na.num_vq = c.num_vq; na.num_audio = c.num_audio; }
+        k_rmsnorm<<<B, 256, 0, s>>>(na);
+        LAUNCH_OK();
+        {   // q,k,v projections as one GEMM (llama.py:619-621), weights are the M operand
+            GemmEpilogue e = epi_swap_atomic(h->acc_qkv, 3 * H, B, 3 * H);
+            if ((st = gemm_launch_maps(h->lmaps[l].wqkv, am.xn, 3 * H, B, H, bn, split_for(H / 64, 3 * H / GEMM_BM), e, s))) return st;
+        }
+        AttnDecArgs aa{};
+        aa.qkv = h->acc_qkv; aa.kcache = h->kplane(l); aa.vcache = h->vplane(l); aa.out = h->attn; aa.part = h->attn_part;
+        aa.counters = h->attn_cnt; aa.pad_len = h->pad_len; aa.st = h->st; aa.inv_freq = h->inv_freq;
+        aa.H = H; aa.nH = c.n_heads; aa.max_seq = c.max_seq;
+        k_attn_decode<<<dim3(c.n_heads, B, nsplit), 128, 0, s>>>(aa);
+        LAUNCH_OK();
+        {   // o_proj accumulated straight into the residual stream (llama.py:663-666,737)
+            GemmEpilogue e = epi_swap_atomic(h->x, H, B, H);
+            if ((st = gemm_launch_maps(h->lmaps[l].wo, am.attn, H, B, H, bn, split_for(H / 64, (H + GEMM_BM - 1) / GEMM_BM), e, s))) return st;
+        }
+        NormArgs nb{};
+        nb.x = h->x; nb.w = h->w.ln2 + (size_t)l * H; nb.xn = h->xn; nb.H = H; nb.eps = c.rms_eps;
+        nb.zero_buf = h->acc_gu; nb.zero_n = 2 * I;
+        k_rmsnorm<<<B, 256, 0, s>>>(nb);
+        LAUNCH_OK();
+        {   // gate_proj | up_proj (llama.py:214)
+            GemmEpilogue e = epi_swap_atomic(h->acc_gu, 2 * I, B, 2 * I);
+            if ((st = gemm_launch_maps(h->lmaps[l].wgu, am.xn, 2 * I, B, H, bn, split_for(H / 64, 2 * I / GEMM_BM), e, s))) return st;
+        }
+        {
+            const long long total = (long long)B * I;
+            k_silu_mul<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(h->acc_gu, h->hmid, I, total);
+            LAUNCH_OK();
+        }
+        {   // down_proj accumulated into the residual stream (llama.py:214,745)
+            GemmEpilogue e = epi_swap_atomic(h->x, H, B, H);
+            if ((st = gemm_launch_maps(h->lmaps[l].wdown, am.hmid, H, B, I, bn, split_for(I / 64, (H + GEMM_BM - 1) / GEMM_BM), e, s))) return st;
+        }
+    }
+    // final norm (llama.py:1002) -> hidden state of this step (gpt.py:422-423) + operand of the heads
+    NormArgs nf{};
+    nf.x = h->x; nf.w = h->w.norm_f; nf.xn = h->xn; nf.out_f32 = h->hidden; nf.H = H; nf.eps = c.rms_eps;
+    nf.zero_buf = h->logits; nf.zero_n = c.num_vq * c.num_audio; nf.st = h->st; nf.write_hid = 1;
+    k_rmsnorm<<<B, 256, 0, s>>>(nf);
+    LAUNCH_OK();
+    if ((st = launch_heads(h, B, s))) return st;
+    k_advance_len<<<1, 1, 0, s>>>(h->st);
+    LAUNCH_OK();
+    return CTP_OK;
+}
+
+static int launch_sampler(ctp_gpt* h, int B, cudaStream_t s) {
+    const ctp_gpt_cfg& c = h->cfg;
+    SampleArgs sa{};
+    sa.logits = h->logits; sa.vocab = c.num_audio; sa.num_vq = c.num_vq; sa.rows = B * c.num_vq; sa.st = h->st;
+    const size_t smem = sizeof(float) * c.num_vq * ((c.num_audio + 31) & ~31);
+    k_sample<<<B, 32 * c.num_vq, smem, s>>>(sa);
+    LAUNCH_OK();
+    return CTP_OK;
+}
+
+static int nsplit_for(const ctp_gpt* h, int B, int ctx_len) {
+    // keep >= ~2 CTAs per SM worth of independent KV streams; one split per 512 slots beyond that
+    int ns = 1;
+    const int base = B * h->cfg.n_heads;
+    while (ns < h->max_splits && (base * ns < 296 || ctx_len / ns > 1024)) ns *= 2;
+    if (ctx_len < ns * 8) ns = 1;
+    return ns;
+}
+
+extern "C" ctp_status ctp_gpt_prefill(ctp_gpt* h, int32_t B, int32_t L0, const float* emb, const int32_t* pad_len_host,
+                                      const ctp_gen_buffers* bufs, int32_t infer_text, ctp_stream stream) {
+    CTP_REQUIRE(h && h->bound, "prefill: weights not bound");
+    CTP_REQUIRE(!infer_text, "prefill: infer_text (refine-text pass) is not built yet (SURVEY.md §8f row f1)");
+    const ctp_gpt_cfg& c = h->cfg;
+    CTP_REQUIRE(B >= 1 && B <= c.max_batch, "prefill: batch %d outside [1,%d]", B, c.max_batch);
+    CTP_REQUIRE(L0 >= 1 && L0 < c.max_seq, "prefill: prompt length %d does not fit max_seq %d", L0, c.max_seq);
+    CTP_REQUIRE(emb && bufs && bufs->ids && bufs->end_idx && bufs->finish && bufs->max_new >= 1, "prefill: bad buffers");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int H = c.hidden, I = c.inter;
+    const long long T = (long long)B * L0;
+    int st = ensure_workspace(h, std::max<long long>(T, c.max_batch));
+    if (st) return (ctp_status)st;
+    std::vector<int> pads(B, 0);
+    if (pad_len_host) {
+        for (int b = 0; b < B; ++b) {
+            CTP_REQUIRE(pad_len_host[b] >= 0 && pad_len_host[b] < L0, "prefill: pad_len[%d]=%d invalid", b, pad_len_host[b]);
+            pads[b] = pad_len_host[b];
+        }
+    }
+    CTP_CUDA_OK(cudaMemcpyAsync(h->pad_len, pads.data(), sizeof(int) * B, cudaMemcpyHostToDevice, s));
+    // generation state
+    GenState gs{};
+    gs.cur_len = L0; gs.step = 0; gs.B = B; gs.max_new = bufs->max_new; gs.ids_buf = bufs->ids; gs.hid_buf = bufs->hiddens;
+    gs.end_idx = bufs->end_idx; gs.finish = bufs->finish; gs.u_base = nullptr; gs.all_done = 0; gs.ticket = 0;
+    CTP_CUDA_OK(cudaMemcpyAsync(h->st, &gs, sizeof(gs), cudaMemcpyHostToDevice, s));
+    CTP_CUDA_OK(cudaMemsetAsync(bufs->end_idx, 0, sizeof(int) * B, s));
+    CTP_CUDA_OK(cudaMemsetAsync(bufs->finish, 0, B, s));
+    CTP_CUDA_OK(cudaStreamSynchronize(s));  // pads / gs are stack/heap temporaries
+    CTP_CUDA_OK(cudaMemcpyAsync(h->x, emb, sizeof(float) * T * H, cudaMemcpyDeviceToDevice, s));
+
+    for (int l = 0; l < c.n_layers; ++l) {
+        NormArgs na{};
+        na.x = h->x; na.w = h->w.ln1 + (size_t)l * H; na.xn = h->xn; na.H = H; na.eps = c.rms_eps;
+        k_rmsnorm<<<(unsigned)T, 256, 0, s>>>(na);
+        LAUNCH_OK();
+        {   // tokens are the M operand here (T = B*L0 rows): compute-bound, 128x256 tiles
+            GemmLaunch g{};
+            g.A = h->xn; g.a_rows = T; g.lda = H;
+            g.B = (const __half*)h->w.wqkv + (size_t)l * 3 * H * H; g.b_rows = 3 * H; g.ldb = H;
+            g.K = H; g.block_n = 256; g.split_k = 1;
+            g.epi.out = h->acc_qkv; g.epi.ldo = 3 * H; g.epi.T = (int)T; g.epi.F = 3 * H;
+            if ((st = gemm_launch(g, s))) return (ctp_status)st;
+        }
+        k_rope_prefill<<<dim3(L0, B), c.n_heads * 32, 0, s>>>(h->acc_qkv, h->kplane(l), h->vplane(l), h->pad_len, h->inv_freq, H,
+                                                               c.n_heads, L0, c.max_seq);
+        LAUNCH_OK();
+        k_attn_prefill<<<dim3(c.n_heads, B, (L0 + 7) / 8), 256, 0, s>>>(h->acc_qkv, h->kplane(l), h->vplane(l), h->attn, h->pad_len,
+                                                                         H, c.n_heads, L0, c.max_seq);
+        LAUNCH_OK();
+        {
+            GemmLaunch g{};
+            g.A = h->attn; g.a_rows = T; g.lda = H;
+            g.B = (const __half*)h->w.wo + (size_t)l * H * H; g.b_rows = H; g.ldb = H;
+            g.K = H; g.block_n = 256; g.split_k = 1;
+            g.epi.out = h->x; g.epi.ldo = H; g.epi.residual = h->x; g.epi.ldr = H; g.epi.T = (int)T; g.epi.F = H;
+            if ((st = gemm_launch(g, s))) return (ctp_status)st;
+        }
+        NormArgs nb{};
+        nb.x = h->x; nb.w = h->w.ln2 + (size_t)l * H; nb.xn = h->xn; nb.H = H; nb.eps = c.rms_eps;
+        k_rmsnorm<<<(unsigned)T, 256, 0, s>>>(nb);
+        LAUNCH_OK();
+        {
+            GemmLaunch g{};
+            g.A = h->xn; g.a_rows = T; g.lda = H;
+            g.B = (const __half*)h->w.wgu + (size_t)l * 2 * I * H; g.b_rows = 2 * I; g.ldb = H;
+            g.K = H; g.block_n = 256; g.split_k = 1;
+            g.epi.out = h->acc_gu; g.epi.ldo = 2 * I; g.epi.T = (int)T; g.epi.F = 2 * I;
+            if ((st = gemm_launch(g, s))) return (ctp_status)st;
+        }
+        {
+            const long long total = T * I;
+            k_silu_mul<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(h->acc_gu, h->hmid, I, total);
+            LAUNCH_OK();
+        }
+        {
+            GemmLaunch g{};
+            g.A = h->hmid; g.a_rows = T; g.lda = I;
+            g.B = (const __half*)h->w.wdown + (size_t)l * H * I; g.b_rows = H; g.ldb = I;
+            g.K = I; g.block_n = 256; g.split_k = 1;
+            g.epi.out = h->x; g.epi.ldo = H; g.epi.residual = h->x; g.epi.ldr = H; g.epi.T = (int)T; g.epi.F = H;
+            if ((st = gemm_launch(g, s))) return (ctp_status)st;
+        }
+    }
+    // last position of every sequence -> final norm -> heads; the decode residual stream continues in x[0..B)
+    k_gather_last<<<B, 256, 0, s>>>(h->x, h->x_last, L0, H);
+    LAUNCH_OK();
+    CTP_CUDA_OK(cudaMemcpyAsync(h->x, h->x_last, sizeof(float) * B * H, cudaMemcpyDeviceToDevice, s));
+    NormArgs nf{};
+    nf.x = h->x; nf.w = h->w.norm_f; nf.xn = h->xn; nf.out_f32 = h->hidden; nf.H = H; nf.eps = c.rms_eps;
+    nf.zero_buf = h->logits; nf.zero_n = c.num_vq * c.num_audio; nf.st = h->st; nf.write_hid = 1;
+    k_rmsnorm<<<B, 256, 0, s>>>(nf);
+    LAUNCH_OK();
+    if ((st = launch_heads(h, B, s))) return (ctp_status)st;
+    h->B = B; h->cur_len = L0; h->step = 0; h->max_new = bufs->max_new; h->have_bufs = true;
+    return CTP_OK;
+}
+
+extern "C" ctp_status ctp_gpt_decode_step(ctp_gpt* h, const int32_t* ids, ctp_stream stream) {
+    CTP_REQUIRE(h && h->bound && h->have_bufs, "decode_step: call prefill first");
+    CTP_REQUIRE(h->cur_len + 1 <= h->cfg.max_seq, "decode_step: KV cache full (%d slots)", h->cfg.max_seq);
+    CTP_REQUIRE(ids != nullptr || h->step >= 1, "decode_step: no sampled codes yet and no ids given");
+    int st = run_decode_trunk(h, h->B, nsplit_for(h, h->B, h->cur_len + 1), ids, (cudaStream_t)stream);
+    if (st) return (ctp_status)st;
+    h->cur_len += 1;
+    return CTP_OK;
+}
+
+static int check_sample_cfg(const ctp_gpt_cfg* c, const ctp_sample_cfg* cfg, int num_vq) {
+    CTP_REQUIRE(cfg, "sample: null cfg");
+    CTP_REQUIRE(cfg->top_k >= 1 && cfg->top_k <= SAMPLE_MAX_K, "sample: top_k must be in [1,%d] (got %d)", SAMPLE_MAX_K, cfg->top_k);
+    CTP_REQUIRE(cfg->min_keep >= 1 && cfg->min_keep <= SAMPLE_MAX_K, "sample: min_keep out of range");
+    CTP_REQUIRE(cfg->rep_window >= 0 && cfg->rep_window <= 32, "sample: rep_window must be <= 32");
+    CTP_REQUIRE(cfg->rep_penalty > 0.f, "sample: rep_penalty must be > 0");
+    for (int q = 0; q < num_vq; ++q) CTP_REQUIRE(cfg->temperature[q] > 0.f, "sample: temperature[%d] must be > 0", q);
+    (void)c;
+    return CTP_OK;
+}
+
+static int upload_sample_state(ctp_gpt* h, const ctp_sample_cfg* cfg, const float* u, cudaStream_t s) {
+    // cfg and u_base live inside the device GenState; update just those fields
+    CTP_CUDA_OK(cudaMemcpyAsync(reinterpret_cast<char*>(h->st) + offsetof(GenState, cfg), cfg, sizeof(*cfg), cudaMemcpyHostToDevice, s));
+    CTP_CUDA_OK(cudaMemcpyAsync(reinterpret_cast<char*>(h->st) + offsetof(GenState, u_base), &u, sizeof(u), cudaMemcpyHostToDevice, s));
+    CTP_CUDA_OK(cudaStreamSynchronize(s));
+    return CTP_OK;
+}
+
+extern "C" ctp_status ctp_gpt_sample_step(ctp_gpt* h, const ctp_sample_cfg* cfg, const float* u, ctp_stream stream) {
+    CTP_REQUIRE(h && h->bound && h->have_bufs, "sample_step: call prefill first");
+    CTP_REQUIRE(h->step < h->max_new, "sample_step: generation buffers full (%d steps)", h->max_new);
+    int st = check_sample_cfg(&h->cfg, cfg, h->cfg.num_vq);
+    if (st) return (ctp_status)st;
+    cudaStream_t s = (cudaStream_t)stream;
+    // single-step mode: u is [B*num_vq] for this step -> bias the base so that base + step*rows == u
+    const float* ubase = u ? u - (long long)h->step * h->B * h->cfg.num_vq : nullptr;
+    if ((st = upload_sample_state(h, cfg, ubase, s))) return (ctp_status)st;
+    if ((st = launch_sampler(h, h->B, s))) return (ctp_status)st;
+    h->step += 1;
+    return CTP_OK;
+}
+
+static int get_graph(ctp_gpt* h, int B, int nsplit, cudaGraphExec_t* out) {
+    GraphKey key{B, nsplit};
+    auto it = h->graphs.find(key);
+    if (it != h->graphs.end()) { *out = it->second; return CTP_OK; }
+    cudaGraph_t graph = nullptr;
+    CTP_CUDA_OK(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+    int st = run_decode_trunk(h, B, nsplit, nullptr, h->cap_stream);
+    if (!st) st = launch_sampler(h, B, h->cap_stream);
+    cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
+    if (st) { if (graph) cudaGraphDestroy(graph); return st; }
+    if (e != cudaSuccess) { ctp_set_error("graph capture failed: %s", cudaGetErrorString(e)); return CTP_ERR_CUDA; }
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { ctp_set_error("graph instantiate failed: %s", cudaGetErrorString(e)); return CTP_ERR_CUDA; }
+    h->graphs[key] = exec;
+    *out = exec;
+    return CTP_OK;
+}
+
+extern "C" ctp_status ctp_gpt_generate(ctp_gpt* h, const ctp_sample_cfg* cfg, int32_t max_steps, const float* u,
+                                       int32_t check_every, int32_t* steps_done, ctp_stream stream) {
+    CTP_REQUIRE(h && h->bound && h->have_bufs, "generate: call prefill first");
+    CTP_REQUIRE(h->step >= 1, "generate: sample the first step (ctp_gpt_sample_step) before the loop");
+    int st = check_sample_cfg(&h->cfg, cfg, h->cfg.num_vq);
+    if (st) return (ctp_status)st;
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((st = upload_sample_state(h, cfg, u, s))) return (ctp_status)st;
+    if (check_every < 1) check_every = 16;
+    int done = 0;
+    int iters = max_steps;
+    iters = std::min(iters, h->max_new - h->step);
+    iters = std::min(iters, h->cfg.max_seq - h->cur_len);
+    cudaEvent_t ev = nullptr;
+    CTP_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    bool pending = false;
+    h->st_pin->all_done = 0;
+    for (int it = 0; it < iters; ++it) {
+        cudaGraphExec_t g;
+        if ((st = get_graph(h, h->B, nsplit_for(h, h->B, h->cur_len + 1), &g))) { cudaEventDestroy(ev); return (ctp_status)st; }
+        cudaError_t e = cudaGraphLaunch(g, s);
+        if (e != cudaSuccess) { ctp_set_error("graph launch: %s", cudaGetErrorString(e)); cudaEventDestroy(ev); return CTP_ERR_CUDA; }
+        h->cur_len += 1; h->step += 1; done += 1;
+        if ((it + 1) % check_every == 0 && it + 1 < iters) {
+            // lagged poll: look at the flag copied after the PREVIOUS chunk while this chunk is already queued
+            if (pending) {
+                cudaEventSynchronize(ev);
+                if (h->st_pin->all_done) break;
+            }
+            cudaMemcpyAsync(&h->st_pin->all_done, reinterpret_cast<char*>(h->st) + offsetof(GenState, all_done), sizeof(int),
+                            cudaMemcpyDeviceToHost, s);
+            cudaEventRecord(ev, s);
+            pending = true;
+        }
+    }
+    cudaEventDestroy(ev);
+    CTP_CUDA_OK(cudaGetLastError());
+    if (steps_done) *steps_done = done;
+    return CTP_OK;
+}
+
+extern "C" const float* ctp_gpt_logits(ctp_gpt* h) { return h ? h->logits : nullptr; }
+extern "C" const float* ctp_gpt_hidden(ctp_gpt* h) { return h ? h->hidden : nullptr; }
+extern "C" ctp_status ctp_gpt_copy_outputs(ctp_gpt* h, float* logits_out, float* hidden_out, ctp_stream stream) {
+    CTP_REQUIRE(h && h->have_bufs, "copy_outputs: call prefill first");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t nl = (size_t)h->B * h->cfg.num_vq * h->cfg.num_audio;
+    if (logits_out) CTP_CUDA_OK(cudaMemcpyAsync(logits_out, h->logits, nl * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (hidden_out) CTP_CUDA_OK(cudaMemcpyAsync(hidden_out, h->hidden, (size_t)h->B * h->cfg.hidden * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return CTP_OK;
+}
+extern "C" ctp_status ctp_gpt_state(ctp_gpt* h, int32_t* cur_len, int32_t* step) {
+    CTP_REQUIRE(h, "state: null handle");
+    if (cur_len) *cur_len = h->cur_len;
+    if (step) *step = h->step;
+    return CTP_OK;
+}
+extern "C" const void* ctp_gpt_kv_plane(ctp_gpt* h, int32_t layer, int32_t which) {
+    if (!h || layer < 0 || layer >= h->cfg.n_layers) return nullptr;
+    return which ? (const void*)h->vplane(layer) : (const void*)h->kplane(layer);
+}
+
+extern "C" ctp_status ctp_sample(int32_t rows, int32_t vocab, int32_t num_vq, const float* logits, const int32_t* history,
+                                 int32_t hist_len, int32_t hist_stride, const ctp_sample_cfg* cfg, int32_t step, const float* u,
+                                 int32_t* next_ids, float* probs_out, ctp_stream stream) {
+    CTP_REQUIRE(rows >= 1 && vocab >= 1 && num_vq >= 1 && num_vq <= MAX_VQ && rows % num_vq == 0, "sample: bad shape");
+    CTP_REQUIRE(logits && (next_ids || probs_out), "sample: null pointer");
+    CTP_REQUIRE(hist_len == 0 || history, "sample: history missing");
+    int st = check_sample_cfg(nullptr, cfg, num_vq);
+    if (st) return (ctp_status)st;
+    SampleArgs sa{};
+    sa.logits = logits; sa.vocab = vocab; sa.num_vq = num_vq; sa.rows = rows; sa.hist = history; sa.hist_stride = hist_stride;
+    sa.hist_len = hist_len; sa.u = u; sa.step = step; sa.cfg = *cfg; sa.next_ids = next_ids; sa.probs_out = probs_out; sa.st = nullptr;
+    const size_t smem = sizeof(float) * num_vq * ((vocab + 31) & ~31);
+    CTP_REQUIRE(smem <= 48 * 1024, "sample: vocab %d too large for the warp sampler", vocab);
+    k_sample<<<rows / num_vq, 32 * num_vq, smem, (cudaStream_t)stream>>>(sa);
+    CTP_CUDA_OK(cudaGetLastError());
+    return CTP_OK;
+}

@@ -1,0 +1,596 @@
+// Device kernels of the GPT decode / prefill path other than the GEMMs (sm_100a).
+// Reference semantics cited per kernel (paths relative to the ChatTTSPlus checkout).
+#pragma once
+#include "ctp_common.cuh"
+#include "../../include/ctp.h"
+
+namespace ctp {
+
+constexpr int HEAD_DIM = 64;
+constexpr int MAX_VQ = 8;
+
+// Generation state, resident in device memory so that a captured step graph can be replayed unchanged:
+// every kernel reads the current cache length / step / buffer pointers from here.
+struct GenState {
+    int cur_len;     // KV slots filled (prompt + decoded); the next token is written at slot cur_len
+    int step;        // number of sample steps taken so far
+    int B;
+    int max_new;
+    int* ids_buf;            // [B][max_new][num_vq]
+    float* hid_buf;          // [B][max_new][H] or null
+    int* end_idx;            // [B]
+    unsigned char* finish;   // [B]
+    const float* u_base;     // [max_new][B*num_vq] or null
+    int all_done;            // set by the sampler when every sequence has finished
+    int ticket;              // scratch counter
+    ctp_sample_cfg cfg;
+};
+
+struct GptDims {
+    int L, H, nH, I, num_vq, num_audio, num_text, max_batch, max_seq;
+    float eps;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Prompt embedding  (GPT.forward, gpt.py:125-149)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_embed_prompt(const int* __restrict__ ids, const unsigned char* __restrict__ text_mask,
+                               const __half* __restrict__ emb_text, const __half* __restrict__ emb_code, float* __restrict__ out,
+                               int H, int num_vq, int num_audio) {
+    const int tok = blockIdx.x;
+    const int* id = ids + (long long)tok * num_vq;
+    const bool is_text = text_mask[tok] != 0;
+    for (int c = threadIdx.x; c < H; c += blockDim.x) {
+        float v;
+        if (is_text) {
+            v = __half2float(emb_text[(long long)id[0] * H + c]);
+        } else {
+            v = 0.f;
+            for (int q = 0; q < num_vq; ++q) v += __half2float(emb_code[((long long)q * num_audio + id[q]) * H + c]);
+        }
+        out[(long long)tok * H + c] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// RMSNorm (llama.py:82-87): xn = w * (x * rsqrt(mean(x^2) + eps)), fp32 math, fp16 operand for the next GEMM.
+// Optional front end for the decode step: x = sum_q emb_code[q][ids[b][q]]  (gpt.py:398-407).
+// Optional back end: also emit the normalised row in fp32 (final norm -> hidden state, gpt.py:422-423) and
+// zero a scratch row (the fp32 split-K accumulator the following GEMM adds into).
+// ---------------------------------------------------------------------------------------------------------
+struct NormArgs {
+    float* x;                 // [rows][H] residual stream (read; written when embedding)
+    const float* w;           // [H]
+    __half* xn;               // [rows][H]
+    float* out_f32;           // [rows][H] or null
+    float* zero_buf;          // [rows][zero_n] or null
+    int zero_n;
+    int H;
+    float eps;
+    // embedding front end (decode only)
+    const GenState* st;       // null -> no embedding
+    const int* ids_ext;       // [B][num_vq] or null (then ids_buf[b][step-1])
+    const __half* emb_code;
+    int num_vq, num_audio;
+    int write_hid;            // 1: also copy out_f32 row into st->hid_buf[b][step]
+};
+
+__global__ void __launch_bounds__(256) k_rmsnorm(NormArgs a) {
+    const int row = blockIdx.x;
+    __shared__ float red[8];
+    __shared__ int sid[MAX_VQ];
+    float* x = a.x + (long long)row * a.H;
+    const bool embed = (a.st != nullptr && a.emb_code != nullptr);
+    if (embed && threadIdx.x < a.num_vq) {
+        int id;
+        if (a.ids_ext) id = a.ids_ext[row * a.num_vq + threadIdx.x];
+        else id = a.st->ids_buf[((long long)row * a.st->max_new + (a.st->step - 1)) * a.num_vq + threadIdx.x];
+        sid[threadIdx.x] = id;
+    }
+    if (embed) __syncthreads();
+    float ss = 0.f;
+    float vals[4];  // H <= 1024 with 256 threads
+    int n = 0;
+    for (int c = threadIdx.x; c < a.H; c += 256, ++n) {
+        float v;
+        if (embed) {
+            v = 0.f;
+            for (int q = 0; q < a.num_vq; ++q) v += __half2float(a.emb_code[((long long)q * a.num_audio + sid[q]) * a.H + c]);
+            x[c] = v;
+        } else {
+            v = x[c];
+        }
+        vals[n] = v;
+        ss += v * v;
+    }
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += red[i];
+    const float rstd = rsqrtf(tot / (float)a.H + a.eps);
+    n = 0;
+    for (int c = threadIdx.x; c < a.H; c += 256, ++n) {
+        const float y = a.w[c] * (vals[n] * rstd);
+        a.xn[(long long)row * a.H + c] = __float2half_rn(y);
+        if (a.out_f32) a.out_f32[(long long)row * a.H + c] = y;
+        if (a.write_hid && a.st->hid_buf && a.st->step < a.st->max_new)
+            a.st->hid_buf[((long long)row * a.st->max_new + a.st->step) * a.H + c] = y;
+    }
+    if (a.zero_buf) {
+        float* z = a.zero_buf + (long long)row * a.zero_n;
+        for (int c = threadIdx.x; c < a.zero_n; c += 256) z[c] = 0.f;
+    }
+}
+
+// h = silu(gate) * up   (llama.py:214), gate/up read from the fp32 accumulator [rows][2I]
+__global__ void k_silu_mul(const float* __restrict__ gu, __half* __restrict__ out, int I, long long total) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long r = i / I;
+    const int c = (int)(i % I);
+    const float g = gu[r * 2 * I + c];
+    const float u = gu[r * 2 * I + I + c];
+    out[i] = __float2half_rn(silu(g) * u);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Decode attention: RoPE (llama.py:106-119,151-182) on the new q/k, KV append (replaces the torch.cat of
+// DynamicCache.update, llama.py:630-633, with an O(1) in-place write), softmax(q K^T / 8) V over the cached slots
+// of this sequence (SDPA q_len = 1, llama.py:653-661).  Left padding: slots [0, pad_len[b]) are masked.
+// grid (nH, B, nsplit), 128 threads; split partials are merged by the last CTA to arrive for each (b, h).
+// ---------------------------------------------------------------------------------------------------------
+struct AttnDecArgs {
+    const float* qkv;       // [B][3H] fp32 accumulators of the QKV GEMM
+    __half* kcache;         // this layer: [maxB][nH][maxS][64]
+    __half* vcache;
+    __half* out;            // [B][H] fp16
+    float* part;            // [B][nH][nsplit][66]
+    int* counters;          // [B][nH]
+    const int* pad_len;     // [B]
+    const GenState* st;
+    const float* inv_freq;  // [32]
+    int H, nH, max_seq;
+};
+
+__global__ void __launch_bounds__(128) k_attn_decode(AttnDecArgs a) {
+    const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z, nsplit = gridDim.z;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cur = a.st->cur_len;  // new token's slot
+    const int pad = a.pad_len[b];
+    __shared__ float sq[HEAD_DIM];
+    __shared__ __align__(16) __half sk_new[HEAD_DIM];
+    __shared__ __align__(16) __half sv_new[HEAD_DIM];
+    __shared__ float s_m[16], s_l[16];
+    __shared__ float s_o[16][HEAD_DIM + 1];
+    __shared__ int s_last;
+
+    const float* qp = a.qkv + (long long)b * 3 * a.H + h * HEAD_DIM;
+    if (tid < 32) {
+        const float pos = (float)(cur - pad);
+        const float ang = pos * a.inv_freq[tid];
+        float sn, cs;
+        sincosf(ang, &sn, &cs);
+        const float q1 = qp[tid], q2 = qp[tid + 32];
+        const float k1 = qp[a.H + tid], k2 = qp[a.H + tid + 32];
+        sq[tid] = (q1 * cs - q2 * sn) * 0.125f;  // 1/sqrt(64) folded into q
+        sq[tid + 32] = (q2 * cs + q1 * sn) * 0.125f;
+        sk_new[tid] = __float2half_rn(k1 * cs - k2 * sn);
+        sk_new[tid + 32] = __float2half_rn(k2 * cs + k1 * sn);
+    } else if (tid < 96) {
+        const int d = tid - 32;
+        sv_new[d] = __float2half_rn(qp[2 * a.H + d]);
+    }
+    __syncthreads();
+    const long long head_off = (((long long)b * a.nH + h) * a.max_seq) * HEAD_DIM;
+    __half* kc = a.kcache + head_off;
+    __half* vc = a.vcache + head_off;
+    if (sp == nsplit - 1 && tid < 16) {  // append (16 threads x 16 B = 64 halfs for K and for V)
+        reinterpret_cast<uint2*>(kc + (long long)cur * HEAD_DIM)[tid] = reinterpret_cast<const uint2*>(sk_new)[tid];
+        reinterpret_cast<uint2*>(vc + (long long)cur * HEAD_DIM)[tid] = reinterpret_cast<const uint2*>(sv_new)[tid];
+    }
+    // slots this split covers: [j0, j1) within [pad, cur]  (cur = the new token, taken from shared memory)
+    const int n = cur + 1 - pad;
+    const int j0 = pad + (int)(((long long)n * sp) / nsplit);
+    const int j1 = pad + (int)(((long long)n * (sp + 1)) / nsplit);
+
+    // 16 groups of 8 lanes; lane `sub` owns dims [8*sub, 8*sub+8)
+    const int grp = tid >> 3, sub = tid & 7;
+    float q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = sq[sub * 8 + i];
+    float m = -INFINITY, l = 0.f, o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = 0.f;
+
+    constexpr int UNROLL = 4;
+    // loop bounds are uniform over the CTA; validity is a per-group predicate (shuffles stay convergent)
+    for (int jb = j0; jb < j1; jb += 16 * UNROLL) {
+        uint4 kr[UNROLL], vr[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int j = jb + grp + u * 16;
+            kr[u] = make_uint4(0, 0, 0, 0);
+            vr[u] = make_uint4(0, 0, 0, 0);
+            if (j < j1) {
+                if (j == cur) {
+                    kr[u] = reinterpret_cast<const uint4*>(sk_new)[sub];
+                    vr[u] = reinterpret_cast<const uint4*>(sv_new)[sub];
+                } else {
+                    kr[u] = __ldg(reinterpret_cast<const uint4*>(kc + (long long)j * HEAD_DIM) + sub);
+                    vr[u] = __ldg(reinterpret_cast<const uint4*>(vc + (long long)j * HEAD_DIM) + sub);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int j = jb + grp + u * 16;
+            const bool valid = j < j1;
+            const __half2* k2 = reinterpret_cast<const __half2*>(&kr[u]);
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(k2[i]);
+                s += q[2 * i] * f.x + q[2 * i + 1] * f.y;
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            if (valid) {
+                const float mn = fmaxf(m, s);
+                const float corr = __expf(m - mn);
+                const float p = __expf(s - mn);
+                l = l * corr + p;
+                const __half2* v2 = reinterpret_cast<const __half2*>(&vr[u]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 f = __half22float2(v2[i]);
+                    o[2 * i] = o[2 * i] * corr + p * f.x;
+                    o[2 * i + 1] = o[2 * i + 1] * corr + p * f.y;
+                }
+                m = mn;
+            }
+        }
+    }
+    // merge the 16 groups
+    if (sub == 0) { s_m[grp] = m; s_l[grp] = l; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_o[grp][sub * 8 + i] = o[i];
+    __syncthreads();
+    float M = -INFINITY, Lsum = 0.f, O = 0.f;
+    if (tid < HEAD_DIM) {
+#pragma unroll
+        for (int g = 0; g < 16; ++g) M = fmaxf(M, s_m[g]);
+#pragma unroll
+        for (int g = 0; g < 16; ++g) {
+            const float w = (s_m[g] == -INFINITY) ? 0.f : __expf(s_m[g] - M);
+            Lsum += s_l[g] * w;
+            O += s_o[g][tid] * w;
+        }
+    }
+    if (nsplit == 1) {
+        if (tid < HEAD_DIM) a.out[(long long)b * a.H + h * HEAD_DIM + tid] = __float2half_rn(O / Lsum);
+        return;
+    }
+    float* pp = a.part + (((long long)b * a.nH + h) * nsplit + sp) * 66;
+    if (tid < HEAD_DIM) pp[tid] = O;
+    if (tid == 0) { pp[64] = M; pp[65] = Lsum; }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const int t = atomicAdd(&a.counters[b * a.nH + h], 1);
+        s_last = (t == nsplit - 1);
+        if (s_last) a.counters[b * a.nH + h] = 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (tid < HEAD_DIM) {
+        const float* p0 = a.part + (((long long)b * a.nH + h) * nsplit) * 66;
+        float MM = -INFINITY;
+        for (int s = 0; s < nsplit; ++s) MM = fmaxf(MM, p0[s * 66 + 64]);
+        float LL = 0.f, OO = 0.f;
+        for (int s = 0; s < nsplit; ++s) {
+            const float ms = p0[s * 66 + 64];
+            const float w = (ms == -INFINITY) ? 0.f : __expf(ms - MM);
+            LL += p0[s * 66 + 65] * w;
+            OO += p0[s * 66 + tid] * w;
+        }
+        a.out[(long long)b * a.H + h * HEAD_DIM + tid] = __float2half_rn(OO / LL);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Prefill: RoPE + KV write for all prompt tokens, then causal attention with left-padding mask.
+// ---------------------------------------------------------------------------------------------------------
+// grid (L0, B), block = nH * 32 threads: thread (h, i) rotates pair (i, i+32) of head h.
+__global__ void k_rope_prefill(float* __restrict__ qkv, __half* __restrict__ kcache, __half* __restrict__ vcache,
+                               const int* __restrict__ pad_len, const float* __restrict__ inv_freq, int H, int nH, int L0,
+                               int max_seq) {
+    const int j = blockIdx.x, b = blockIdx.y;
+    const int h = threadIdx.x >> 5, i = threadIdx.x & 31;
+    const int pad = pad_len[b];
+    const float pos = (j >= pad) ? (float)(j - pad) : 1.0f;  // gpt.py:238-245: padded slots get position 1
+    float sn, cs;
+    sincosf(pos * inv_freq[i], &sn, &cs);
+    float* row = qkv + ((long long)b * L0 + j) * 3 * H;
+    const float q1 = row[h * 64 + i], q2 = row[h * 64 + i + 32];
+    row[h * 64 + i] = q1 * cs - q2 * sn;
+    row[h * 64 + i + 32] = q2 * cs + q1 * sn;
+    const float k1 = row[H + h * 64 + i], k2 = row[H + h * 64 + i + 32];
+    const long long off = ((((long long)b * nH + h) * max_seq) + j) * HEAD_DIM;
+    kcache[off + i] = __float2half_rn(k1 * cs - k2 * sn);
+    kcache[off + i + 32] = __float2half_rn(k2 * cs + k1 * sn);
+    vcache[off + i] = __float2half_rn(row[2 * H + h * 64 + i]);
+    vcache[off + i + 32] = __float2half_rn(row[2 * H + h * 64 + i + 32]);
+}
+
+// grid (nH, B, ceil(L0/8)), 256 threads = 8 warps, one query row per warp; keys strided over lanes.
+// K/V for the (b,h) pair are read from the cache (fp16, L2-resident for prompt-sized L0).
+__global__ void __launch_bounds__(256) k_attn_prefill(const float* __restrict__ qkv, const __half* __restrict__ kcache,
+                                                       const __half* __restrict__ vcache, __half* __restrict__ out,
+                                                       const int* __restrict__ pad_len, int H, int nH, int L0, int max_seq) {
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.z * 8 + warp;  // query slot
+    __shared__ float sq[8][HEAD_DIM];
+    __shared__ float sp[8][32];
+    const int pad = pad_len[b];
+    if (i < L0) {
+        const float* qr = qkv + ((long long)b * L0 + i) * 3 * H + h * HEAD_DIM;
+        sq[warp][lane] = qr[lane] * 0.125f;
+        sq[warp][lane + 32] = qr[lane + 32] * 0.125f;
+    }
+    __syncwarp();
+    if (i >= L0) return;
+    const long long head_off = (((long long)b * nH + h) * max_seq) * HEAD_DIM;
+    const __half* kc = kcache + head_off;
+    const __half* vc = vcache + head_off;
+    // padded query rows (i < pad) attend to themselves only: their output is never consumed (left padding)
+    const int jlo = (i >= pad) ? pad : i;
+    const int jhi = i;  // inclusive
+    float m = -INFINITY, l = 0.f;
+    float o0 = 0.f, o1 = 0.f;  // this lane owns output dims lane and lane+32
+    for (int jb = jlo; jb <= jhi; jb += 32) {
+        const int j = jb + lane;
+        float s = -INFINITY;
+        if (j <= jhi) {
+            const uint4* kr = reinterpret_cast<const uint4*>(kc + (long long)j * HEAD_DIM);
+            s = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint4 kk = __ldg(kr + c);
+                const __half2* k2 = reinterpret_cast<const __half2*>(&kk);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const float2 f = __half22float2(k2[t]);
+                    s += sq[warp][c * 8 + 2 * t] * f.x + sq[warp][c * 8 + 2 * t + 1] * f.y;
+                }
+            }
+        }
+        const float mb = warp_max(s);
+        const float mn = fmaxf(m, mb);
+        const float corr = __expf(m - mn);
+        const float p = (j <= jhi) ? __expf(s - mn) : 0.f;
+        l = l * corr + warp_sum(p);
+        o0 *= corr;
+        o1 *= corr;
+        sp[warp][lane] = p;
+        __syncwarp();
+        const int cnt = min(32, jhi - jb + 1);
+        for (int t = 0; t < cnt; ++t) {
+            const float pt = sp[warp][t];
+            const __half* vr = vc + (long long)(jb + t) * HEAD_DIM;
+            o0 += pt * __half2float(vr[lane]);
+            o1 += pt * __half2float(vr[lane + 32]);
+        }
+        __syncwarp();
+        m = mn;
+    }
+    __half* orow = out + ((long long)b * L0 + i) * H + h * HEAD_DIM;
+    orow[lane] = __float2half_rn(o0 / l);
+    orow[lane + 32] = __float2half_rn(o1 / l);
+}
+
+// x_last[b] = x[b][L0-1]  (only the last prompt position feeds the heads, gpt.py:442)
+__global__ void k_gather_last(const float* __restrict__ x, float* __restrict__ out, int L0, int H) {
+    const int b = blockIdx.x;
+    for (int c = threadIdx.x; c < H; c += blockDim.x) out[(long long)b * H + c] = x[((long long)b * L0 + L0 - 1) * H + c];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Sampler: one warp per (b, q) logits row.  gpt.py:469-494 + processors.py:18-34 + TopP/TopK warpers.
+//
+// TopP (ascending cumulative prob <= 1-p removed, last min_keep kept) followed by TopK(k) leaves exactly the
+// highest-scoring tokens, in rank order, while the probability mass strictly above a token is < top_p, capped at
+// k tokens and never fewer than min_keep: so the 20 best scores plus the full-row softmax normaliser suffice and no
+// 626-wide sort is needed.  (Exact ties at the k-th score are broken by token id instead of all being kept.)
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SAMPLE_MAX_K = 32;
+
+struct SampleArgs {
+    const float* logits;   // [rows][vocab]
+    int vocab, num_vq, rows;
+    // history for the repetition penalty: row r looks at hist[r_b][t][r_q], t in [hist_len - window, hist_len)
+    const int* hist;       // element (b, t, q) at hist[(b*hist_stride + t)*num_vq + q]
+    int hist_stride;       // tokens per batch row in the history buffer
+    int hist_len;          // valid history length (ignored when st != null: then st->step)
+    const float* u;        // [rows] or null
+    int step;              // (ignored when st != null)
+    ctp_sample_cfg cfg;    // (ignored when st != null: then st->cfg)
+    int* next_ids;         // [rows] or null
+    float* probs_out;      // [rows][vocab] or null
+    GenState* st;          // generation mode: write ids_buf / finish / end_idx
+};
+
+__device__ __forceinline__ uint32_t philox_mix(uint64_t seed, uint32_t a, uint32_t b) {
+    // Philox-2x32-10 style counter hash (counter = (a, b), key from seed) -> 32 random bits
+    uint32_t k = (uint32_t)(seed ^ (seed >> 32));
+    uint32_t c0 = a, c1 = b;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint64_t p = (uint64_t)0xD256D193u * c0;
+        const uint32_t hi = (uint32_t)(p >> 32), lo = (uint32_t)p;
+        c0 = hi ^ k ^ c1;
+        c1 = lo;
+        k += 0x9E3779B9u;
+    }
+    return c0;
+}
+
+// blockDim = 32 * num_vq; block b handles rows b*num_vq .. b*num_vq + num_vq-1 (one warp each).
+__global__ void k_sample(SampleArgs a) {
+    extern __shared__ float s_scores[];  // [num_vq][vocab_pad]
+    __shared__ int s_choice[MAX_VQ];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x;
+    const int row = b * a.num_vq + warp;
+    const int V = a.vocab;
+    const int vpad = (V + 31) & ~31;
+    float* sc = s_scores + warp * vpad;
+    const ctp_sample_cfg& cfg = a.st ? a.st->cfg : a.cfg;
+    const int step = a.st ? a.st->step : a.step;
+    const int hist_len = a.st ? a.st->step : a.hist_len;
+    const int* hist = a.st ? a.st->ids_buf : a.hist;
+    const int hstride = a.st ? a.st->max_new : a.hist_stride;
+    const float* u_ptr = a.st ? (a.st->u_base ? a.st->u_base + (long long)step * a.rows : nullptr) : a.u;
+
+    // 1. temperature (gpt.py:469)
+    const float inv_t = 1.0f / cfg.temperature[warp];
+    const float* lg = a.logits + (long long)row * V;
+    for (int v = lane; v < V; v += 32) sc[v] = lg[v] * inv_t;
+    __syncwarp();
+    // 2. windowed repetition penalty (processors.py:18-34)
+    if (cfg.rep_penalty != 1.0f && row < cfg.rep_max_ids) {
+        const int w = min(hist_len, cfg.rep_window);
+        int my = -1;
+        if (lane < w) my = hist[((long long)b * hstride + (hist_len - w + lane)) * a.num_vq + warp];
+        int mult = 0;
+        bool first = true;
+        for (int t = 0; t < w; ++t) {
+            const int other = __shfl_sync(0xffffffffu, my, t);
+            if (other == my && lane < w) {
+                ++mult;
+                if (t < lane) first = false;
+            }
+        }
+        if (lane < w && first && my >= 0 && my < V) {
+            const float alpha = powf(cfg.rep_penalty, (float)mult);
+            const float s = sc[my];
+            sc[my] = (s < 0.f) ? s * alpha : s / alpha;
+        }
+        __syncwarp();
+    }
+    // full-row softmax normaliser (TopP works on probabilities of the whole row)
+    float mx = -INFINITY;
+    for (int v = lane; v < V; v += 32) mx = fmaxf(mx, sc[v]);
+    mx = warp_max(mx);
+    float z = 0.f;
+    for (int v = lane; v < V; v += 32) z += __expf(sc[v] - mx);
+    z = warp_sum(z);
+    // 3. the K best scores in rank order (K = max(top_k, min_keep), or all-by-mass when top_k is disabled)
+    int K = cfg.top_k > 0 ? max(cfg.top_k, cfg.min_keep) : SAMPLE_MAX_K;
+    K = min(min(K, SAMPLE_MAX_K), V);
+    float my_val = -INFINITY;  // lane k holds rank-k candidate
+    int my_idx = -1;
+    for (int k = 0; k < K; ++k) {
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int v = lane; v < V; v += 32) {
+            const float s = sc[v];
+            if (s > bv) { bv = s; bi = v; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == k) { my_val = bv; my_idx = bi; }
+        if (lane == 0 && bi < V) sc[bi] = -INFINITY;  // remove from the pool
+        __syncwarp();
+    }
+    // 4. TopP on rank order: token at rank k survives iff (mass strictly above it) < top_p, or k < min_keep.
+    //    (reference: cumulative prob from the bottom <= 1 - top_p is removed.)
+    const float pk = (lane < K && my_idx >= 0 && my_idx < V) ? __expf(my_val - mx) / z : 0.f;
+    float above = pk;  // inclusive prefix sum over lanes, then make exclusive
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(0xffffffffu, above, o);
+        if (lane >= o) above += t;
+    }
+    above -= pk;
+    bool keep = (lane < K) && (my_idx >= 0 && my_idx < V) && (my_val > -INFINITY);
+    if (cfg.top_p > 0.f && cfg.top_p < 1.f) {
+        // removed iff 1 - above <= 1 - top_p  (written like the reference's comparison on the ascending cumsum)
+        const float cum_from_bottom = 1.0f - above;
+        if (lane >= cfg.min_keep && cum_from_bottom <= (1.0f - cfg.top_p)) keep = false;
+    }
+    // 5. min-length EOS ban (gpt.py:477-478)
+    if (step < cfg.min_new && my_idx == cfg.eos) keep = false;
+    // 6. softmax over survivors and inverse-CDF draw in token-id order
+    const float e = keep ? __expf(my_val - mx) : 0.f;
+    const float zs = warp_sum(e);
+    const float p = e / zs;
+    // rank of my token id among survivors
+    float cdf_before = 0.f;  // mass of surviving tokens with a smaller id
+    for (int t = 0; t < K; ++t) {
+        const int oi = __shfl_sync(0xffffffffu, my_idx, t);
+        const float op = __shfl_sync(0xffffffffu, p, t);
+        if (oi < my_idx) cdf_before += op;
+    }
+    float uu;
+    if (u_ptr) uu = u_ptr[row];
+    else uu = (float)(philox_mix(cfg.seed, (uint32_t)step, (uint32_t)row) >> 8) * (1.0f / 16777216.0f);
+    // chosen = survivor with cdf_before <= u < cdf_before + p; fall back to the largest id survivor
+    const bool hit = keep && (cdf_before <= uu) && (uu < cdf_before + p);
+    unsigned ballot = __ballot_sync(0xffffffffu, hit);
+    int chosen;
+    if (ballot) {
+        chosen = __shfl_sync(0xffffffffu, my_idx, __ffs(ballot) - 1);
+    } else {
+        int best = keep ? my_idx : -1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+        chosen = best;
+    }
+    if (a.probs_out) {
+        float* po = a.probs_out + (long long)row * V;
+        for (int v = lane; v < V; v += 32) po[v] = 0.f;
+        __syncwarp();
+        if (keep) po[my_idx] = p;
+    }
+    if (a.next_ids && lane == 0) a.next_ids[row] = chosen;
+    if (a.st) {
+        if (lane == 0) s_choice[warp] = chosen;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            GenState* st = a.st;
+            bool eos = false;
+            for (int q = 0; q < a.num_vq; ++q) {
+                eos |= (s_choice[q] == cfg.eos);
+                if (step < st->max_new) st->ids_buf[((long long)b * st->max_new + step) * a.num_vq + q] = s_choice[q];
+            }
+            const bool fin = (st->finish[b] != 0) || eos;   // gpt.py:486-487
+            st->finish[b] = fin ? 1 : 0;
+            if (!fin) st->end_idx[b] += 1;                   // gpt.py:530-531
+            __threadfence();
+            const int t = atomicAdd(&st->ticket, 1);
+            if (t == (int)gridDim.x - 1) {                   // last block: global bookkeeping
+                st->ticket = 0;
+                int all = 1;
+                __threadfence();
+                const volatile unsigned char* fin_v = st->finish;
+                for (int i = 0; i < (int)gridDim.x; ++i) all &= (fin_v[i] != 0);
+                st->all_done = all;
+                st->step = step + 1;
+            }
+        }
+    }
+}
+
+// cur_len += 1 after a trunk step (the new token's K/V now occupy slot cur_len)
+__global__ void k_advance_len(GenState* st) { st->cur_len += 1; }
+
+}  // namespace ctp
