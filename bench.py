@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py — the headline benchmark of the hot path (BASELINE.json: audio-code frames/s + RTF, batch 32, B200).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--gen 512] [--batch 32]
+
+One "step" = one whole generation job of configs[1]: B=32 synthetic 128-token prompts (default speaker row), 512
+generated code frames per sequence (EOS banned: min_new = max_new), then DVAE+Vocos to 24 kHz waveforms.
+  value  : frames/s (1 frame = 4 codes = 512 samples) with the prompts resident in HBM, CUDA-event timed
+  e2e    : the same through ChatTTSPlusPipeline.infer_ids with pinned HOST ids in and HOST waveforms out
+  roofline: decode-step algorithmic bytes / CUDA-event time of the decode loop vs measured HBM peak
+  cpu_baseline / --impl reference: the fp32 oracle port (reference PyTorch CPU path restated) on the host cores
+Multi-GPU (torchrun, one rank per GPU): every rank runs its own batch-32 replica (weak scaling, no data-path
+collective; NCCL only for the speaker-embedding broadcast, the barrier and the max-over-ranks time).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from chatttsplus_b200 import synth  # noqa: E402
+
+L0 = 128
+_CPU_CACHE = {}
+
+
+def algorithmic_bytes_decode(B, l0, steps):
+    """per step W + KV read of the cached slots + KV write + embedding rows + outputs (16-bit
+    weights and KV).  steps = number of decode-loop iterations; iteration i attends l0 + i - 1 cached slots."""
+    W = 381_396_480
+    total = 0
+    for i in range(1, steps + 1):
+        ctx = l0 + i - 1
+        total += W + B * ctx * 61_440 + B * 61_440 + B * 4 * 768 * 2 + B * (4 * 626 * 4 + 768 * 2)
+    return total
+
+
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def synthetic_prompt(cfg, B, seed):
+    """configs[1]: 128 text tokens per sequence (all VQ columns equal, tokenizer.py:126), no padding, position 1 is the
+    [spk_emb] slot that receives the default speaker embedding."""
+    g = torch.Generator().manual_seed(seed)
+    ids1 = torch.randint(1, cfg.num_text_tokens, (B, L0, 1), generator=g)
+    spk_id = 0  # synthetic stand-in for the [spk_emb] token id
+    ids1[:, 1, 0] = spk_id
+    ids = ids1.expand(-1, -1, cfg.num_vq).clone()
+    mask = torch.ones(B, L0, dtype=torch.long)
+    return ids, mask, mask.bool(), spk_id
+
+
+def build_models(device):
+    from chatttsplus_b200.gpt import GPT
+    from chatttsplus_b200.pipeline import ChatTTSPlusPipeline
+    from chatttsplus_b200.vocoder import DVAE, Vocos
+    cfg = synth.GPTConfig()
+    gpt = GPT(dict(hidden_size=768, intermediate_size=3072, num_attention_heads=12, num_hidden_layers=20), max_batch=32)
+    gpt.load_state_dict(synth.make_gpt_state(cfg, seed=1234))
+    gpt.to(device)
+    dcfg, vcfg = synth.DVAEConfig(), synth.VocosConfig()
+    d = DVAE(decoder_config=dict(idim=384, odim=384, hidden=512, n_layer=12, bn_dim=128), dim=384)
+    d.load_state_dict(synth.make_dvae_state(dcfg, seed=4321))
+    d.to(device)
+    v = Vocos(backbone_config=dict(input_channels=100, dim=512, intermediate_dim=1536, num_layers=8),
+              head_config=dict(dim=512, n_fft=1024, hop_length=256, padding="center"))
+    v.load_state_dict(synth.make_vocos_state(vcfg, seed=9876))
+    v.to(device)
+    pipe = ChatTTSPlusPipeline.from_models(tokenizer=None, gpt=gpt, dvae_decode=d, vocos=v, spk_stat=synth.make_spk_stat(), device=device)
+    return cfg, pipe
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from chatttsplus_b200 import _lib
+    from chatttsplus_b200.commons.utils import InferCodeParams
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    B, GEN = args.batch, args.gen
+    cfg, pipe = build_models(device)
+    gpt = pipe.models_dict["gpt"]
+    gpt.record_timing = True
+    ids, mask, text_mask, spk_id = synthetic_prompt(cfg, B, seed=1234 + rank)
+    # default speaker: one vector for the whole job, broadcast from rank 0 over NCCL/NVLink (setup, not data path)
+    spk = pipe._sample_random_speaker() if rank == 0 else torch.empty(768, device=device)
+    if world > 1:
+        dist.broadcast(spk, 0)
+    params = InferCodeParams(prompt="", spk_emb=spk, temperature=0.3, top_P=0.7, top_K=20, repetition_penalty=1.05,
+                             max_new_token=GEN, min_new_token=GEN, show_tqdm=False, ensure_non_empty=False)
+    ids_pin, mask_pin, tm_pin = ids.pin_memory(), mask.pin_memory(), text_mask.pin_memory()
+    ids_dev, mask_dev, tm_dev = ids.to(device), mask.to(device), text_mask.to(device)
+    wav_host = torch.empty(B, 256 * (2 * GEN - 1), dtype=torch.float32).pin_memory()
+
+    def job(resident: bool):
+        torch.manual_seed(1234 + rank)
+        src = (ids_dev, mask_dev, tm_dev) if resident else (ids_pin, mask_pin, tm_pin)
+        wavs = None
+        # the attention mask stays on the host (it only yields per-sequence pad counts): pinned copy in the e2e leg
+        for wavs in pipe.infer_ids(src[0], mask_pin if not resident else mask, src[2], params, spk_emb_ids=spk_id):
+            pass
+        if not resident:
+            for b, w in enumerate(wavs):
+                wav_host[b, : w.numel()].copy_(w, non_blocking=True)
+        return wavs
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(resident, steps, sampler=None):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler:
+            sampler.start()
+        _lib.lib().ctp_launch_count(1)
+        e0.record()
+        dec_ms = pre_ms = 0.0
+        for _ in range(steps):
+            job(resident)
+            dec_ms += gpt.timing["decode_ms"]
+            pre_ms += gpt.timing["prefill_ms"]
+        e1.record()
+        barrier()
+        launches = int(_lib.lib().ctp_launch_count(0))
+        clocks = sampler.stop() if sampler else None
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms, dec_ms, pre_ms], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, dec_ms, pre_ms = t.tolist()
+        return ms, dec_ms, pre_ms, launches, clocks
+
+    for _ in range(max(args.warmup, 3)):
+        job(True)
+    job(False)
+    ms, dec_ms, pre_ms, launches, clocks = timed(True, args.steps, ClockSampler(local) if rank == 0 else None)
+    e2e_ms, _, _, _, _ = timed(False, args.steps)
+    frames = B * GEN * args.steps * world
+    value = frames / (ms / 1e3)
+    e2e_value = frames / (e2e_ms / 1e3)
+    audio_s = world * args.steps * B * (256 * (2 * GEN - 1)) / 24000.0
+    # roofline of the decode step (the dominant unit: one CUDA-graph replay = 20 fused-layer groups + heads + sampler)
+    dec_steps = (GEN - 1) * args.steps
+    alg_bytes = algorithmic_bytes_decode(B, L0, GEN - 1) * args.steps
+    peak, peak_src = 6650.0, "fallback"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        pass
+    achieved = alg_bytes / (dec_ms / 1e3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "decode_step_traffic.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_step")
+    except Exception:
+        pass
+    out = {
+        "metric": "audio-code frames/s (GPT decode loop + DVAE/Vocos vocoder, 24 kHz)", "value": round(value, 1), "unit": "frames/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": f"configs[1]: batch={B} synthetic {L0}-token prompts, default speaker, {GEN} generated codes, hidden->mel->wav",
+                   "per_gpu_batch": B, "prompt_len": L0, "gen_frames": GEN, "parallelism": f"dp{world} (independent replicas)",
+                   "weights": "seeded synthetic, real shapes (no checkpoint offline)",
+                   "cache": "working set per step (0.38 GB weights + >=0.25 GB KV) exceeds the 126 MB L2; no flush needed",
+                   "rtf": round((ms / 1e3) / audio_s, 6), "decode_only_frames_per_s": round(B * dec_steps * world / (dec_ms / 1e3), 1),
+                   "prefill_ms_per_job": round(pre_ms / args.steps, 3), "decode_us_per_step": round(1e3 * dec_ms / dec_steps, 2)},
+        "e2e": {"value": round(e2e_value, 1), "unit": "frames/s", "h2d_bytes_per_step": int(ids.numel() * 8 + mask.numel() * 8 + text_mask.numel()),
+                "d2h_bytes_per_step": int(B * 256 * (2 * GEN - 1) * 4)},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                     "traffic": traffic, "kernel": "decode step (CUDA-graph replay)", "peak_source": peak_src,
+                     "algorithmic_bytes_per_step_mean": int(alg_bytes / dec_steps)},
+        "clocks": clocks,
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu:
+            out["cpu_baseline"] = cpu_baseline(B, sample_steps=2)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(B, sample_steps=2, voc_frames=32):
+    """The oracle port (fp32 restatement of the reference's PyTorch CPU path) on the host cores, bounded sample:
+    decode steps at the job's MEAN context (L = 128 + 256) with a pre-filled KV cache, plus the vocoder on one short
+    utterance; prefill is NOT charged to the CPU arm (conservative for the speed-up)."""
+    from oracle import ctp_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = synth.GPTConfig()
+    if "gpt" not in _CPU_CACHE:
+        _CPU_CACHE["gpt"] = synth.make_gpt_state(cfg, seed=1234)
+        _CPU_CACHE["dvae"] = synth.make_dvae_state(synth.DVAEConfig(), 4321)
+        _CPU_CACHE["vocos"] = synth.make_vocos_state(synth.VocosConfig(), 9876)
+    sd = _CPU_CACHE["gpt"]
+    ctx = L0 + 256
+    g = torch.Generator().manual_seed(0)
+    cache = O.KVCache.empty(cfg.num_hidden_layers)
+    for l in range(cfg.num_hidden_layers):
+        cache.k[l] = torch.randn(B, 12, ctx, 64, generator=g)
+        cache.v[l] = torch.randn(B, 12, ctx, 64, generator=g)
+    ids = torch.randint(0, 625, (B, 1, 4), generator=g)
+    temp = torch.full((B * 4, 1), 0.3)
+    hist = torch.randint(0, 625, (B * 4, 16), generator=g)
+    with torch.inference_mode():
+        def step(i):
+            x = O.code_embed(sd, ids, 4)
+            mask = torch.ones(B, ctx + i + 1, dtype=torch.bool)
+            pos = torch.full((B, 1), ctx + i)
+            h = O.trunk_forward(sd, x, mask, pos, cache, cfg.num_hidden_layers, cfg.num_attention_heads)
+            logits = O.head_code_logits(sd, h[:, -1], 4)
+            s = O.process_logits(logits, hist, temp, rep_penalty=1.05, rep_max_ids=625, rep_window=16, top_p=0.7, top_k=20,
+                                 ban_eos=True, eos_token=625)
+            torch.multinomial(torch.softmax(s, -1), 1)
+        step(0)  # warm-up
+        t0 = time.perf_counter()
+        for i in range(sample_steps):
+            step(1 + i)
+        t_step = (time.perf_counter() - t0) / sample_steps
+        dsd, vsd = _CPU_CACHE["dvae"], _CPU_CACHE["vocos"]
+        hid = torch.randn(voc_frames, 768, generator=g)
+        O.decode_to_wav(dsd, vsd, hid[:8])
+        t0 = time.perf_counter()
+        O.decode_to_wav(dsd, vsd, hid)
+        t_voc_frame = (time.perf_counter() - t0) / voc_frames
+    fps = B / (t_step + B * t_voc_frame)
+    return {"value": round(fps, 2), "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"oracle port, fp32, {cores} threads: {sample_steps} decode steps of batch {B} at the mean context {ctx} "
+                      f"({t_step * 1e3:.0f} ms/step) + vocoder on one {voc_frames}-frame utterance ({t_voc_frame * 1e3:.1f} ms/frame); prefill not charged"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU path for this metric/config = the oracle port (the reference package
+    cannot be imported whole here or on the GPU box: pybase16384 / vocos / vector_quantize_pytorch are absent)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_baseline(args.batch, sample_steps=1, voc_frames=16)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        vals.append(cpu_baseline(args.batch, sample_steps=1, voc_frames=16))
+    dt = time.perf_counter() - t0
+    v = sum(x["value"] for x in vals) / len(vals)
+    cb = dict(vals[-1])
+    cb["value"] = round(v, 2)
+    out = {"impl": "reference", "metric": "audio-code frames/s (GPT decode loop + DVAE/Vocos vocoder, 24 kHz)", "value": round(v, 2),
+           "unit": "frames/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": round(1e3 * dt / args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"configs[1]: batch={args.batch} synthetic {L0}-token prompts, {args.gen} generated codes, hidden->mel->wav "
+                                  "(bounded sample per step, see cpu_baseline.sample)"},
+           "cpu_baseline": cb, "e2e": {"value": round(v, 2), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--gen", type=int, default=512)
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

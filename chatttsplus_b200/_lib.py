@@ -67,6 +67,7 @@ SYMBOLS = {
     "ctp_last_error": (C.c_char_p, []),
     "ctp_version": (C.c_int, []),
     "ctp_device_check": (C.c_int, [C.c_int]),
+    "ctp_launch_count": (C.c_longlong, [C.c_int]),
     "ctp_gpt_create": (C.c_int, [C.POINTER(_VP), C.POINTER(GptCfg)]),
     "ctp_gpt_destroy": (None, [_VP]),
     "ctp_gpt_bind_weights": (C.c_int, [_VP, C.POINTER(GptWeights)]),
@@ -85,6 +86,7 @@ SYMBOLS = {
     "ctp_voc_destroy": (None, [_VP]),
     "ctp_voc_bind_weights": (C.c_int, [_VP, C.POINTER(VocWeights)]),
     "ctp_voc_decode": (C.c_int, [_VP, _I32, C.POINTER(_I32), _VP, _VP, C.POINTER(_I64), _VP, _VP]),
+    "ctp_voc_decode_mel": (C.c_int, [_VP, _I32, C.POINTER(_I32), _VP, _VP, C.POINTER(_I64), _VP]),
     "ctp_gemm_f16": (C.c_int, [_I32, _I32, _I32, _VP, _I64, _VP, _I64, _VP, _I64, _VP, _I32, _I32, _I32, _VP]),
 }
 

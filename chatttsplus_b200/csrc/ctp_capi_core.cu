@@ -13,7 +13,16 @@ void ctp_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static long long g_launches = 0;
+static thread_local bool g_capturing = false;
+static thread_local long long g_capture_launches = 0;
+void ctp_count_launch(int n) { if (g_capturing) g_capture_launches += n; else g_launches += n; }
+void ctp_count_capture_begin() { g_capturing = true; g_capture_launches = 0; }
+long long ctp_count_capture_end() { g_capturing = false; return g_capture_launches; }
+
 extern "C" {
+
+long long ctp_launch_count(int reset) { long long v = g_launches; if (reset) g_launches = 0; return v; }
 
 const char* ctp_last_error(void) { return g_err; }
 int ctp_version(void) { return 100; }

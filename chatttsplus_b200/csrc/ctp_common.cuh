@@ -11,6 +11,11 @@
 // Host-side error plumbing: every C-ABI entry returns ctp_status and records a thread-local message.
 // ---------------------------------------------------------------------------------------------------------
 void ctp_set_error(const char* fmt, ...);
+// Kernel-launch accounting (bench.py's gpu_launches): every launch site calls ctp_count_launch(); while a step graph is
+// being captured the launches are tallied per graph and added once per replay.
+void ctp_count_launch(int n = 1);
+void ctp_count_capture_begin();
+long long ctp_count_capture_end();
 
 #define CTP_CUDA_OK(expr)                                                                          \
     do {                                                                                           \

@@ -85,6 +85,7 @@ static int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, long long a
     }
     dim3 grid((unsigned)((b_rows + BN - 1) / BN), (unsigned)((a_rows + GEMM_BM - 1) / GEMM_BM), (unsigned)split_k);
     gemm_tcgen05_kernel<BN><<<grid, GEMM_THREADS, GemmSmem<BN>::TOTAL, stream>>>(tmA, tmB, shp, epi);
+    ctp_count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         ctp_set_error("gemm launch failed: %s", cudaGetErrorString(e));

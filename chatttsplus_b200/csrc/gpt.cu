@@ -58,6 +58,7 @@ struct ctp_gpt {
     ActMaps act32{}, act64{};
     // decode activation maps point at the first max_batch rows of xn / attn / hmid
     std::map<GraphKey, cudaGraphExec_t> graphs;
+    std::map<GraphKey, long long> graph_nodes;
     cudaStream_t cap_stream = nullptr;
 
     // host mirror of the generation state
@@ -200,6 +201,7 @@ extern "C" ctp_status ctp_gpt_embed_prompt(ctp_gpt* h, int32_t B, int32_t L0, co
     k_embed_prompt<<<B * L0, 256, 0, (cudaStream_t)stream>>>(ids, text_mask, (const __half*)h->w.emb_text,
                                                              (const __half*)h->w.emb_code, emb_out, h->cfg.hidden,
                                                              h->cfg.num_vq, h->cfg.num_audio);
+    ctp_count_launch();
     CTP_CUDA_OK(cudaGetLastError());
     return CTP_OK;
 }
@@ -218,7 +220,7 @@ static int split_for(int k_blocks, int m_tiles, int target_ctas = 148) {
     return s;
 }
 
-#define LAUNCH_OK() do { cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { ctp_set_error("%s:%d launch: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); return CTP_ERR_CUDA; } } while (0)
+#define LAUNCH_OK() do { ctp_count_launch(); cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { ctp_set_error("%s:%d launch: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); return CTP_ERR_CUDA; } } while (0)
 
 // heads: logits[b][q*A + a] = hidden_n[b] . head_code[q*A + a]   (gpt.py:424-439; weight_norm folded at bind)
 static int launch_heads(ctp_gpt* h, int B, cudaStream_t s) {
@@ -456,8 +458,10 @@ static int get_graph(ctp_gpt* h, int B, int nsplit, cudaGraphExec_t* out) {
     if (it != h->graphs.end()) { *out = it->second; return CTP_OK; }
     cudaGraph_t graph = nullptr;
     CTP_CUDA_OK(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+    ctp_count_capture_begin();
     int st = run_decode_trunk(h, B, nsplit, nullptr, h->cap_stream);
     if (!st) st = launch_sampler(h, B, h->cap_stream);
+    const long long n_nodes = ctp_count_capture_end();
     cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
     if (st) { if (graph) cudaGraphDestroy(graph); return st; }
     if (e != cudaSuccess) { ctp_set_error("graph capture failed: %s", cudaGetErrorString(e)); return CTP_ERR_CUDA; }
@@ -466,6 +470,7 @@ static int get_graph(ctp_gpt* h, int B, int nsplit, cudaGraphExec_t* out) {
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) { ctp_set_error("graph instantiate failed: %s", cudaGetErrorString(e)); return CTP_ERR_CUDA; }
     h->graphs[key] = exec;
+    h->graph_nodes[key] = n_nodes;
     *out = exec;
     return CTP_OK;
 }
@@ -490,6 +495,7 @@ extern "C" ctp_status ctp_gpt_generate(ctp_gpt* h, const ctp_sample_cfg* cfg, in
     for (int it = 0; it < iters; ++it) {
         cudaGraphExec_t g;
         if ((st = get_graph(h, h->B, nsplit_for(h, h->B, h->cur_len + 1), &g))) { cudaEventDestroy(ev); return (ctp_status)st; }
+        ctp_count_launch((int)h->graph_nodes[GraphKey{h->B, nsplit_for(h, h->B, h->cur_len + 1)}]);
         cudaError_t e = cudaGraphLaunch(g, s);
         if (e != cudaSuccess) { ctp_set_error("graph launch: %s", cudaGetErrorString(e)); cudaEventDestroy(ev); return CTP_ERR_CUDA; }
         h->cur_len += 1; h->step += 1; done += 1;
@@ -546,6 +552,7 @@ extern "C" ctp_status ctp_sample(int32_t rows, int32_t vocab, int32_t num_vq, co
     const size_t smem = sizeof(float) * num_vq * ((vocab + 31) & ~31);
     CTP_REQUIRE(smem <= 48 * 1024, "sample: vocab %d too large for the warp sampler", vocab);
     k_sample<<<rows / num_vq, 32 * num_vq, smem, (cudaStream_t)stream>>>(sa);
+    ctp_count_launch();
     CTP_CUDA_OK(cudaGetLastError());
     return CTP_OK;
 }

@@ -107,6 +107,8 @@ class GPT:
         self._max_batch = int(kwargs.get("max_batch", 32))
         self._max_seq = 0
         self._max_batch_alloc = 0
+        self.record_timing = False   # bench.py: CUDA events around prefill / decode loop on the launching stream
+        self.timing: Dict[str, float] = {}
         self.model_path = kwargs.get("model_path", None)
         if self.model_path:
             self.logger.info(f"loading GPT pretrained model: {self.model_path}")
@@ -357,6 +359,9 @@ class GPT:
             pad_arr = (C.c_int32 * B)(*pads)
             cfg = self._sample_cfg(temperature, eos, min_new_token, logits_warpers, logits_processors)
             strm = _lib.stream_ptr()
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if self.record_timing else None
+            if evs:
+                evs[0].record()
             _lib.check(lib.ctp_gpt_prefill(self._handle, B, L0, _lib.ptr(emb32), pad_arr, C.byref(bufs), 0, strm), "ctp_gpt_prefill")
 
             def draw_uniforms():
@@ -393,6 +398,8 @@ class GPT:
                 hid = [hid_buf[b, : n[b]] for b in range(B)] if hid_buf is not None else []
                 return GPT.GenerationOutputs(ids=ids, attentions=[], hiddens=hid)
 
+            if evs:
+                evs[1].record()
             remaining = max_new - 1
             chunk = int(stream_batch) if stream else remaining
             done_total = 1
@@ -411,7 +418,12 @@ class GPT:
                 if stream and remaining > 0 and not all_done:
                     all_done = bool(finish.all().item())
                     yield outputs()
+            if evs:
+                evs[2].record()
             torch.cuda.current_stream().synchronize()
+            if evs:
+                self.timing = {"prefill_ms": evs[0].elapsed_time(evs[1]), "decode_ms": evs[1].elapsed_time(evs[2]),
+                               "decode_steps": done_total - 1, "B": B, "L0": L0}
             if pbar is not None:
                 pbar.close()
             if not bool(finish.all().item()):

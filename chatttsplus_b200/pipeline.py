@@ -1,0 +1,258 @@
+"""``ChatTTSPlusPipeline`` — the inference API of reference ``chattts_plus/pipelines/chattts_plus_pipeline.py`` with
+the generation hot path (``_infer_code`` -> ``GPT.generate``, ``_decode_to_wavs`` -> DVAE + Vocos) running in libctp.
+
+Kept verbatim from the reference (so ``webui.py`` and ``tests/test_pipelines.py`` drive it unchanged):
+  ``ChatTTSPlusPipeline(cfg, device=, dtype=, coef=)``, the ``cfg.MODELS[name].{name, infer_type, kwargs}`` model table
+  (chattts_plus_pipeline.py:113-129), ``infer(text, stream, lang, skip_refine_text, refine_text_only, use_decoder,
+  do_text_*, params_refine_text, params_infer_code, **kwargs{speaker_emb_path, speaker_audio_path,
+  speaker_audio_text, lora_path, slice_size, speaker_save_dir})`` -> generator of ``List[Tensor]`` (:472-579),
+  ``sample_random_speaker`` / ``_encode_spk_emb`` (:307-331).
+Differences (all host-side): no hub downloads (offline image: missing checkpoints raise); LoRA is merged natively
+(no peft); utterances are vocoded as one batch; the broken stream slicing (:445-464) is replaced by per-chunk yields.
+``ChatTTSPlusPipeline.from_models`` builds a pipeline from already constructed models (synthetic-weight tests, bench).
+"""
+from __future__ import annotations
+
+import os
+import time
+from typing import List, Optional, Union
+
+import numpy as np
+import torch
+
+from . import gpt as _gpt_mod
+from . import processors
+from . import text as _text
+from . import tokenizer as _tok_mod
+from . import vocoder as _voc_mod
+from .commons import constants, logger
+from .commons.utils import InferCodeParams, RefineTextParams
+
+# the plugin table the YAML's ``name`` fields resolve against (reference: getattr(models, name))
+MODEL_REGISTRY = {"Tokenizer": _tok_mod.Tokenizer, "DVAE": _voc_mod.DVAE, "GPT": _gpt_mod.GPT, "Vocos": _voc_mod.Vocos}
+
+
+class ChatTTSPlusPipeline:
+    def __init__(self, cfg=None, **kwargs):
+        self.logger = logger.get_logger(self.__class__.__name__)
+        self.cfg = cfg
+        self.device = torch.device(kwargs.get("device", "cuda" if torch.cuda.is_available() else "cpu"))
+        self.dtype = kwargs.get("dtype", None) or (torch.float16 if self.device.type == "cuda" else torch.float32)
+        self.logger.info(f"device: {str(self.device)}")
+        self.logger.info(f"dtype: {str(self.dtype)} (kernels: fp16 operands, fp32 accumulate/residual)")
+        self.models_dict = dict()
+        self.infer_type = "pytorch"
+        self.load_lora = False
+        self.normalizer = _text.Normalizer(None)
+        self.std = self.mean = None
+        self._engines = {}
+        if cfg is not None:
+            self.load_models(**kwargs)
+
+    # ---- construction ------------------------------------------------------------------------------------
+    @classmethod
+    def from_models(cls, tokenizer, gpt, dvae_decode, vocos, dvae_encode=None, spk_stat: Optional[torch.Tensor] = None,
+                    device="cuda"):
+        p = cls(None, device=device)
+        p.models_dict = {"tokenizer": tokenizer, "gpt": gpt, "dvae_decode": dvae_decode, "vocos": vocos}
+        if dvae_encode is not None:
+            p.models_dict["dvae_encode"] = dvae_encode
+        if spk_stat is not None:
+            p.std, p.mean = spk_stat.to(p.device, torch.float32).chunk(2)
+        return p
+
+    def load_models(self, **kwargs):
+        """chattts_plus_pipeline.py:54-155 without the hub downloads (this image is offline)."""
+        coef = kwargs.get("coef", None)
+        self.dave_coef = coef
+        for dv in ("dvae_encode", "dvae_decode"):
+            if dv in self.cfg.MODELS and coef is not None:
+                self.cfg.MODELS[dv]["kwargs"]["coef"] = coef
+        for model_name in self.cfg.MODELS:
+            entry = self.cfg.MODELS[model_name]
+            self.logger.info("loading model: {} >>>>".format(model_name))
+            path_org = entry["kwargs"]["model_path"]
+            path_new = os.path.join(constants.CHECKPOINT_DIR, path_org.replace("checkpoints/", ""))
+            if not os.path.exists(path_new):
+                raise FileNotFoundError(f"{path_new} not found (no network in this environment: place the ChatTTS assets under "
+                                        f"{constants.CHECKPOINT_DIR} or build the pipeline with ChatTTSPlusPipeline.from_models)")
+            entry["kwargs"]["model_path"] = path_new
+            if entry["infer_type"] != "pytorch":
+                raise ValueError(f"infer_type {entry['infer_type']!r}: this build has one backend (the sm_100a library); "
+                                 "use configs/infer/chattts_plus.yaml")
+            kw = dict(entry["kwargs"])
+            model_ = MODEL_REGISTRY[entry["name"]](**kw)
+            if model_name != "tokenizer":
+                model_.eval().to(self.device, dtype=self.dtype)
+            self.models_dict[model_name] = model_
+        spk_stat_path = os.path.join(constants.CHECKPOINT_DIR, "asset/spk_stat.pt")
+        assert os.path.exists(spk_stat_path), f"Missing spk_stat.pt: {spk_stat_path}"
+        spk_stat = torch.load(spk_stat_path, weights_only=True, mmap=True).to(self.device, dtype=torch.float32)
+        self.std, self.mean = spk_stat.chunk(2)
+        normalizer_json = os.path.join(constants.CHECKPOINT_DIR, "homophones_map.json")
+        self.normalizer = _text.Normalizer(normalizer_json if os.path.exists(normalizer_json) else None)
+
+    def _engine(self, use_decoder: bool) -> _voc_mod.VocoderEngine:
+        key = "dvae_decode" if use_decoder else "dvae_encode"
+        if key not in self._engines:
+            self._engines[key] = _voc_mod.VocoderEngine(self.models_dict[key], self.models_dict["vocos"])
+        return self._engines[key]
+
+    # ---- hot path ----------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def infer_ids(self, input_ids: torch.Tensor, attention_mask: torch.Tensor, text_mask: torch.Tensor,
+                  params: InferCodeParams, *, stream: bool = False, use_decoder: bool = True, spk_emb_ids: Optional[int] = None,
+                  uniforms: Optional[torch.Tensor] = None, return_codes: bool = False):
+        """``_infer_code`` after tokenisation + ``_decode_to_wavs`` (chattts_plus_pipeline.py:195-235,286-305):
+        host or device ``input_ids [B, L, num_vq]`` -> generator of ``List[wav]`` (and the GenerationOutputs if asked)."""
+        gpt = self.models_dict["gpt"]
+        dev = self.device
+        input_ids = input_ids.to(dev, non_blocking=True)
+        text_mask = text_mask.to(dev, non_blocking=True)
+        temperature = params.temperature if isinstance(params.temperature, list) else [params.temperature] * gpt.num_vq
+        emb = gpt(input_ids, text_mask)
+        if params.spk_emb is not None:
+            sid = spk_emb_ids if spk_emb_ids is not None else self.models_dict["tokenizer"].spk_emb_ids
+            _tok_mod.apply_spk_emb(emb, params.spk_emb, input_ids, sid)
+        num_code = int(gpt.emb_code[0].num_embeddings - 1)
+        warpers, procs = processors.gen_logits(num_code=num_code, top_P=params.top_P, top_K=params.top_K,
+                                               repetition_penalty=params.repetition_penalty)
+        gen = gpt.generate(emb, input_ids, temperature=torch.tensor(temperature), eos_token=num_code,
+                           attention_mask=attention_mask, max_new_token=params.max_new_token, min_new_token=params.min_new_token,
+                           logits_warpers=warpers, logits_processors=procs, infer_text=False, return_hidden=use_decoder,
+                           stream=stream, show_tqdm=params.show_tqdm, ensure_non_empty=params.ensure_non_empty,
+                           stream_batch=params.stream_batch, uniforms=uniforms)
+        for result in gen:
+            wavs = self._decode_to_wavs(result.hiddens if use_decoder else result.ids, use_decoder)
+            yield (wavs, result) if return_codes else wavs
+
+    @torch.no_grad()
+    def _infer_code(self, text, stream: bool, return_hidden: bool, params: InferCodeParams):
+        """Tokenise and run the decoder loop; yields GenerationOutputs (chattts_plus_pipeline.py:157-235)."""
+        self.logger.info("Start inference audio code >>>>")
+        if not isinstance(text, list):
+            text = [text]
+        assert len(text), "text should not be empty"
+        gpt, tok = self.models_dict["gpt"], self.models_dict["tokenizer"]
+        text = [t.replace("[Stts]", "").replace("[spk_emb]", "").replace("[empty_spk]", "").strip() for t in text]
+        if params.prompt:
+            text = [params.prompt + i for i in text]
+        txt_smp = "" if params.txt_smp is None else params.txt_smp
+        tag = "[spk_emb]" if params.spk_emb is not None else "[empty_spk]"
+        text = [f"[Stts]{tag}{txt_smp}{i}[Ptts]" for i in text]
+        input_ids, attention_mask, text_mask = tok.encode(text, gpt.num_vq, prompt_str=params.spk_smp, device="cpu")
+        for wavs, result in self.infer_ids(input_ids, attention_mask, text_mask, params, stream=stream, use_decoder=return_hidden,
+                                           return_codes=True):
+            result._wavs = wavs
+            yield result
+
+    @torch.inference_mode()
+    def _decode_to_wavs(self, result_list, use_decoder: bool):
+        self.logger.info("Start decode to wavs >>>>")
+        if len(result_list) == 0:
+            return []
+        wavs, _ = self._engine(use_decoder).decode_batch(list(result_list))
+        return wavs
+
+    # ---- speakers ----------------------------------------------------------------------------------------
+    def sample_random_speaker(self) -> str:
+        return self._encode_spk_emb(self._sample_random_speaker())
+
+    @staticmethod
+    @torch.no_grad()
+    def _encode_spk_emb(spk_emb: torch.Tensor) -> str:
+        return _tok_mod.Tokenizer._encode_spk_emb(spk_emb)
+
+    @torch.no_grad()
+    def _sample_random_speaker(self) -> torch.Tensor:
+        dim = self.std.shape[-1]
+        return torch.randn(dim, device=self.std.device, dtype=self.std.dtype).mul_(self.std).add_(self.mean)
+
+    def _load_speaker(self, path: str):
+        """Accept what the shipped speaker files contain (a torch-saved b14 str) or a tensor ([768] or [1,768])."""
+        try:
+            spk = torch.load(path, weights_only=True, map_location="cpu")
+        except Exception:
+            if path.endswith(".safetensors"):
+                import safetensors.torch
+                spk = next(iter(safetensors.torch.load_file(path).values()))
+            else:
+                spk = torch.load(path, weights_only=False, map_location="cpu")
+        if isinstance(spk, dict):
+            spk = next(iter(spk.values()))
+        if isinstance(spk, str):
+            return spk
+        if not isinstance(spk, torch.Tensor):
+            raise ValueError(f"speaker embedding file holds {type(spk)}")
+        return spk.reshape(-1).float()
+
+    # ---- public API --------------------------------------------------------------------------------------
+    def _infer(self, text_in, stream=False, lang=None, skip_refine_text=False, refine_text_only=False, use_decoder=True,
+               do_text_normalization=True, do_text_optimization=True, do_homophone_replacement=True,
+               params_refine_text=RefineTextParams(), params_infer_code=InferCodeParams(), **kwargs):
+        if not isinstance(text_in, list):
+            text_in = [text_in]
+        if do_text_optimization:  # chattts_plus_pipeline.py:353-377
+            text_list = []
+            for t in text_in:
+                text_list.extend([s.strip() for s in t.split("\n") if s.strip()])
+            retext, short = [], ""
+            for it in _text.split_text(text_list):
+                if len(it) < 30:
+                    short += f"{it} [uv_break] "
+                    if len(short) > 30:
+                        retext.append(short)
+                        short = ""
+                else:
+                    retext.append(short + it)
+                    short = ""
+            if len(short) > 30 or len(retext) < 1:
+                retext.append(short)
+            elif short:
+                retext[-1] += f" [uv_break] {short}"
+            text_in = retext
+        text_in = [self.normalizer(t, do_text_normalization, do_homophone_replacement, lang) for t in text_in]
+        slice_size = kwargs.get("slice_size", 4)
+        gpt = self.models_dict["gpt"]
+        for ii in range(0, len(text_in), slice_size):
+            text = text_in[ii:ii + slice_size].copy()
+            if not skip_refine_text:
+                raise NotImplementedError("refine-text pass (infer_text=True) is the next scope row (SURVEY.md §8f f1): "
+                                          "call infer(..., skip_refine_text=True)")
+            if refine_text_only:
+                continue
+            for ti in range(len(text)):
+                if not text[ti].strip().endswith("[uv_break]"):
+                    text[ti] += " [uv_break]"
+            lora_path = kwargs.get("lora_path", None)
+            if lora_path:
+                self.logger.info(f"load lora into gpt: {lora_path}")
+                gpt.load_lora(lora_path)
+            try:
+                for result in self._infer_code(text, stream, use_decoder, params_infer_code):
+                    yield result._wavs
+            finally:
+                if lora_path:
+                    self.logger.info("unload lora !")
+                    gpt.unload_lora()
+
+    @torch.no_grad()
+    def infer(self, text, stream=False, lang=None, skip_refine_text=False, refine_text_only=False, use_decoder=True,
+              do_text_normalization=True, do_text_optimization=True, do_homophone_replacement=True,
+              params_refine_text=RefineTextParams(), params_infer_code=InferCodeParams(), **kwargs):
+        if kwargs.get("speaker_audio_path", None):
+            raise NotImplementedError("zero-shot speaker prompt (DVAE encode) is the next scope row (SURVEY.md §8f f3)")
+        elif kwargs.get("speaker_emb_path", None):
+            p = kwargs["speaker_emb_path"]
+            assert os.path.exists(p), f"speaker_emb_path {p} not exists!"
+            self.logger.info(f"loading speaker_emb from {p}")
+            params_infer_code.spk_emb = self._load_speaker(p)
+        else:
+            self.logger.info("speaker_emb is None, random select a speaker!")
+            speaker_emb = self.sample_random_speaker()
+            params_infer_code.spk_emb = speaker_emb
+            spk_dir = kwargs.get("speaker_save_dir", os.path.join(constants.PROJECT_DIR, "results/speakers"))
+            os.makedirs(spk_dir, exist_ok=True)
+            torch.save(speaker_emb, f"{spk_dir}/{time.time()}.pt")
+        return self._infer(text, stream, lang, skip_refine_text, refine_text_only, use_decoder, do_text_normalization,
+                           do_text_optimization, do_homophone_replacement, params_refine_text, params_infer_code, **kwargs)

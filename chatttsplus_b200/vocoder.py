@@ -1,0 +1,343 @@
+"""``DVAE`` / ``Vocos`` host-side mirrors and the fused batch vocoder engine (libctp ``ctp_voc_*``).
+
+Reference interfaces kept:
+  * ``DVAE(decoder_config, encoder_config=None, vq_config=None, dim=512, coef=None, model_path=...)``,
+    ``DVAE.__call__(inp, mode="decode")`` -> mel ``[B, 100, 2T]``        (chattts_plus/models/dvae.py:203-291)
+  * ``Vocos`` object with ``.parameters()`` (dtype probe) and ``.decode(mel)`` -> wav ``[B, 256*(T-1)]``
+    (pip ``vocos`` as assembled by chattts_plus_pipeline.py:93-111 and called at :300-303)
+  * ``VocoderEngine.decode_batch`` = ``ChatTTSPlusPipeline._decode_to_wavs`` for the whole batch in one library
+    call (the reference loops utterance by utterance at batch 1, chattts_plus_pipeline.py:298-304).
+The encode side (mel-spectrogram -> GFSQ ids, dvae.py:171-199,263-270) is the "next" scope row f3.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .commons import b14
+from .commons import logger as _logger
+from .synth import DVAEConfig, VocosConfig
+
+MEL_PAD = 104
+
+
+def _dev_f16(t, dev):
+    return t.detach().to(dev, torch.float16).contiguous()
+
+
+def _dev_f32(t, dev):
+    return t.detach().to(dev, torch.float32).contiguous()
+
+
+def _pack_convnext(sd: Dict[str, torch.Tensor], prefix: str, dev, keep: list) -> _lib.ConvNextW:
+    t = dict(
+        dw_w=_dev_f32(sd[prefix + "dwconv.weight"].squeeze(1), dev), dw_b=_dev_f32(sd[prefix + "dwconv.bias"], dev),
+        ln_w=_dev_f32(sd[prefix + "norm.weight"], dev), ln_b=_dev_f32(sd[prefix + "norm.bias"], dev),
+        pw1_w=_dev_f16(sd[prefix + "pwconv1.weight"], dev), pw1_b=_dev_f32(sd[prefix + "pwconv1.bias"], dev),
+        pw2_w=_dev_f16(sd[prefix + "pwconv2.weight"], dev), pw2_b=_dev_f32(sd[prefix + "pwconv2.bias"], dev),
+        gamma=_dev_f32(sd[prefix + "gamma"], dev))
+    keep.append(t)
+    return _lib.ConvNextW(**{k: v.data_ptr() for k, v in t.items()})
+
+
+def _im2col_weight(w: torch.Tensor, c_pad: Optional[int] = None) -> torch.Tensor:
+    """Conv1d weight [O, C, K] -> [O, K*C'] with k = tap*C' + c (the order the overlapping-row TMA window has)."""
+    O, Cc, K = w.shape
+    if c_pad is not None and c_pad > Cc:
+        w = F.pad(w, (0, 0, 0, c_pad - Cc))
+    return w.permute(0, 2, 1).reshape(O, -1)
+
+
+class DVAE:
+    def __init__(self, decoder_config: dict, encoder_config: Optional[dict] = None, vq_config: Optional[dict] = None,
+                 dim=512, coef: Optional[str] = None, **kwargs):
+        self.logger = _logger.get_logger(self.__class__.__name__)
+        d = dict(decoder_config)
+        self.cfg = DVAEConfig(dim=int(dim), idim=int(d["idim"]), odim=int(d["odim"]), hidden=int(d.get("hidden", 256)),
+                              n_layer=int(d.get("n_layer", 12)), bn_dim=int(d.get("bn_dim", 64)),
+                              kernel=int(d.get("kernel", 7)), dilation=int(d.get("dilation", 2)), vq=vq_config is not None)
+        if vq_config is not None:
+            v = dict(vq_config)
+            self.cfg.vq_dim = int(v["dim"]); self.cfg.vq_levels = tuple(v["levels"]); self.cfg.vq_G = int(v["G"]); self.cfg.vq_R = int(v["R"])
+            if tuple(self.cfg.vq_levels) != (5, 5, 5, 5) or self.cfg.vq_G != 2 or self.cfg.vq_R != 2:
+                raise _lib.CtpError("the GFSQ embed kernel is built for levels [5,5,5,5], G=2, R=2")
+        self.has_encoder = encoder_config is not None
+        if coef is None:
+            coef_t = torch.rand(100)
+        else:
+            coef_t = torch.from_numpy(np.copy(np.frombuffer(b14.decode_from_string(coef), dtype=np.float32)))
+        self.coef = coef_t.view(1, 100, 1)  # dvae.py:213-222 (overwritten by load_state_dict, as in the reference)
+        self.device = torch.device("cpu")
+        self._state: Optional[Dict[str, torch.Tensor]] = None
+        self._keep: list = []
+        self._w: Optional[dict] = None
+        self._engine: Optional["VocoderEngine"] = None
+        self.model_path = kwargs.get("model_path", None)
+        if self.model_path:
+            self.logger.info(f"loading DVAE pretrained model: {self.model_path}")
+            self.from_pretrained(self.model_path)
+
+    def __repr__(self) -> str:
+        return b14.encode_to_string(self.coef.cpu().numpy().astype(np.float32).tobytes())
+
+    def eval(self):
+        return self
+
+    def from_pretrained(self, file_path: str):
+        self.load_state_dict(torch.load(file_path, weights_only=True, mmap=True))
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True):
+        need = ["coef", "decoder.conv_in.0.weight", "decoder.conv_in.0.bias", "decoder.conv_in.2.weight", "decoder.conv_in.2.bias",
+                "decoder.conv_out.weight", "out_conv.weight"]
+        for l in range(self.cfg.n_layer):
+            for n in ("dwconv.weight", "dwconv.bias", "norm.weight", "norm.bias", "pwconv1.weight", "pwconv1.bias",
+                      "pwconv2.weight", "pwconv2.bias", "gamma"):
+                need.append(f"decoder.decoder_block.{l}.{n}")
+        if self.cfg.vq:
+            for g in range(self.cfg.vq_G):
+                need += [f"vq_layer.quantizer.rvqs.{g}.project_out.weight", f"vq_layer.quantizer.rvqs.{g}.project_out.bias"]
+        missing = [k for k in need if k not in sd]
+        if missing:
+            raise RuntimeError(f"Error(s) in loading state_dict for DVAE: missing {missing[:5]}")
+        # encoder-side tensors (downsample_conv.*, encoder.*, preprocessor_mel.*, project_in) are accepted and unused here
+        self._state = {k: sd[k].detach().cpu() for k in sd}
+        self.coef = self._state["coef"].float().view(1, 100, 1)
+        if self.device.type == "cuda":
+            self._pack()
+        return self
+
+    def to(self, device=None, dtype=None, **kw):
+        if device is not None:
+            device = torch.device(device)
+            if device.type == "cuda":
+                if not torch.cuda.is_available():
+                    raise _lib.CtpError("chatttsplus_b200.DVAE needs a CUDA (sm_100a) device; there is no CPU path")
+                if device.index is None:
+                    device = torch.device("cuda", torch.cuda.current_device())
+                self.device = device
+                if self._state is not None:
+                    self._pack()
+        return self
+
+    def _pack(self):
+        sd, dev, c = self._state, self.device, self.cfg
+        self._keep = []
+        w = dict(
+            conv_in0_w=_dev_f16(_im2col_weight(sd["decoder.conv_in.0.weight"].float()), dev), conv_in0_b=_dev_f32(sd["decoder.conv_in.0.bias"], dev),
+            conv_in2_w=_dev_f16(_im2col_weight(sd["decoder.conv_in.2.weight"].float()), dev), conv_in2_b=_dev_f32(sd["decoder.conv_in.2.bias"], dev),
+            conv_out_w=_dev_f16(sd["decoder.conv_out.weight"].float().squeeze(-1), dev),
+            out_conv_w=_dev_f16(_im2col_weight(sd["out_conv.weight"].float()), dev),
+            coef=_dev_f32(sd["coef"].reshape(-1), dev))
+        if c.vq:
+            w["vq_proj_w"] = _dev_f32(torch.stack([sd[f"vq_layer.quantizer.rvqs.{g}.project_out.weight"] for g in range(c.vq_G)]), dev)
+            w["vq_proj_b"] = _dev_f32(torch.stack([sd[f"vq_layer.quantizer.rvqs.{g}.project_out.bias"] for g in range(c.vq_G)]), dev)
+        blocks = (_lib.ConvNextW * c.n_layer)(*[_pack_convnext(sd, f"decoder.decoder_block.{l}.", dev, self._keep) for l in range(c.n_layer)])
+        self._w = dict(tensors=w, blocks=blocks)
+        self._engine = None
+
+    def __call__(self, inp: torch.Tensor, mode: str = "decode") -> torch.Tensor:
+        return self.forward(inp, mode)
+
+    @torch.inference_mode()
+    def forward(self, inp: torch.Tensor, mode: str = "decode") -> torch.Tensor:
+        if mode == "encode":
+            raise NotImplementedError("DVAE encode (zero-shot speaker prompt) is the next scope row (SURVEY.md §8f f3)")
+        if self._w is None:
+            raise _lib.CtpError("DVAE weights are not on a CUDA device: call .to('cuda') after loading")
+        if self._engine is None:
+            self._engine = VocoderEngine(self, None)
+        B = inp.shape[0]
+        if self.cfg.vq:   # codes [B, 4, T]
+            items = [inp[b].permute(1, 0) for b in range(B)]
+        else:             # hidden [B, 768, T]
+            items = [inp[b].permute(1, 0) for b in range(B)]
+        mels = self._engine.decode_batch(items, want_wav=False, want_mel=True)[1]
+        return torch.stack([m.permute(1, 0) for m in mels])  # [B, 100, 2T]
+
+
+class Vocos:
+    """vocos.Vocos-compatible surface used by the pipeline: ``parameters()`` and ``decode(mel)``."""
+
+    def __init__(self, feature_extractor_config: Optional[dict] = None, backbone_config: Optional[dict] = None,
+                 head_config: Optional[dict] = None, **kwargs):
+        self.logger = _logger.get_logger(self.__class__.__name__)
+        b = dict(backbone_config or {})
+        hc = dict(head_config or {})
+        self.cfg = VocosConfig(input_channels=int(b.get("input_channels", 100)), dim=int(b.get("dim", 512)),
+                               intermediate_dim=int(b.get("intermediate_dim", 1536)), num_layers=int(b.get("num_layers", 8)),
+                               n_fft=int(hc.get("n_fft", 1024)), hop_length=int(hc.get("hop_length", 256)))
+        if hc.get("padding", "center") != "center":
+            raise _lib.CtpError("only ISTFT padding='center' is implemented (configs/infer/chattts_plus.yaml:62-66)")
+        self.device = torch.device("cpu")
+        self._state = None
+        self._keep: list = []
+        self._w = None
+        self._engine = None
+        self._dtype_probe = torch.zeros(1, dtype=torch.float32)
+        self.model_path = kwargs.get("model_path", None)
+        if self.model_path:
+            self.load_state_dict(torch.load(self.model_path, weights_only=True, mmap=True))
+
+    def eval(self):
+        return self
+
+    def parameters(self):
+        return iter([self._dtype_probe])
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True):
+        need = ["backbone.embed.weight", "backbone.embed.bias", "backbone.norm.weight", "backbone.norm.bias",
+                "backbone.final_layer_norm.weight", "backbone.final_layer_norm.bias", "head.out.weight", "head.out.bias"]
+        missing = [k for k in need if k not in sd]
+        if missing:
+            raise RuntimeError(f"Error(s) in loading state_dict for Vocos: missing {missing}")
+        self._state = {k: sd[k].detach().cpu() for k in sd}
+        if "head.istft.window" not in self._state:
+            self._state["head.istft.window"] = torch.hann_window(self.cfg.n_fft, periodic=True)
+        if self.device.type == "cuda":
+            self._pack()
+        return self
+
+    def to(self, device=None, dtype=None, **kw):
+        if device is not None:
+            device = torch.device(device)
+            if device.type == "cuda":
+                if not torch.cuda.is_available():
+                    raise _lib.CtpError("chatttsplus_b200.Vocos needs a CUDA (sm_100a) device; there is no CPU path")
+                if device.index is None:
+                    device = torch.device("cuda", torch.cuda.current_device())
+                self.device = device
+                self._dtype_probe = torch.zeros(1, device=device, dtype=torch.float32)
+                if self._state is not None:
+                    self._pack()
+        return self
+
+    def _pack(self):
+        sd, dev, c = self._state, self.device, self.cfg
+        self._keep = []
+        w = dict(
+            embed_w=_dev_f16(_im2col_weight(sd["backbone.embed.weight"].float(), MEL_PAD), dev), embed_b=_dev_f32(sd["backbone.embed.bias"], dev),
+            norm_w=_dev_f32(sd["backbone.norm.weight"], dev), norm_b=_dev_f32(sd["backbone.norm.bias"], dev),
+            final_ln_w=_dev_f32(sd["backbone.final_layer_norm.weight"], dev), final_ln_b=_dev_f32(sd["backbone.final_layer_norm.bias"], dev),
+            head_w=_dev_f16(sd["head.out.weight"], dev), head_b=_dev_f32(sd["head.out.bias"], dev),
+            window=_dev_f32(sd["head.istft.window"], dev))
+        blocks = (_lib.ConvNextW * c.num_layers)(*[_pack_convnext(sd, f"backbone.convnext.{l}.", dev, self._keep) for l in range(c.num_layers)])
+        self._w = dict(tensors=w, blocks=blocks)
+        self._engine = None
+
+    @torch.inference_mode()
+    def decode(self, mel: torch.Tensor) -> torch.Tensor:
+        """mel [B, 100, T] -> wav [B, hop*(T-1)]"""
+        if self._w is None:
+            raise _lib.CtpError("Vocos weights are not on a CUDA device")
+        if self._engine is None:
+            self._engine = VocoderEngine(None, self)
+        wavs = self._engine.decode_mel([mel[b].permute(1, 0) for b in range(mel.shape[0])])
+        return torch.stack(wavs)
+
+
+class VocoderEngine:
+    """One libctp vocoder handle bound to a DVAE and/or a Vocos weight set."""
+
+    def __init__(self, dvae: Optional[DVAE], vocos: Optional[Vocos], max_frames: int = 1 << 15):
+        assert dvae is not None or vocos is not None
+        self.dvae, self.vocos = dvae, vocos
+        self.device = (dvae or vocos).device
+        self._handle = C.c_void_p(0)
+        self._max_frames = 0
+        self._want_frames = int(max_frames)
+
+    def _ensure(self, frames_needed: int):
+        if self._handle and frames_needed <= self._max_frames:
+            return
+        lib = _lib.lib()
+        if self._handle:
+            lib.ctp_voc_destroy(self._handle)
+            self._handle = C.c_void_p(0)
+        dc = self.dvae.cfg if self.dvae else DVAEConfig()
+        vc = self.vocos.cfg if self.vocos else VocosConfig()
+        self._max_frames = max(self._want_frames, frames_needed)
+        cfg = _lib.VocCfg(dvae_idim=dc.idim, dvae_bn=dc.bn_dim, dvae_hidden=dc.hidden, dvae_layers=dc.n_layer, dvae_odim=dc.odim,
+                          dvae_dilation=dc.dilation, n_mels=dc.n_mels, use_vq=1 if dc.vq else 0, voc_dim=vc.dim, voc_inter=vc.intermediate_dim,
+                          voc_layers=vc.num_layers, n_fft=vc.n_fft, hop=vc.hop_length, max_frames=self._max_frames)
+        h = C.c_void_p(0)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.ctp_voc_create(C.byref(h), C.byref(cfg)), "ctp_voc_create")
+            self._handle = h
+            w = _lib.VocWeights()
+            if self.dvae is not None:
+                for k, t in self.dvae._w["tensors"].items():
+                    setattr(w, k, t.data_ptr())
+                w.dvae_blocks = C.cast(self.dvae._w["blocks"], C.POINTER(_lib.ConvNextW))
+            if self.vocos is not None:
+                for k, t in self.vocos._w["tensors"].items():
+                    setattr(w, k, t.data_ptr())
+                w.voc_blocks = C.cast(self.vocos._w["blocks"], C.POINTER(_lib.ConvNextW))
+            _lib.check(lib.ctp_voc_bind_weights(self._handle, C.byref(w)), "ctp_voc_bind_weights")
+
+    def __del__(self):
+        try:
+            if self._handle:
+                _lib.lib().ctp_voc_destroy(self._handle)
+        except Exception:
+            pass
+
+    @torch.inference_mode()
+    def decode_batch(self, items: Sequence[torch.Tensor], want_wav: bool = True, want_mel: bool = False):
+        """items[i]: hiddens ``[n_i, 2*idim]`` (float) or codes ``[n_i, 4]`` (int) -> (wavs, mels).
+
+        wavs[i]: fp32 ``[hop*(2 n_i - 1)]``; mels[i]: fp32 ``[2 n_i, 100]``."""
+        dev = self.device
+        vq = bool(self.dvae.cfg.vq)
+        lens = [int(t.shape[0]) for t in items]
+        keep = [i for i, n in enumerate(lens) if n >= 1]
+        if not keep:
+            return [torch.zeros(0, device=dev) for _ in items], [torch.zeros(0, 100, device=dev) for _ in items]
+        glens = [lens[i] for i in keep]
+        hop = self.vocos.cfg.hop_length if self.vocos else 256
+        with torch.cuda.device(dev):
+            if vq:
+                src = torch.cat([items[i].to(dev, torch.int32).reshape(lens[i], -1) for i in keep]).contiguous()
+            else:
+                src = torch.cat([items[i].to(dev, torch.float32) for i in keep]).contiguous()
+            self._ensure(max(2 * n for n in glens) + 32)
+            wlen = [hop * (2 * n - 1) for n in glens]
+            offs = np.concatenate([[0], np.cumsum(wlen)]).astype(np.int64)
+            wav = torch.empty(int(offs[-1]), device=dev, dtype=torch.float32) if want_wav else None
+            mel = torch.empty(2 * sum(glens), 100, device=dev, dtype=torch.float32) if want_mel else None
+            n = len(glens)
+            lens_arr = (C.c_int32 * n)(*glens)
+            offs_arr = (C.c_int64 * n)(*offs[:-1].tolist())
+            _lib.check(_lib.lib().ctp_voc_decode(self._handle, n, lens_arr, _lib.ptr(src), _lib.ptr(wav), offs_arr, _lib.ptr(mel),
+                                                 _lib.stream_ptr()), "ctp_voc_decode")
+        wavs: List[torch.Tensor] = [torch.zeros(0, device=dev) for _ in items]
+        mels: List[torch.Tensor] = [torch.zeros(0, 100, device=dev) for _ in items]
+        mrow = 0
+        for k, i in enumerate(keep):
+            if want_wav:
+                wavs[i] = wav[int(offs[k]): int(offs[k + 1])]
+            if want_mel:
+                mels[i] = mel[mrow: mrow + 2 * glens[k]]
+                mrow += 2 * glens[k]
+        return wavs, mels
+
+    @torch.inference_mode()
+    def decode_mel(self, mels: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+        """mels[i]: ``[T_i, 100]`` -> wav ``[hop*(T_i-1)]``"""
+        dev = self.device
+        hop = self.vocos.cfg.hop_length
+        lens = [int(m.shape[0]) for m in mels]
+        with torch.cuda.device(dev):
+            src = torch.cat([m.to(dev, torch.float32) for m in mels]).contiguous()
+            self._ensure(max(lens) + 32)
+            wlen = [hop * (n - 1) for n in lens]
+            offs = np.concatenate([[0], np.cumsum(wlen)]).astype(np.int64)
+            wav = torch.empty(int(offs[-1]), device=dev, dtype=torch.float32)
+            n = len(lens)
+            _lib.check(_lib.lib().ctp_voc_decode_mel(self._handle, n, (C.c_int32 * n)(*lens), _lib.ptr(src), _lib.ptr(wav),
+                                                     (C.c_int64 * n)(*offs[:-1].tolist()), _lib.stream_ptr()), "ctp_voc_decode_mel")
+        return [wav[int(offs[k]): int(offs[k + 1])] for k in range(n)]

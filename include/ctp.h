@@ -41,6 +41,8 @@ CTP_API const char* ctp_last_error(void);
 CTP_API int ctp_version(void);
 /* CTP_OK iff device `dev` exists and is compute capability 10.x. */
 CTP_API ctp_status ctp_device_check(int dev);
+/* Number of libctp kernels launched by this process so far (graph replays count their kernel nodes); reset != 0 zeroes it. */
+CTP_API long long ctp_launch_count(int reset);
 
 /* ======================================================================================================
  * GPT decoder (reference: chattts_plus/models/gpt.py GPT, chattts_plus/models/llama.py LlamaModel;
@@ -215,7 +217,7 @@ typedef struct ctp_voc_weights {
 
 CTP_API ctp_status ctp_voc_create(ctp_voc** out, const ctp_voc_cfg* cfg);
 CTP_API void ctp_voc_destroy(ctp_voc* h);
-CTP_API ctp_status ctp_voc_bind_weights(ctp_voc* h, const ctp_voc_weights* w);
+CTP_API ctp_status ctp_voc_bind_weights(ctp_voc* h, const ctp_voc_weights* w); /* a DVAE-only or Vocos-only set may be bound (other pointers NULL) */
 
 /* _decode_to_wavs for a whole batch (chattts_plus_pipeline.py:286-305): utterance i has lens_host[i] code frames;
  * src = concatenated hiddens fp32 [sum n_i][2*idim] (use_vq=0) or codes int32 [sum n_i][4] (use_vq=1);
@@ -223,6 +225,12 @@ CTP_API ctp_status ctp_voc_bind_weights(ctp_voc* h, const ctp_voc_weights* w);
  * mel_out (optional, may be NULL): concatenated fp32 mel [sum 2*n_i][n_mels] (the DVAE output, dvae.py:291). */
 CTP_API ctp_status ctp_voc_decode(ctp_voc* h, int32_t n_utt, const int32_t* lens_host, const void* src, float* wav_out,
                                   const int64_t* wav_offsets_host, float* mel_out, ctp_stream stream);
+/* wav_out may be NULL (DVAE only: DVAE.__call__(inp, "decode"), dvae.py:254-291, needs mel_out).
+ *
+ * vocos.Vocos.decode(mel) alone (chattts_plus_pipeline.py:303, tests/test_models.py:104-148): mel fp32
+ * [sum T_i][n_mels] concatenated, utterance i has mel_lens_host[i] frames -> wav of hop*(T_i-1) samples. */
+CTP_API ctp_status ctp_voc_decode_mel(ctp_voc* h, int32_t n_utt, const int32_t* mel_lens_host, const float* mel,
+                                      float* wav_out, const int64_t* wav_offsets_host, ctp_stream stream);
 
 /* ======================================================================================================
  * Building block exposed for tests and profiling: C = epilogue(A[M,K] * B[N,K]^T), fp16 in, fp32 accumulate,
