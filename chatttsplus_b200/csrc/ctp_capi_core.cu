@@ -4,6 +4,7 @@
 
 #include <stdarg.h>
 
+namespace ctp { extern long long* g_dbg; }
 static thread_local char g_err[1024] = "";
 
 void ctp_set_error(const char* fmt, ...) {
@@ -42,6 +43,9 @@ ctp_status ctp_device_check(int dev) {
     }
     return CTP_OK;
 }
+
+// bring-up hook (not part of include/ctp.h): device buffer of per-CTA clock64 stamps for subsequent GEMM launches
+__attribute__((visibility("default"))) void ctp_debug_gemm_stamps(long long* buf) { ctp::g_dbg = buf; }
 
 ctp_status ctp_gemm_f16(int32_t M, int32_t N, int32_t K, const void* A, int64_t lda, const void* B, int64_t ldb, void* out,
                         int64_t ldo, const float* bias, int32_t flags, int32_t block_n, int32_t split_k, ctp_stream stream) {

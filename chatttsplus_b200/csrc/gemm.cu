@@ -15,6 +15,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 static EncodeTiledFn g_encode = nullptr;
 static std::once_flag g_once;
 static int g_init_status = 0;
+long long* g_dbg = nullptr;  // set by ctp_debug_gemm_stamps
 static uint32_t g_desc[4] = {1, 64, 2, 2};  // LBO>>4, SBO>>4, layout type, K-advance per UMMA_K (in 16-byte units)
 
 template <int BN>
@@ -76,6 +77,7 @@ static int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, long long a
                      int split_k, const GemmEpilogue& epi, cudaStream_t stream) {
     GemmShape shp;
     shp.k_blocks = (int)((K + GEMM_BK - 1) / GEMM_BK);
+    shp.dbg = g_dbg;
     shp.desc_lbo = g_desc[0]; shp.desc_sbo = g_desc[1]; shp.desc_layout = g_desc[2]; shp.desc_kadv = g_desc[3];
     if (split_k < 1) split_k = 1;
     if (split_k > shp.k_blocks) split_k = shp.k_blocks;

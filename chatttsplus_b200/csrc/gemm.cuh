@@ -33,6 +33,7 @@ struct GemmShape {
     // shared-memory matrix descriptor fields (defaults = 128B-swizzled K-major canonical layout); overridable through
     // the CTP_DESC environment variable for bring-up diagnostics only
     uint32_t desc_lbo, desc_sbo, desc_layout, desc_kadv;
+    long long* dbg;  // bring-up only: per-CTA clock64 stamps [cta][8], or null
 };
 
 constexpr int GEMM_BM = 128;
@@ -157,6 +158,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int kb0 = (int)(((long long)shp.k_blocks * blockIdx.z) / nsplit);
     const int kb1 = (int)(((long long)shp.k_blocks * (blockIdx.z + 1)) / nsplit);
     const int nkb = kb1 - kb0;
+    long long* dbg = shp.dbg ? shp.dbg + ((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
+    if (dbg && threadIdx.x == 0) dbg[0] = clock64();
 
     if (warp == 4 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -174,6 +177,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
     if (warp == 4) {
         if (lane == 0) {
@@ -195,6 +199,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int s = i % STAGES;
                 const uint32_t ph = (i / STAGES) & 1;
                 mbar_wait(&full_bar[s], ph);
+                if (dbg && i == 0) dbg[2] = clock64();
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(ring + s * S::STAGE_BYTES);
                 const uint64_t da = make_kmajor_desc(a_addr, shp.desc_lbo, shp.desc_sbo, shp.desc_layout);
@@ -208,11 +213,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above retire
             }
             umma_commit(accum_bar);  // accumulator complete
+            if (dbg) dbg[3] = clock64();
         }
     } else {
         // epilogue warps 0..3: TMEM lanes [32*warp, 32*warp+32)
         if (nkb > 0) {
             mbar_wait(accum_bar, 0);
+            if (dbg && threadIdx.x == 0) dbg[4] = clock64();
             tc_fence_after();
             const int row_g = m0 + warp * 32 + lane;
             const bool add_bias = (blockIdx.z == 0);
@@ -224,9 +231,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
     }
+    if (dbg && threadIdx.x == 0) dbg[5] = clock64();
     tc_fence_before();
     __syncthreads();
     if (warp == 5) tmem_dealloc<TMEM_COLS>(tmem_base);
+    if (dbg && threadIdx.x == 160) dbg[6] = clock64();
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -231,4 +231,4 @@ def test_lora_merge_matches_oracle():
     assert rel_rms(base, first_logits(osd)) < 5e-3
     assert rel_rms(with_lora, first_logits(merged)) < 5e-3
     assert rel_rms(first_logits(merged), first_logits(osd)) > 2e-2, "adapter too weak to test anything"
-    assert torch.equal(base, back)
+    assert torch.allclose(base, back, atol=1e-4)  # split-K fp32 atomics: summation order varies run to run
