@@ -2,9 +2,11 @@
 // C-ABI entry points are declared in include/ctp.h (each cites the reference interface it replaces).
 #include "gemm.cuh"
 #include "gpt_kernels.cuh"
+#include "step_kernel.cuh"
 
 #include <map>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -60,6 +62,14 @@ struct ctp_gpt {
     std::map<GraphKey, cudaGraphExec_t> graphs;
     std::map<GraphKey, long long> graph_nodes;
     cudaStream_t cap_stream = nullptr;
+
+    // fused persistent step kernel (v1): packed weights, step buffers, grid-barrier state
+    __half* wqkv_p = nullptr; __half* wo_p = nullptr; __half* wgu_p = nullptr; __half* wdn_p = nullptr; __half* whead_p = nullptr;
+    float* qbuf = nullptr; __half* attn_p = nullptr; __half* h_p = nullptr;
+    unsigned long long* bar = nullptr;   // [0] arrivals counter, [1] epoch (arrivals completed by previous launches)
+    int sm_count = 0, step_smem = 0, ring_slots = 0;
+    bool fused_ok = false;
+    bool use_fused = true;
 
     // host mirror of the generation state
     int B = 0, cur_len = 0, step = 0, max_new = 0;
@@ -147,6 +157,37 @@ extern "C" ctp_status ctp_gpt_create(ctp_gpt** out, const ctp_gpt_cfg* cfg) {
         for (int i = 0; i < 32; ++i) f[i] = 1.0f / powf(cfg->rope_theta, (float)(2 * i) / (float)HEAD_DIM);
         CK(cudaMemcpy(h->inv_freq, f, sizeof(f), cudaMemcpyHostToDevice));
     }
+    {   // fused step kernel resources
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, dev));
+        h->sm_count = prop.multiProcessorCount;
+        const int I = cfg->inter;
+        const int areg = (H / 64) * A_KB_BYTES + A_OVERRUN;
+        const int fixed = areg + 512 + 1024;
+        int S = ((int)prop.sharedMemPerBlockOptin - fixed) / SLOT_BYTES;
+        if (S > MAX_RING) S = MAX_RING;
+        h->ring_slots = S;
+        h->step_smem = S * SLOT_BYTES + fixed;
+        h->fused_ok = (S >= 7) && (I % 192 == 0) && (H % 64 == 0) && cfg->num_vq <= 4 && cfg->num_audio <= 640 && mb <= 32;
+        if (const char* e = getenv("CTP_DECODE_IMPL")) h->use_fused = (strcmp(e, "v0") != 0);
+        if (h->fused_ok) {
+            CK(cudaFuncSetAttribute(k_decode_step, cudaFuncAttributeMaxDynamicSharedMemorySize, h->step_smem));
+            const size_t L = cfg->n_layers;
+            const size_t F16 = ((size_t)cfg->num_vq * cfg->num_audio + 15) / 16 * 16;
+            CK(cudaMalloc(&h->wqkv_p, sizeof(__half) * L * 3 * H * H));
+            CK(cudaMalloc(&h->wo_p, sizeof(__half) * L * H * H));
+            CK(cudaMalloc(&h->wgu_p, sizeof(__half) * L * 2 * I * H));
+            CK(cudaMalloc(&h->wdn_p, sizeof(__half) * L * H * I));
+            CK(cudaMalloc(&h->whead_p, sizeof(__half) * F16 * H));
+            CK(cudaMalloc(&h->qbuf, sizeof(float) * 32 * H));
+            CK(cudaMalloc(&h->attn_p, sizeof(__half) * 32 * H + 65536));
+            CK(cudaMalloc(&h->h_p, sizeof(__half) * 32 * I + 65536));
+            CK(cudaMemset(h->attn_p, 0, sizeof(__half) * 32 * H + 65536));
+            CK(cudaMemset(h->h_p, 0, sizeof(__half) * 32 * I + 65536));
+            CK(cudaMalloc(&h->bar, sizeof(unsigned long long) * 2));
+            CK(cudaMemset(h->bar, 0, sizeof(unsigned long long) * 2));
+        }
+    }
 #undef CK
     int st = ensure_workspace(h, mb);
     if (st) { ctp_gpt_destroy(h); return (ctp_status)st; }
@@ -160,6 +201,8 @@ extern "C" void ctp_gpt_destroy(ctp_gpt* h) {
     cudaFree(h->x); cudaFree(h->xn); cudaFree(h->acc_qkv); cudaFree(h->attn); cudaFree(h->acc_gu); cudaFree(h->hmid);
     cudaFree(h->x_last); cudaFree(h->hidden); cudaFree(h->logits); cudaFree(h->kv); cudaFree(h->attn_part);
     cudaFree(h->attn_cnt); cudaFree(h->pad_len); cudaFree(h->inv_freq); cudaFree(h->st);
+    cudaFree(h->wqkv_p); cudaFree(h->wo_p); cudaFree(h->wgu_p); cudaFree(h->wdn_p); cudaFree(h->whead_p);
+    cudaFree(h->qbuf); cudaFree(h->attn_p); cudaFree(h->h_p); cudaFree(h->bar);
     if (h->st_pin) cudaFreeHost(h->st_pin);
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     delete h;
@@ -185,6 +228,28 @@ extern "C" ctp_status ctp_gpt_bind_weights(ctp_gpt* h, const ctp_gpt_weights* w)
         if ((st = make_tmap_kmajor(&m.wdown, wd, H, I, I, GEMM_BM))) return (ctp_status)st;
     }
     if ((st = make_tmap_kmajor(&h->head_map, w->head_code, (long long)c.num_vq * c.num_audio, H, H, GEMM_BM))) return (ctp_status)st;
+    if (h->fused_ok) {   // per-item pre-swizzled blobs for the fused step kernel (one bulk copy fills a ring slot)
+        const int nH = c.n_heads, nkbH = (int)(H / 64), nkbI = (int)(I / 64);
+        for (int l = 0; l < c.n_layers; ++l) {
+            const __half* wqkv = (const __half*)w->wqkv + (size_t)l * 3 * H * H;
+            const __half* wo = (const __half*)w->wo + (size_t)l * H * H;
+            const __half* wgu = (const __half*)w->wgu + (size_t)l * 2 * I * H;
+            const __half* wd = (const __half*)w->wdown + (size_t)l * H * I;
+            int n_items = 3 * nH * 4;
+            k_pack_weights<<<n_items * nkbH, 128>>>(wqkv, h->wqkv_p + (size_t)l * 3 * H * H, PACK_QKV, (int)(3 * H), (int)H, nH, (int)I, n_items, 16, nkbH, 1);
+            n_items = (int)(H / 16);
+            k_pack_weights<<<n_items * nkbH, 128>>>(wo, h->wo_p + (size_t)l * H * H, PACK_PLAIN16, (int)H, (int)H, nH, (int)I, n_items, 16, nkbH, 1);
+            n_items = (int)(I / 24);
+            k_pack_weights<<<n_items * nkbH, 384>>>(wgu, h->wgu_p + (size_t)l * 2 * I * H, PACK_GU, (int)(2 * I), (int)H, nH, (int)I, n_items, 48, nkbH, 1);
+            n_items = (int)(H / 16) * DN_KSPLIT;
+            k_pack_weights<<<n_items * (nkbI / DN_KSPLIT), 128>>>(wd, h->wdn_p + (size_t)l * H * I, PACK_DN, (int)H, (int)I, nH, (int)I, n_items, 16, nkbI / DN_KSPLIT, DN_KSPLIT);
+        }
+        const int F = c.num_vq * c.num_audio;
+        const int n_items = (F + 15) / 16;
+        k_pack_weights<<<n_items * nkbH, 128>>>((const __half*)w->head_code, h->whead_p, PACK_PLAIN16, F, (int)H, nH, (int)I, n_items, 16, nkbH, 1);
+        CTP_CUDA_OK(cudaGetLastError());
+        CTP_CUDA_OK(cudaDeviceSynchronize());
+    }
     h->w = *w;
     h->bound = true;
     // weights are baked into captured graphs as tensor maps
@@ -231,6 +296,24 @@ static int launch_heads(ctp_gpt* h, int B, cudaStream_t s) {
     const int m_tiles = (F + GEMM_BM - 1) / GEMM_BM;
     GemmEpilogue e = epi_swap_atomic(h->logits, F, B, F);
     return gemm_launch_maps(h->head_map, am.xn, F, B, c.hidden, bn, split_for(c.hidden / 64, m_tiles), e, s);
+}
+
+// Fused path: ONE cooperative launch per decode step (step_kernel.cuh).
+static int run_decode_fused(ctp_gpt* h, int B, const int* ids_ext, int do_sample, cudaStream_t s) {
+    const ctp_gpt_cfg& c = h->cfg;
+    StepParams p{};
+    p.L = c.n_layers; p.H = c.hidden; p.nH = c.n_heads; p.I = c.inter; p.num_vq = c.num_vq; p.num_audio = c.num_audio; p.B = B;
+    p.max_seq = c.max_seq; p.eps = c.rms_eps; p.ring_slots = h->ring_slots; p.do_sample = do_sample;
+    p.wqkv_p = h->wqkv_p; p.wo_p = h->wo_p; p.wgu_p = h->wgu_p; p.wdn_p = h->wdn_p; p.whead_p = h->whead_p;
+    p.ln1 = h->w.ln1; p.ln2 = h->w.ln2; p.norm_f = h->w.norm_f; p.emb_code = (const __half*)h->w.emb_code;
+    p.x = h->x; p.q = h->qbuf; p.attn_p = h->attn_p; p.h_p = h->h_p; p.kv = h->kv; p.kv_plane = (long long)h->kv_plane_elems();
+    p.logits = h->logits; p.hidden = h->hidden; p.st = h->st; p.pad_len = h->pad_len; p.inv_freq = h->inv_freq; p.ids_ext = ids_ext;
+    p.bar = h->bar; p.bar_epoch = h->bar + 1;
+    void* args[] = {&p};
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)k_decode_step, dim3(h->sm_count), dim3(STEP_THREADS), args, (size_t)h->step_smem, s);
+    ctp_count_launch();
+    if (e != cudaSuccess) { ctp_set_error("fused decode step launch failed: %s", cudaGetErrorString(e)); return CTP_ERR_CUDA; }
+    return CTP_OK;
 }
 
 // One decode trunk step for B sequences (ids_ext == nullptr -> codes of the previous sample step).
@@ -413,7 +496,9 @@ extern "C" ctp_status ctp_gpt_decode_step(ctp_gpt* h, const int32_t* ids, ctp_st
     CTP_REQUIRE(h && h->bound && h->have_bufs, "decode_step: call prefill first");
     CTP_REQUIRE(h->cur_len + 1 <= h->cfg.max_seq, "decode_step: KV cache full (%d slots)", h->cfg.max_seq);
     CTP_REQUIRE(ids != nullptr || h->step >= 1, "decode_step: no sampled codes yet and no ids given");
-    int st = run_decode_trunk(h, h->B, nsplit_for(h, h->B, h->cur_len + 1), ids, (cudaStream_t)stream);
+    int st;
+    if (h->fused_ok && h->use_fused && h->B <= 32) st = run_decode_fused(h, h->B, ids, 0, (cudaStream_t)stream);
+    else st = run_decode_trunk(h, h->B, nsplit_for(h, h->B, h->cur_len + 1), ids, (cudaStream_t)stream);
     if (st) return (ctp_status)st;
     h->cur_len += 1;
     return CTP_OK;
@@ -492,12 +577,17 @@ extern "C" ctp_status ctp_gpt_generate(ctp_gpt* h, const ctp_sample_cfg* cfg, in
     CTP_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     bool pending = false;
     h->st_pin->all_done = 0;
+    const bool fused = h->fused_ok && h->use_fused && h->B <= 32;
     for (int it = 0; it < iters; ++it) {
-        cudaGraphExec_t g;
-        if ((st = get_graph(h, h->B, nsplit_for(h, h->B, h->cur_len + 1), &g))) { cudaEventDestroy(ev); return (ctp_status)st; }
-        ctp_count_launch((int)h->graph_nodes[GraphKey{h->B, nsplit_for(h, h->B, h->cur_len + 1)}]);
-        cudaError_t e = cudaGraphLaunch(g, s);
-        if (e != cudaSuccess) { ctp_set_error("graph launch: %s", cudaGetErrorString(e)); cudaEventDestroy(ev); return CTP_ERR_CUDA; }
+        if (fused) {
+            if ((st = run_decode_fused(h, h->B, nullptr, 1, s))) { cudaEventDestroy(ev); return (ctp_status)st; }
+        } else {
+            cudaGraphExec_t g;
+            if ((st = get_graph(h, h->B, nsplit_for(h, h->B, h->cur_len + 1), &g))) { cudaEventDestroy(ev); return (ctp_status)st; }
+            ctp_count_launch((int)h->graph_nodes[GraphKey{h->B, nsplit_for(h, h->B, h->cur_len + 1)}]);
+            cudaError_t e = cudaGraphLaunch(g, s);
+            if (e != cudaSuccess) { ctp_set_error("graph launch: %s", cudaGetErrorString(e)); cudaEventDestroy(ev); return CTP_ERR_CUDA; }
+        }
         h->cur_len += 1; h->step += 1; done += 1;
         if ((it + 1) % check_every == 0 && it + 1 < iters) {
             // lagged poll: look at the flag copied after the PREVIOUS chunk while this chunk is already queued

@@ -439,12 +439,15 @@ __device__ __forceinline__ uint32_t philox_mix(uint64_t seed, uint32_t a, uint32
     return c0;
 }
 
-// blockDim = 32 * num_vq; block b handles rows b*num_vq .. b*num_vq + num_vq-1 (one warp each).
-__global__ void k_sample(SampleArgs a) {
-    extern __shared__ float s_scores[];  // [num_vq][vocab_pad]
-    __shared__ int s_choice[MAX_VQ];
+// One warp per (b, q) row: warps 0..num_vq-1 of the calling block handle rows b*num_vq + warp.
+// FUSED: called from the persistent step kernel (compute warps only: named barrier 1 over 128 threads, n_blocks = B).
+template <bool FUSED>
+__device__ __forceinline__ void sample_block(const SampleArgs& a, const int b, const int n_blocks, float* s_scores, int* s_choice) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x;
+    if (warp >= a.num_vq) {
+        if (a.st) { if (FUSED) asm volatile("bar.sync 1, 128;" ::: "memory"); else __syncthreads(); }
+        return;
+    }
     const int row = b * a.num_vq + warp;
     const int V = a.vocab;
     const int vpad = (V + 31) & ~31;
@@ -459,7 +462,7 @@ __global__ void k_sample(SampleArgs a) {
     // 1. temperature (gpt.py:469)
     const float inv_t = 1.0f / cfg.temperature[warp];
     const float* lg = a.logits + (long long)row * V;
-    for (int v = lane; v < V; v += 32) sc[v] = lg[v] * inv_t;
+    for (int v = lane; v < V; v += 32) sc[v] = (FUSED ? __ldcg(lg + v) : lg[v]) * inv_t;
     __syncwarp();
     // 2. windowed repetition penalty (processors.py:18-34)
     if (cfg.rep_penalty != 1.0f && row < cfg.rep_max_ids) {
@@ -564,7 +567,7 @@ __global__ void k_sample(SampleArgs a) {
     if (a.next_ids && lane == 0) a.next_ids[row] = chosen;
     if (a.st) {
         if (lane == 0) s_choice[warp] = chosen;
-        __syncthreads();
+        if (FUSED) asm volatile("bar.sync 1, 128;" ::: "memory"); else __syncthreads();
         if (threadIdx.x == 0) {
             GenState* st = a.st;
             bool eos = false;
@@ -577,17 +580,25 @@ __global__ void k_sample(SampleArgs a) {
             if (!fin) st->end_idx[b] += 1;                   // gpt.py:530-531
             __threadfence();
             const int t = atomicAdd(&st->ticket, 1);
-            if (t == (int)gridDim.x - 1) {                   // last block: global bookkeeping
+            if (t == n_blocks - 1) {                   // last block: global bookkeeping
                 st->ticket = 0;
                 int all = 1;
                 __threadfence();
                 const volatile unsigned char* fin_v = st->finish;
-                for (int i = 0; i < (int)gridDim.x; ++i) all &= (fin_v[i] != 0);
+                for (int i = 0; i < n_blocks; ++i) all &= (fin_v[i] != 0);
                 st->all_done = all;
                 st->step = step + 1;
+                if (FUSED) { st->cur_len += 1; }
             }
         }
     }
+}
+
+// blockDim = 32 * num_vq; block b handles rows b*num_vq .. b*num_vq + num_vq-1.
+__global__ void k_sample(SampleArgs a) {
+    extern __shared__ float s_scores_dyn[];  // [num_vq][vocab_pad]
+    __shared__ int s_choice[MAX_VQ];
+    sample_block<false>(a, blockIdx.x, gridDim.x, s_scores_dyn, s_choice);
 }
 
 // cur_len += 1 after a trunk step (the new token's K/V now occupy slot cur_len)
