@@ -74,8 +74,9 @@ int make_tmap_kmajor(CUtensorMap* out, const void* base, long long rows, long lo
 
 template <int BN>
 static int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, long long a_rows, long long b_rows, long long K,
-                     int split_k, const GemmEpilogue& epi, cudaStream_t stream) {
+                     int split_k, const GemmEpilogue& epi, cudaStream_t stream, const void* pf_ptr, unsigned long long pf_bytes) {
     GemmShape shp;
+    shp.pf_ptr = pf_ptr; shp.pf_bytes = pf_bytes;
     shp.k_blocks = (int)((K + GEMM_BK - 1) / GEMM_BK);
     shp.dbg = g_dbg;
     shp.desc_lbo = g_desc[0]; shp.desc_sbo = g_desc[1]; shp.desc_layout = g_desc[2]; shp.desc_kadv = g_desc[3];
@@ -97,14 +98,14 @@ static int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, long long a
 }
 
 int gemm_launch_maps(const CUtensorMap& tmA, const CUtensorMap& tmB, long long a_rows, long long b_rows, long long K,
-                     int block_n, int split_k, const GemmEpilogue& epi, cudaStream_t stream) {
+                     int block_n, int split_k, const GemmEpilogue& epi, cudaStream_t stream, const void* pf_ptr, unsigned long long pf_bytes) {
     int st = gemm_init();
     if (st) return st;
     switch (block_n) {
-        case 32: return launch_bn<32>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream);
-        case 64: return launch_bn<64>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream);
-        case 128: return launch_bn<128>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream);
-        case 256: return launch_bn<256>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream);
+        case 32: return launch_bn<32>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream, pf_ptr, pf_bytes);
+        case 64: return launch_bn<64>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream, pf_ptr, pf_bytes);
+        case 128: return launch_bn<128>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream, pf_ptr, pf_bytes);
+        case 256: return launch_bn<256>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream, pf_ptr, pf_bytes);
         default: ctp_set_error("gemm: unsupported block_n %d", block_n); return CTP_ERR_INVALID;
     }
 }

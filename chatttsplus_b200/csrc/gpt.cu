@@ -69,7 +69,18 @@ struct ctp_gpt {
     unsigned long long* bar = nullptr;   // [0] arrivals counter, [1] epoch (arrivals completed by previous launches)
     int sm_count = 0, step_smem = 0, ring_slots = 0;
     bool fused_ok = false;
-    bool use_fused = true;
+    bool use_fused = false;  // measured (profiles/README.md): the per-op graph path is faster today; CTP_DECODE_IMPL=fused selects the fused kernel
+    // lanes: the batch is split into K contiguous row slices, each running its own fused-step kernel on its own stream over
+    // sm_count/K SMs.  The fused step is a latency chain (DRAM 8 %, issue-active 16 % at K=1, profiles/README.md): independent
+    // lanes overlap each other's grid barriers and dependent sequences.
+    static constexpr int MAX_LANES = 8;
+    int n_lanes = 1;
+    struct Lane {
+        float* x = nullptr; float* q = nullptr; __half* attn_p = nullptr; __half* h_p = nullptr;
+        unsigned long long* bar = nullptr; GenState* st = nullptr; GenState* st_pin = nullptr;
+        cudaStream_t stream = nullptr; cudaEvent_t done = nullptr;
+    } lanes[MAX_LANES];
+    cudaEvent_t fork_ev = nullptr;
 
     // host mirror of the generation state
     int B = 0, cur_len = 0, step = 0, max_new = 0;
@@ -162,14 +173,14 @@ extern "C" ctp_status ctp_gpt_create(ctp_gpt** out, const ctp_gpt_cfg* cfg) {
         CK(cudaGetDeviceProperties(&prop, dev));
         h->sm_count = prop.multiProcessorCount;
         const int I = cfg->inter;
-        const int areg = (H / 64) * A_KB_BYTES + A_OVERRUN;
+        const int areg = (H / 64) * A_KB_BYTES + DBUF_BYTES;
         const int fixed = areg + 512 + 1024;
         int S = ((int)prop.sharedMemPerBlockOptin - fixed) / SLOT_BYTES;
         if (S > MAX_RING) S = MAX_RING;
         h->ring_slots = S;
         h->step_smem = S * SLOT_BYTES + fixed;
         h->fused_ok = (S >= 7) && (I % 192 == 0) && (H % 64 == 0) && cfg->num_vq <= 4 && cfg->num_audio <= 640 && mb <= 32;
-        if (const char* e = getenv("CTP_DECODE_IMPL")) h->use_fused = (strcmp(e, "v0") != 0);
+        if (const char* e = getenv("CTP_DECODE_IMPL")) h->use_fused = (strcmp(e, "fused") == 0);
         if (h->fused_ok) {
             CK(cudaFuncSetAttribute(k_decode_step, cudaFuncAttributeMaxDynamicSharedMemorySize, h->step_smem));
             const size_t L = cfg->n_layers;
@@ -186,6 +197,26 @@ extern "C" ctp_status ctp_gpt_create(ctp_gpt** out, const ctp_gpt_cfg* cfg) {
             CK(cudaMemset(h->h_p, 0, sizeof(__half) * 32 * I + 65536));
             CK(cudaMalloc(&h->bar, sizeof(unsigned long long) * 2));
             CK(cudaMemset(h->bar, 0, sizeof(unsigned long long) * 2));
+            h->n_lanes = 1;
+            if (const char* e = getenv("CTP_LANES")) h->n_lanes = atoi(e);
+            if (h->n_lanes < 1) h->n_lanes = 1;
+            if (h->n_lanes > ctp_gpt::MAX_LANES) h->n_lanes = ctp_gpt::MAX_LANES;
+            CK(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
+            for (int k = 0; k < h->n_lanes; ++k) {
+                ctp_gpt::Lane& ln = h->lanes[k];
+                CK(cudaMalloc(&ln.x, sizeof(float) * 32 * H));
+                CK(cudaMalloc(&ln.q, sizeof(float) * 32 * H));
+                CK(cudaMalloc(&ln.attn_p, sizeof(__half) * 32 * H));
+                CK(cudaMalloc(&ln.h_p, sizeof(__half) * 32 * I));
+                CK(cudaMemset(ln.attn_p, 0, sizeof(__half) * 32 * H));
+                CK(cudaMemset(ln.h_p, 0, sizeof(__half) * 32 * I));
+                CK(cudaMalloc(&ln.bar, sizeof(unsigned long long) * 2));
+                CK(cudaMemset(ln.bar, 0, sizeof(unsigned long long) * 2));
+                CK(cudaMalloc(&ln.st, sizeof(GenState)));
+                CK(cudaMallocHost(&ln.st_pin, sizeof(GenState)));
+                CK(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+                CK(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+            }
         }
     }
 #undef CK
@@ -203,6 +234,14 @@ extern "C" void ctp_gpt_destroy(ctp_gpt* h) {
     cudaFree(h->attn_cnt); cudaFree(h->pad_len); cudaFree(h->inv_freq); cudaFree(h->st);
     cudaFree(h->wqkv_p); cudaFree(h->wo_p); cudaFree(h->wgu_p); cudaFree(h->wdn_p); cudaFree(h->whead_p);
     cudaFree(h->qbuf); cudaFree(h->attn_p); cudaFree(h->h_p); cudaFree(h->bar);
+    for (int k = 0; k < ctp_gpt::MAX_LANES; ++k) {
+        ctp_gpt::Lane& ln = h->lanes[k];
+        cudaFree(ln.x); cudaFree(ln.q); cudaFree(ln.attn_p); cudaFree(ln.h_p); cudaFree(ln.bar); cudaFree(ln.st);
+        if (ln.st_pin) cudaFreeHost(ln.st_pin);
+        if (ln.stream) cudaStreamDestroy(ln.stream);
+        if (ln.done) cudaEventDestroy(ln.done);
+    }
+    if (h->fork_ev) cudaEventDestroy(h->fork_ev);
     if (h->st_pin) cudaFreeHost(h->st_pin);
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     delete h;
@@ -298,19 +337,40 @@ static int launch_heads(ctp_gpt* h, int B, cudaStream_t s) {
     return gemm_launch_maps(h->head_map, am.xn, F, B, c.hidden, bn, split_for(c.hidden / 64, m_tiles), e, s);
 }
 
+// bring-up hook (not in include/ctp.h): device buffer [n_cta][128][2] of clock64 stamps around every grid barrier
+static long long* g_step_dbg = nullptr;
+extern "C" __attribute__((visibility("default"))) void ctp_debug_step_stamps(long long* buf) { g_step_dbg = buf; }
+
 // Fused path: ONE cooperative launch per decode step (step_kernel.cuh).
+static int run_decode_fused_lane(ctp_gpt* h, int b0, int Bk, int grid, float* x, float* q, __half* attn_p, __half* h_p,
+                                 unsigned long long* bar, GenState* st, const int* ids_ext, int do_sample, cudaStream_t s);
+
 static int run_decode_fused(ctp_gpt* h, int B, const int* ids_ext, int do_sample, cudaStream_t s) {
+    return run_decode_fused_lane(h, 0, B, h->sm_count, h->x, h->qbuf, h->attn_p, h->h_p, h->bar, h->st, ids_ext, do_sample, s);
+}
+
+static int run_decode_fused_lane(ctp_gpt* h, int b0, int B, int grid, float* x, float* q, __half* attn_p, __half* h_p,
+                                 unsigned long long* bar, GenState* st, const int* ids_ext, int do_sample, cudaStream_t s) {
     const ctp_gpt_cfg& c = h->cfg;
     StepParams p{};
+    p.b0 = b0;
     p.L = c.n_layers; p.H = c.hidden; p.nH = c.n_heads; p.I = c.inter; p.num_vq = c.num_vq; p.num_audio = c.num_audio; p.B = B;
     p.max_seq = c.max_seq; p.eps = c.rms_eps; p.ring_slots = h->ring_slots; p.do_sample = do_sample;
     p.wqkv_p = h->wqkv_p; p.wo_p = h->wo_p; p.wgu_p = h->wgu_p; p.wdn_p = h->wdn_p; p.whead_p = h->whead_p;
     p.ln1 = h->w.ln1; p.ln2 = h->w.ln2; p.norm_f = h->w.norm_f; p.emb_code = (const __half*)h->w.emb_code;
-    p.x = h->x; p.q = h->qbuf; p.attn_p = h->attn_p; p.h_p = h->h_p; p.kv = h->kv; p.kv_plane = (long long)h->kv_plane_elems();
-    p.logits = h->logits; p.hidden = h->hidden; p.st = h->st; p.pad_len = h->pad_len; p.inv_freq = h->inv_freq; p.ids_ext = ids_ext;
-    p.bar = h->bar; p.bar_epoch = h->bar + 1;
+    p.x = x; p.q = q; p.attn_p = attn_p; p.h_p = h_p; p.kv = h->kv; p.kv_plane = (long long)h->kv_plane_elems();
+    p.logits = h->logits; p.hidden = h->hidden; p.st = st; p.pad_len = h->pad_len; p.inv_freq = h->inv_freq; p.ids_ext = ids_ext;
+    p.bar = bar; p.bar_epoch = bar + 1; p.dbg = g_step_dbg;
     void* args[] = {&p};
-    cudaError_t e = cudaLaunchCooperativeKernel((void*)k_decode_step, dim3(h->sm_count), dim3(STEP_THREADS), args, (size_t)h->step_smem, s);
+    cudaError_t e;
+    if (grid == h->sm_count) {
+        e = cudaLaunchCooperativeKernel((void*)k_decode_step, dim3(grid), dim3(STEP_THREADS), args, (size_t)h->step_smem, s);
+    } else {
+        // lanes: cooperative launches do not overlap each other; a plain launch is safe because the lanes together never exceed
+        // one CTA per SM (the kernel's shared-memory footprint allows exactly one), so every CTA of every lane is resident
+        k_decode_step<<<grid, STEP_THREADS, (size_t)h->step_smem, s>>>(p);
+        e = cudaGetLastError();
+    }
     ctp_count_launch();
     if (e != cudaSuccess) { ctp_set_error("fused decode step launch failed: %s", cudaGetErrorString(e)); return CTP_ERR_CUDA; }
     return CTP_OK;
@@ -332,7 +392,8 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
         LAUNCH_OK();
         {   // q,k,v projections as one GEMM (llama.py:619-621), weights are the M operand
             GemmEpilogue e = epi_swap_atomic(h->acc_qkv, 3 * H, B, 3 * H);
-            if ((st = gemm_launch_maps(h->lmaps[l].wqkv, am.xn, 3 * H, B, H, bn, split_for(H / 64, 3 * H / GEMM_BM), e, s))) return st;
+            if ((st = gemm_launch_maps(h->lmaps[l].wqkv, am.xn, 3 * H, B, H, bn, split_for(H / 64, 3 * H / GEMM_BM), e, s,
+                                       (const __half*)h->w.wo + (size_t)l * H * H, sizeof(__half) * (size_t)H * H))) return st;
         }
         AttnDecArgs aa{};
         aa.qkv = h->acc_qkv; aa.kcache = h->kplane(l); aa.vcache = h->vplane(l); aa.out = h->attn; aa.part = h->attn_part;
@@ -342,7 +403,8 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
         LAUNCH_OK();
         {   // o_proj accumulated straight into the residual stream (llama.py:663-666,737)
             GemmEpilogue e = epi_swap_atomic(h->x, H, B, H);
-            if ((st = gemm_launch_maps(h->lmaps[l].wo, am.attn, H, B, H, bn, split_for(H / 64, (H + GEMM_BM - 1) / GEMM_BM), e, s))) return st;
+            if ((st = gemm_launch_maps(h->lmaps[l].wo, am.attn, H, B, H, bn, split_for(H / 64, (H + GEMM_BM - 1) / GEMM_BM), e, s,
+                                       (const __half*)h->w.wgu + (size_t)l * 2 * I * H, sizeof(__half) * (size_t)2 * I * H))) return st;
         }
         NormArgs nb{};
         nb.x = h->x; nb.w = h->w.ln2 + (size_t)l * H; nb.xn = h->xn; nb.H = H; nb.eps = c.rms_eps;
@@ -351,7 +413,8 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
         LAUNCH_OK();
         {   // gate_proj | up_proj (llama.py:214)
             GemmEpilogue e = epi_swap_atomic(h->acc_gu, 2 * I, B, 2 * I);
-            if ((st = gemm_launch_maps(h->lmaps[l].wgu, am.xn, 2 * I, B, H, bn, split_for(H / 64, 2 * I / GEMM_BM), e, s))) return st;
+            if ((st = gemm_launch_maps(h->lmaps[l].wgu, am.xn, 2 * I, B, H, bn, split_for(H / 64, 2 * I / GEMM_BM), e, s,
+                                       (const __half*)h->w.wdown + (size_t)l * H * I, sizeof(__half) * (size_t)H * I))) return st;
         }
         {
             const long long total = (long long)B * I;
@@ -360,7 +423,9 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
         }
         {   // down_proj accumulated into the residual stream (llama.py:214,745)
             GemmEpilogue e = epi_swap_atomic(h->x, H, B, H);
-            if ((st = gemm_launch_maps(h->lmaps[l].wdown, am.hmid, H, B, I, bn, split_for(I / 64, (H + GEMM_BM - 1) / GEMM_BM), e, s))) return st;
+            const void* nxt = (l + 1 < c.n_layers) ? (const void*)((const __half*)h->w.wqkv + (size_t)(l + 1) * 3 * H * H) : h->w.head_code;
+            const size_t nxt_bytes = (l + 1 < c.n_layers) ? sizeof(__half) * (size_t)3 * H * H : sizeof(__half) * (size_t)c.num_vq * c.num_audio * H;
+            if ((st = gemm_launch_maps(h->lmaps[l].wdown, am.hmid, H, B, I, bn, split_for(I / 64, (H + GEMM_BM - 1) / GEMM_BM), e, s, nxt, nxt_bytes))) return st;
         }
     }
     // final norm (llama.py:1002) -> hidden state of this step (gpt.py:422-423) + operand of the heads
@@ -578,6 +643,59 @@ extern "C" ctp_status ctp_gpt_generate(ctp_gpt* h, const ctp_sample_cfg* cfg, in
     bool pending = false;
     h->st_pin->all_done = 0;
     const bool fused = h->fused_ok && h->use_fused && h->B <= 32;
+    int K = fused ? h->n_lanes : 1;
+    while (K > 1 && (h->B < K || h->sm_count / K < 8)) K /= 2;
+    if (fused && K > 1) {
+        // ---- K independent row slices, each with its own generation state, stream and share of the SMs
+        cudaEventDestroy(ev);
+        int b0s[ctp_gpt::MAX_LANES], bks[ctp_gpt::MAX_LANES];
+        for (int k = 0; k < K; ++k) { b0s[k] = (int)((long long)h->B * k / K); bks[k] = (int)((long long)h->B * (k + 1) / K) - b0s[k]; }
+        CTP_CUDA_OK(cudaMemcpyAsync(h->st_pin, h->st, sizeof(GenState), cudaMemcpyDeviceToHost, s));
+        CTP_CUDA_OK(cudaStreamSynchronize(s));
+        for (int k = 0; k < K; ++k) {
+            *h->lanes[k].st_pin = *h->st_pin;
+            h->lanes[k].st_pin->ticket = 0;
+            h->lanes[k].st_pin->all_done = 0;
+            CTP_CUDA_OK(cudaMemcpyAsync(h->lanes[k].st, h->lanes[k].st_pin, sizeof(GenState), cudaMemcpyHostToDevice, s));
+        }
+        CTP_CUDA_OK(cudaEventRecord(h->fork_ev, s));
+        for (int k = 0; k < K; ++k) CTP_CUDA_OK(cudaStreamWaitEvent(h->lanes[k].stream, h->fork_ev, 0));
+        const int grid = h->sm_count / K;
+        int launched = 0;
+        bool stop = false;
+        for (int it = 0; it < iters && !stop; ++it) {
+            for (int k = 0; k < K; ++k) {
+                ctp_gpt::Lane& ln = h->lanes[k];
+                if ((st = run_decode_fused_lane(h, b0s[k], bks[k], grid, ln.x, ln.q, ln.attn_p, ln.h_p, ln.bar, ln.st, nullptr, 1, ln.stream))) return (ctp_status)st;
+            }
+            ++launched;
+            if ((it + 1) % check_every == 0 && it + 1 < iters) {
+                // poll: every lane reports whether all of ITS rows have finished (small sync every check_every steps)
+                bool all = true;
+                for (int k = 0; k < K; ++k) {
+                    cudaMemcpyAsync(&h->lanes[k].st_pin->all_done, reinterpret_cast<char*>(h->lanes[k].st) + offsetof(GenState, all_done),
+                                    sizeof(int), cudaMemcpyDeviceToHost, h->lanes[k].stream);
+                }
+                for (int k = 0; k < K; ++k) { cudaStreamSynchronize(h->lanes[k].stream); all = all && h->lanes[k].st_pin->all_done; }
+                if (all) stop = true;
+            }
+        }
+        for (int k = 0; k < K; ++k) {
+            CTP_CUDA_OK(cudaEventRecord(h->lanes[k].done, h->lanes[k].stream));
+            CTP_CUDA_OK(cudaStreamWaitEvent(s, h->lanes[k].done, 0));
+        }
+        // fold the lane counters back into the handle's state (all lanes advanced by `launched` steps)
+        h->cur_len += launched; h->step += launched;
+        {
+            int vals[2] = {h->cur_len, h->step};
+            CTP_CUDA_OK(cudaMemcpyAsync(reinterpret_cast<char*>(h->st) + offsetof(GenState, cur_len), &vals[0], sizeof(int), cudaMemcpyHostToDevice, s));
+            CTP_CUDA_OK(cudaMemcpyAsync(reinterpret_cast<char*>(h->st) + offsetof(GenState, step), &vals[1], sizeof(int), cudaMemcpyHostToDevice, s));
+            CTP_CUDA_OK(cudaStreamSynchronize(s));
+        }
+        CTP_CUDA_OK(cudaGetLastError());
+        if (steps_done) *steps_done = launched;
+        return CTP_OK;
+    }
     for (int it = 0; it < iters; ++it) {
         if (fused) {
             if ((st = run_decode_fused(h, h->B, nullptr, 1, s))) { cudaEventDestroy(ev); return (ctp_status)st; }

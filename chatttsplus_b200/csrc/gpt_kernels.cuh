@@ -422,6 +422,7 @@ struct SampleArgs {
     int* next_ids;         // [rows] or null
     float* probs_out;      // [rows][vocab] or null
     GenState* st;          // generation mode: write ids_buf / finish / end_idx
+    int b0;                // lanes: first global row handled by this launch (ticket / all_done cover rows [b0, b0 + n_blocks))
 };
 
 __device__ __forceinline__ uint32_t philox_mix(uint64_t seed, uint32_t a, uint32_t b) {
@@ -440,12 +441,12 @@ __device__ __forceinline__ uint32_t philox_mix(uint64_t seed, uint32_t a, uint32
 }
 
 // One warp per (b, q) row: warps 0..num_vq-1 of the calling block handle rows b*num_vq + warp.
-// FUSED: called from the persistent step kernel (compute warps only: named barrier 1 over 128 threads, n_blocks = B).
+// FUSED: called from the persistent step kernel (compute warps only: named barrier 1 over 256 threads, n_blocks = B).
 template <bool FUSED>
 __device__ __forceinline__ void sample_block(const SampleArgs& a, const int b, const int n_blocks, float* s_scores, int* s_choice) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp >= a.num_vq) {
-        if (a.st) { if (FUSED) asm volatile("bar.sync 1, 128;" ::: "memory"); else __syncthreads(); }
+        if (a.st) { if (FUSED) asm volatile("bar.sync 1, 256;" ::: "memory"); else __syncthreads(); }
         return;
     }
     const int row = b * a.num_vq + warp;
@@ -567,7 +568,7 @@ __device__ __forceinline__ void sample_block(const SampleArgs& a, const int b, c
     if (a.next_ids && lane == 0) a.next_ids[row] = chosen;
     if (a.st) {
         if (lane == 0) s_choice[warp] = chosen;
-        if (FUSED) asm volatile("bar.sync 1, 128;" ::: "memory"); else __syncthreads();
+        if (FUSED) asm volatile("bar.sync 1, 256;" ::: "memory"); else __syncthreads();
         if (threadIdx.x == 0) {
             GenState* st = a.st;
             bool eos = false;
@@ -585,7 +586,7 @@ __device__ __forceinline__ void sample_block(const SampleArgs& a, const int b, c
                 int all = 1;
                 __threadfence();
                 const volatile unsigned char* fin_v = st->finish;
-                for (int i = 0; i < n_blocks; ++i) all &= (fin_v[i] != 0);
+                for (int i = 0; i < n_blocks; ++i) all &= (fin_v[a.b0 + i] != 0);
                 st->all_done = all;
                 st->step = step + 1;
                 if (FUSED) { st->cur_len += 1; }

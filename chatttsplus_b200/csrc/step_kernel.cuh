@@ -8,10 +8,12 @@
 //                      KV-cache tiles — into a ring of 16 KB shared-memory slots.  Weights and old KV do not depend on
 //                      this step's activations, so the producer runs ahead across phase boundaries: HBM keeps
 //                      streaming while the other warps sit in a grid barrier.
-//   warp 5 (one lane)  MMA issuer: tcgen05.mma with the 32 batch rows as the (padded) M=128 operand and 16..48 weight
-//                      rows as the N operand, full K per CTA -> no split-K atomics except the 512-element down_proj tile.
-//   warps 0-3          norm prologues, RoPE / SiLU / residual epilogues (TMEM -> registers), decode attention over the
-//                      KV tiles in the ring, the sampler; thread 0 runs the grid barrier between phases.
+//   warps 0-3          per-CTA GEMM tiles D[32 batch rows x 16..48 weight rows] over the full K with warp-level
+//                      mma.sync (m16n8k16, fp16 in / fp32 accumulate): at M=32 the 128-row tcgen05 atom costs ~128 cycles per
+//                      instruction for 16-48 useful weight rows (measured, profiles/README.md), so the decode step uses HMMA
+//                      and tcgen05 is kept for the M>=4096 GEMMs (prefill, vocoder).  Also: norm prologues, RoPE / SiLU /
+//                      residual epilogues, decode attention over the KV tiles in the ring, the sampler; thread 0 runs
+//                      the grid barrier between phases.
 //
 // Weight blobs are pre-packed at bind time into the exact shared-memory image the UMMA descriptor expects
 // (K-major, 128-byte swizzle, one contiguous blob per work item), so a slot is filled by a single bulk copy.
@@ -20,16 +22,23 @@
 
 namespace ctp {
 
-constexpr int STEP_THREADS = 192;
+constexpr int NCOMP = 256;                 // compute threads (8 warps); warp 8 is the producer
+constexpr int STEP_THREADS = NCOMP + 32;
 constexpr int SLOT_BYTES = 16384;
 constexpr int MAX_RING = 12;
 constexpr int A_KB_BYTES = 4096;      // one activation k-block: 32 rows x 128 B (the MMA reads 128 rows = 16 KB from it)
-constexpr int A_OVERRUN = 12288;
+constexpr int A_OVERRUN = 0;
+constexpr int DBUF_BYTES = 2 * 32 * 52 * 4;   // two K-half partial tiles [32][48 + 4 pad] fp32 between MMA fragments and epilogue
 constexpr int DN_KSPLIT = 3;
+constexpr int TMEM_COLS_STEP = 256;
+// consecutive tcgen05.mma into ONE accumulator tile serialise on the accumulate dependency (~125+ cycles each, measured);
+// the K loop therefore rotates over NCHAIN independent accumulators that the epilogue sums
+__host__ __device__ constexpr int n_chains(int N) { return N <= 16 ? 8 : 4; }
 
 struct StepParams {
     // dims
     int L, H, nH, I, num_vq, num_audio, B, max_seq;
+    int b0;                // first global batch row of this lane (B = rows of the lane); KV / ids / logits use b0 + b
     float eps;
     int ring_slots;        // S
     int do_sample;         // 1: run the sampler phase (generate loop); 0: trunk + heads only (teacher-forced step)
@@ -56,6 +65,7 @@ struct StepParams {
     const int* ids_ext;    // teacher-forced ids [B][num_vq] or null
     unsigned long long* bar;        // grid barrier counter (monotonic)
     unsigned long long* bar_epoch;  // number of barriers completed by all previous launches
+    long long* dbg;                 // bring-up: [cta][barrier][2] clock64 at arrive / leave, or null
 };
 
 __device__ __forceinline__ uint64_t ld_acquire_u64(const unsigned long long* p) {
@@ -64,42 +74,47 @@ __device__ __forceinline__ uint64_t ld_acquire_u64(const unsigned long long* p) 
     return v;
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-__device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 struct StepCtx {
     uint8_t* ring;
     uint8_t* areg;           // activation operand region (after the ring)
     uint64_t* full;
     uint64_t* empty;
-    uint64_t* a_ready;       // compute warps -> MMA: activation operand written (norm phases)
-    uint64_t* acc_ready;     // MMA -> epilogue
-    uint64_t* acc_free;      // epilogue -> MMA
-    uint32_t tmem;
     int S;
     int cta, G;
     unsigned long long bar_base;  // counter value at launch
+    int dbg_e;                    // bring-up: barrier id the current phase ends with
 };
 
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// poll with relaxed loads (no L1 invalidate per iteration), then one acquire fence
 __device__ __forceinline__ void wait_counter(const unsigned long long* bar, unsigned long long target) {
     long long t0 = clock64();
-    while (ld_acquire_u64(bar) < target) {
+    while (ld_relaxed_u64(bar) < target) {
         if (clock64() - t0 > 4000000000LL) {
             printf("ctp: grid barrier timeout (cta %d thread %d target %llu have %llu)\n", blockIdx.x, threadIdx.x, target,
                    ld_acquire_u64(bar));
             __trap();
         }
     }
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 
 // grid barrier #e of this launch, executed by the 128 compute threads
 __device__ __forceinline__ void grid_barrier(const StepParams& p, const StepCtx& c, int e) {
     compute_sync();
     if (threadIdx.x == 0) {
-        __threadfence();
+        long long* d = p.dbg ? p.dbg + ((size_t)c.cta * 128 + e) * 8 : nullptr;
+        if (d) d[0] = clock64();
         fence_proxy_async_all();   // generic global writes of this phase -> visible to other CTAs' bulk copies
-        atomicAdd(p.bar, 1ULL);
+        asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p.bar), "l"(1ULL) : "memory");   // release: orders the CTA's writes
         wait_counter(p.bar, c.bar_base + (unsigned long long)(e + 1) * c.G);
-        __threadfence();
+        if (d) d[1] = clock64();
     }
     compute_sync();
 }
@@ -219,9 +234,9 @@ __device__ void step_producer(const StepParams& p, const StepCtx& c) {
             const int n_units = p.B * p.nH;
             for (int u = c.cta; u < n_units; u += c.G) {
                 const int b = u / p.nH, h = u % p.nH;
-                const int pad = p.pad_len[b];
+                const int pad = p.pad_len[p.b0 + b];
                 const int n_old = cur - pad;
-                const size_t head_off = ((size_t)b * p.nH + h) * p.max_seq * HEAD_DIM;
+                const size_t head_off = ((size_t)(p.b0 + b) * p.nH + h) * p.max_seq * HEAD_DIM;
                 for (int t = 0; t < att_tiles(n_old); ++t) {
                     const int j0 = pad + t * 64;
                     const int n = min(64, cur - j0);
@@ -241,123 +256,100 @@ __device__ void step_producer(const StepParams& p, const StepCtx& c) {
     gemm_loads(0, PH_HEAD, -1);
 }
 
-// =====================================================================================================================
-// MMA issuer (warp 5, one lane)
-// =====================================================================================================================
-struct MmaState { uint32_t idx; uint32_t item; uint32_t a_phase; };
-
-__device__ void mma_phase(const StepParams& p, const StepCtx& c, MmaState& m, int layer, int ph, bool norm_phase) {
-    const int n_it = phase_items(p, ph);
-    bool first = true;
-    for (int it = c.cta; it < n_it; it += c.G) {
-        const GemmItem g = make_item(p, layer, ph, it);
-        if (norm_phase && first) {
-            mbar_wait(c.a_ready, m.a_phase & 1);   // activation operand of this phase is in shared memory
-            m.a_phase++;
-        }
-        first = false;
-        if (m.item > 0) mbar_wait(c.acc_free, (m.item - 1) & 1);  // previous accumulator has been drained
-        const uint32_t idesc = make_idesc_f16(128, g.N);
-        const uint32_t w0 = m.idx, a0 = m.idx + g.n_wslots;
-        const uint32_t n_slots = g.n_wslots + g.n_aslots;
-        for (uint32_t s = 0; s < n_slots; ++s) wait_full(c, m.idx + s);
-        tc_fence_after();
-        for (int kb = 0; kb < g.nkb; ++kb) {
-            uint32_t a_addr;
-            if (g.a_glob) a_addr = smem_u32(slot_ptr(c, a0 + kb / 4)) + (kb % 4) * A_KB_BYTES;
-            else a_addr = smem_u32(c.areg) + kb * A_KB_BYTES;
-            const uint32_t b_addr = smem_u32(slot_ptr(c, w0 + kb / g.kb_per_wslot)) + (kb % g.kb_per_wslot) * (g.N * 128);
-            const uint64_t da = make_kmajor_desc(a_addr, 1, 64, 2);
-            const uint64_t db = make_kmajor_desc(b_addr, 1, 64, 2);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16(c.tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-        }
-        for (uint32_t s = 0; s < n_slots; ++s) umma_commit(&c.empty[(m.idx + s) % c.S]);
-        umma_commit(c.acc_ready);
-        m.idx += n_slots;
-        m.item++;
-    }
-}
-
-// the MMA warp only skips over the attention tiles in the slot sequence
+// number of attention tiles this CTA streams in one layer
 __device__ __forceinline__ uint32_t att_slot_count(const StepParams& p, const StepCtx& c, int cur) {
     uint32_t n = 0;
     const int n_units = p.B * p.nH;
-    for (int u = c.cta; u < n_units; u += c.G) n += att_tiles(cur - p.pad_len[u / p.nH]);
+    for (int u = c.cta; u < n_units; u += c.G) n += att_tiles(cur - p.pad_len[p.b0 + u / p.nH]);
     return n;
-}
-
-__device__ void step_mma(const StepParams& p, const StepCtx& c) {
-    MmaState m{0, 0, 0};
-    const int cur = p.st->cur_len;
-    for (int l = 0; l < p.L; ++l) {
-        mma_phase(p, c, m, l, PH_QKV, true);
-        m.idx += att_slot_count(p, c, cur);
-        mma_phase(p, c, m, l, PH_O, false);
-        mma_phase(p, c, m, l, PH_GU, true);
-        mma_phase(p, c, m, l, PH_DN, false);
-    }
-    mma_phase(p, c, m, 0, PH_HEAD, true);
 }
 
 // =====================================================================================================================
 // COMPUTE warps 0-3
 // =====================================================================================================================
-// RMSNorm of all B rows of x into the activation region (fp16, K-major 128B-swizzled k-blocks) — llama.py:82-87.
-// out32 (CTA 0 in the heads phase): also emit the normalised rows in fp32 (hidden state) and into hid_buf.
-__device__ void norm_prologue(const StepParams& p, const StepCtx& c, const float* w, float* out32, bool write_hid) {
+template <int NT>
+__device__ __forceinline__ void norm_rows_batched(const StepParams& p, const StepCtx& c, const float* w, float* out32, bool write_hid) {
+    // warp handles rows warp, warp+8, ...; 4 rows per batch so that 4*NT*2 float4 loads are in flight per lane
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nchunk = p.H / 8;  // 16-byte chunks per row
-    for (int r = warp; r < p.B; r += 4) {
-        const float* xr = p.x + (size_t)r * p.H;
-        float v[4][8];
-        float ss = 0.f;
+    const int nchunk = p.H / 8;  // 16-byte fp16 chunks per row
+    float4 wa[NT], wb[NT];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const int ch = lane + 32 * t;
-            if (ch < nchunk) {
-                const float4 a = __ldcg(reinterpret_cast<const float4*>(xr + ch * 8));       // x is updated by other CTAs
-                const float4 b = __ldcg(reinterpret_cast<const float4*>(xr + ch * 8 + 4));   // inside this launch: skip L1
-                v[t][0] = a.x; v[t][1] = a.y; v[t][2] = a.z; v[t][3] = a.w; v[t][4] = b.x; v[t][5] = b.y; v[t][6] = b.z; v[t][7] = b.w;
+    for (int t = 0; t < NT; ++t) {
+        const int ch = lane + 32 * t;
+        if (ch < nchunk) {
+            wa[t] = *reinterpret_cast<const float4*>(w + ch * 8);
+            wb[t] = *reinterpret_cast<const float4*>(w + ch * 8 + 4);
+        }
+    }
+    for (int r0 = warp; r0 < 32; r0 += 16) {
+        float4 va[2][NT], vb[2][NT];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) ss += v[t][i] * v[t][i];
+        for (int i = 0; i < 2; ++i) {
+            const int r = (r0 + 8 * i + c.cta) & 31;   // rotate the row order per CTA: all SMs read x, spread them over the L2 slices
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const int ch = lane + 32 * t;
+                if (r < p.B && ch < nchunk) {
+                    const float* xr = p.x + (size_t)r * p.H + ch * 8;
+                    va[i][t] = __ldcg(reinterpret_cast<const float4*>(xr));       // x is updated by other CTAs inside
+                    vb[i][t] = __ldcg(reinterpret_cast<const float4*>(xr + 4));   // this launch: bypass L1
+                } else {
+                    va[i][t] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    vb[i][t] = va[i][t];
+                }
             }
         }
-        ss = warp_sum(ss);
-        const float rstd = rsqrtf(ss / (float)p.H + p.eps);
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const int ch = lane + 32 * t;
-            if (ch < nchunk) {
-                const float4 wa = *reinterpret_cast<const float4*>(w + ch * 8);
-                const float4 wb = *reinterpret_cast<const float4*>(w + ch * 8 + 4);
-                const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-                float y[8];
+        for (int i = 0; i < 2; ++i) {
+            const int r = (r0 + 8 * i + c.cta) & 31;
+            float ss = 0.f;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) y[i] = ww[i] * (v[t][i] * rstd);
-                __half2 h0 = __floats2half2_rn(y[0], y[1]), h1 = __floats2half2_rn(y[2], y[3]);
-                __half2 h2 = __floats2half2_rn(y[4], y[5]), h3 = __floats2half2_rn(y[6], y[7]);
-                uint4 pk;
-                pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                const int kb = ch >> 3, cc = ch & 7;
-                *reinterpret_cast<uint4*>(c.areg + kb * A_KB_BYTES + r * 128 + ((cc ^ (r & 7)) << 4)) = pk;
-                if (out32) {
-                    float* o = out32 + (size_t)r * p.H + ch * 8;
-                    *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
-                    *reinterpret_cast<float4*>(o + 4) = make_float4(y[4], y[5], y[6], y[7]);
-                    if (write_hid && p.st->hid_buf && p.st->step < p.st->max_new) {
-                        float* hb = p.st->hid_buf + ((size_t)r * p.st->max_new + p.st->step) * p.H + ch * 8;
-                        *reinterpret_cast<float4*>(hb) = make_float4(y[0], y[1], y[2], y[3]);
-                        *reinterpret_cast<float4*>(hb + 4) = make_float4(y[4], y[5], y[6], y[7]);
+            for (int t = 0; t < NT; ++t) {
+                ss += va[i][t].x * va[i][t].x + va[i][t].y * va[i][t].y + va[i][t].z * va[i][t].z + va[i][t].w * va[i][t].w;
+                ss += vb[i][t].x * vb[i][t].x + vb[i][t].y * vb[i][t].y + vb[i][t].z * vb[i][t].z + vb[i][t].w * vb[i][t].w;
+            }
+            ss = warp_sum(ss);
+            if (r >= p.B) continue;   // warp-uniform
+            const float rstd = rsqrtf(ss / (float)p.H + p.eps);
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const int ch = lane + 32 * t;
+                if (ch < nchunk) {
+                    float y[8];
+                    y[0] = wa[t].x * (va[i][t].x * rstd); y[1] = wa[t].y * (va[i][t].y * rstd);
+                    y[2] = wa[t].z * (va[i][t].z * rstd); y[3] = wa[t].w * (va[i][t].w * rstd);
+                    y[4] = wb[t].x * (vb[i][t].x * rstd); y[5] = wb[t].y * (vb[i][t].y * rstd);
+                    y[6] = wb[t].z * (vb[i][t].z * rstd); y[7] = wb[t].w * (vb[i][t].w * rstd);
+                    __half2 h0 = __floats2half2_rn(y[0], y[1]), h1 = __floats2half2_rn(y[2], y[3]);
+                    __half2 h2 = __floats2half2_rn(y[4], y[5]), h3 = __floats2half2_rn(y[6], y[7]);
+                    uint4 pk;
+                    pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                    pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                    const int kb = ch >> 3, cc = ch & 7;
+                    *reinterpret_cast<uint4*>(c.areg + kb * A_KB_BYTES + r * 128 + ((cc ^ (r & 7)) << 4)) = pk;
+                    if (out32) {
+                        float* o = out32 + (size_t)(p.b0 + r) * p.H + ch * 8;
+                        *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
+                        *reinterpret_cast<float4*>(o + 4) = make_float4(y[4], y[5], y[6], y[7]);
+                        if (write_hid && p.st->hid_buf && p.st->step < p.st->max_new) {
+                            float* hb = p.st->hid_buf + ((size_t)(p.b0 + r) * p.st->max_new + p.st->step) * p.H + ch * 8;
+                            *reinterpret_cast<float4*>(hb) = make_float4(y[0], y[1], y[2], y[3]);
+                            *reinterpret_cast<float4*>(hb + 4) = make_float4(y[4], y[5], y[6], y[7]);
+                        }
                     }
                 }
             }
         }
     }
-    fence_proxy_async();   // generic-proxy smem writes -> visible to tcgen05.mma (async proxy)
+}
+
+// RMSNorm of all B rows of x into the activation region (fp16, K-major 128B-swizzled k-blocks) — llama.py:82-87.
+// out32 (CTA 0 in the heads phase): also emit the normalised rows in fp32 (hidden state) and into hid_buf.
+__device__ void norm_prologue(const StepParams& p, const StepCtx& c, const float* w, float* out32, bool write_hid) {
+    if (p.H <= 768) norm_rows_batched<3>(p, c, w, out32, write_hid);
+    else norm_rows_batched<4>(p, c, w, out32, write_hid);
     compute_sync();
-    if (threadIdx.x == 0) mbar_arrive(c.a_ready);
+    if (threadIdx.x == 0 && p.dbg) p.dbg[((size_t)c.cta * 128 + c.dbg_e) * 8 + 2] = clock64();
 }
 
 // write 8 consecutive fp16 values (k0 multiple of 8) of batch row b into a packed activation buffer in global memory
@@ -372,234 +364,320 @@ __device__ __forceinline__ void store_packed8(__half* base, int b, int k0, const
     *reinterpret_cast<uint4*>(dst) = pk;
 }
 
-// read NC accumulator columns (NC in {16, 48}) of lane `lane` (= batch row) from TMEM
-template <int NC>
-__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v) {
+// ---- warp-level MMA helpers -------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t (&r)[2]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void hmma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// 16-byte chunk `chunk` (0..7) of row `row` inside a 128B-swizzled K-major k-block that starts at `kb_base`
+__device__ __forceinline__ uint32_t swz(uint32_t kb_base, int row, int chunk) {
+    return kb_base + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+}
+
+// One GEMM work item: D[32 x N] = A[32 x K] . W[N x K]^T with K = 64*nkb, A and W as swizzled k-blocks in shared memory.
+// 8 warps: warp w owns m-tile (w & 1), the n-tiles [NT*((w>>1)&1), +NT) with NT = N/16, and the k-blocks of parity (w >> 2).
+// All fragments of a k-block are loaded before its MMAs (two accumulator sets break the accumulate dependency); the two
+// K-half partial tiles are staged in `dbuf` ([2][32][N+4] fp32) and summed by the epilogue.
+template <int N>
+__device__ __forceinline__ void gemm_item_mma(const StepParams& p, const StepCtx& c, const GemmItem& g, uint32_t slot0, float* dbuf) {
+    constexpr int NT = N / 16;           // n-tiles (of 8 rows) per warp: 1 (N=16) or 3 (N=48)
+    constexpr int LD = N + 4;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = 16 * (warp & 1);
+    const int n0 = 8 * NT * ((warp >> 1) & 1);
+    const int khalf = warp >> 2;
+    float acc[2][NT][4];
 #pragma unroll
-    for (int c0 = 0; c0 < NC; c0 += 16) {
-        uint32_t r[16];
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-              "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-            : "r"(taddr + (uint32_t)c0)
-            : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    for (int e = 0; e < 2; ++e)
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[c0 + i] = __uint_as_float(r[i]);
+        for (int i = 0; i < NT; ++i) { acc[e][i][0] = acc[e][i][1] = acc[e][i][2] = acc[e][i][3] = 0.f; }
+    const uint32_t w0 = slot0, a0 = slot0 + g.n_wslots;
+    uint32_t w_seen = 0, a_seen = 0;
+    const int a_row = m0 + (lane & 7) + ((lane >> 3) & 1) * 8, a_hi = lane >> 4;           // A: x4 = (m lo/hi) x (k lo/hi)
+    const int b_row4 = (lane & 7) + ((lane >> 4) & 1) * 8, b_hi4 = (lane >> 3) & 1;          // B x4: (n-tile 0/1) x (k lo/hi)
+    const int b_row2 = lane & 7, b_hi2 = (lane >> 3) & 1;                                    // B x2: one n-tile x (k lo/hi)
+    for (int kb = khalf; kb < g.nkb; kb += 2) {
+        constexpr int KPS = SLOT_BYTES / (N * 128);   // k-blocks per weight slot: 8 (N=16) or 2 (N=48)
+        const uint32_t wneed = (uint32_t)(kb / KPS) + 1;
+        while (w_seen < wneed) { wait_full(c, w0 + w_seen); ++w_seen; }
+        uint32_t a_base;
+        if (g.a_glob) {
+            const uint32_t aneed = (uint32_t)(kb >> 2) + 1;
+            while (a_seen < aneed) { wait_full(c, a0 + a_seen); ++a_seen; }
+            a_base = smem_u32(slot_ptr(c, a0 + (kb >> 2))) + (kb & 3) * A_KB_BYTES;
+        } else {
+            a_base = smem_u32(c.areg) + kb * A_KB_BYTES;
+        }
+        const uint32_t b_base = smem_u32(slot_ptr(c, w0 + kb / KPS)) + (kb % KPS) * (N * 128);
+        uint32_t a[4][4], bw[4][2 * NT];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            ldsm_x4(swz(a_base, a_row, 2 * ks + a_hi), a[ks]);
+            if (NT == 1) {
+                uint32_t t2[2];
+                ldsm_x2(swz(b_base, n0 + b_row2, 2 * ks + b_hi2), t2);
+                bw[ks][0] = t2[0]; bw[ks][1] = t2[1];
+            } else {
+                uint32_t t4[4], t2[2];
+                ldsm_x4(swz(b_base, n0 + b_row4, 2 * ks + b_hi4), t4);
+                ldsm_x2(swz(b_base, n0 + 16 + b_row2, 2 * ks + b_hi2), t2);
+                bw[ks][0] = t4[0]; bw[ks][1] = t4[1]; bw[ks][2 % (2 * NT)] = t4[2]; bw[ks][3 % (2 * NT)] = t4[3];
+                bw[ks][4 % (2 * NT)] = t2[0]; bw[ks][5 % (2 * NT)] = t2[1];
+            }
+        }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+            for (int i = 0; i < NT; ++i) hmma_16816(acc[ks & 1][i], a[ks], bw[ks][2 * i], bw[ks][2 * i + 1]);
+    }
+    // C fragment: c0,c1 -> row lane/4, cols 2*(lane%4)+{0,1}; c2,c3 -> row lane/4 + 8
+    float* dh = dbuf + khalf * (32 * LD);
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+        const int col = n0 + 8 * i + 2 * (lane & 3);
+        const int r = m0 + (lane >> 2);
+        *reinterpret_cast<float2*>(dh + r * LD + col) = make_float2(acc[0][i][0] + acc[1][i][0], acc[0][i][1] + acc[1][i][1]);
+        *reinterpret_cast<float2*>(dh + (r + 8) * LD + col) = make_float2(acc[0][i][2] + acc[1][i][2], acc[0][i][3] + acc[1][i][3]);
+    }
+    compute_sync();   // both partial tiles complete; every warp is done reading this item's slots
+    if (threadIdx.x == 0) {
+        const uint32_t n_slots = g.n_wslots + g.n_aslots;
+        for (uint32_t s2 = 0; s2 < n_slots; ++s2) mbar_arrive(&c.empty[(slot0 + s2) % c.S]);
     }
 }
 
-// Epilogues: executed by warp 0 (TMEM lanes 0..31 = batch rows).  `item` counts this CTA's GEMM items (parity).
-__device__ void gemm_epilogues(const StepParams& p, const StepCtx& c, uint32_t& item, int layer, int ph) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// 4 consecutive fp16 values (k0 multiple of 4) of batch row b into a packed activation buffer in global memory
+__device__ __forceinline__ void store_packed4(__half* base, int b, int k0, const float* y) {
+    __half2 h0 = __floats2half2_rn(y[0], y[1]), h1 = __floats2half2_rn(y[2], y[3]);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+    const int kb = k0 >> 6, cc = (k0 & 63) >> 3;
+    uint8_t* dst = reinterpret_cast<uint8_t*>(base) + (size_t)kb * A_KB_BYTES + b * 128 + ((cc ^ (b & 7)) << 4) + (k0 & 7) * 2;
+    *reinterpret_cast<uint2*>(dst) = pk;
+}
+
+// GEMM phase of this CTA: items it, it+G, ... ; 256-thread epilogues: thread = (batch row b = tid & 31, column group cg = tid >> 5)
+__device__ void gemm_phase(const StepParams& p, const StepCtx& c, uint32_t& idx, int layer, int ph) {
+    const int tid = threadIdx.x;
+    const int b = tid & 31, cg = tid >> 5;   // cg in 0..7
+    const bool live = b < p.B;
     const int n_it = phase_items(p, ph);
     const int cur = p.st->cur_len;
+    float* dbuf = reinterpret_cast<float*>(c.areg + (p.H / 64) * A_KB_BYTES);
     for (int it = c.cta; it < n_it; it += c.G) {
-        if (warp == 0) {
-            mbar_wait(c.acc_ready, item & 1);
-            tc_fence_after();
-            const int b = lane;
-            const bool live = b < p.B;
-            if (ph == PH_GU) {
-                float v[48];
-                tmem_ld_cols<48>(c.tmem, v);
-                if (live) {
-                    float y[24];
+        const GemmItem g = make_item(p, layer, ph, it);
+        if (ph == PH_GU) gemm_item_mma<48>(p, c, g, idx, dbuf);
+        else gemm_item_mma<16>(p, c, g, idx, dbuf);
+        idx += g.n_wslots + g.n_aslots;
+        if (p.dbg && tid == 0 && it == c.cta) p.dbg[((size_t)c.cta * 128 + c.dbg_e) * 8 + 3] = clock64();
+        if (ph == PH_GU) {
+            if (live && cg < 6) {   // h = silu(gate) * up (llama.py:214): gate cols [4cg, 4cg+4), up cols 24 + the same
+                const float* d0 = dbuf + b * 52;
+                const float* d1 = d0 + 32 * 52;
+                float y[4];
 #pragma unroll
-                    for (int i = 0; i < 24; ++i) y[i] = silu(v[i]) * v[24 + i];   // llama.py:214
-                    store_packed8(p.h_p, b, 24 * it, y);
-                    store_packed8(p.h_p, b, 24 * it + 8, y + 8);
-                    store_packed8(p.h_p, b, 24 * it + 16, y + 16);
+                for (int i = 0; i < 4; ++i) {
+                    const float gte = d0[4 * cg + i] + d1[4 * cg + i];
+                    const float up = d0[24 + 4 * cg + i] + d1[24 + 4 * cg + i];
+                    y[i] = silu(gte) * up;
+                }
+                store_packed4(p.h_p, b, 24 * it + 4 * cg, y);
+            }
+        } else if (live) {
+            const float* d0 = dbuf + b * 20;
+            const float* d1 = d0 + 32 * 20;
+            if (ph == PH_QKV) {
+                const int type = it / (p.nH * 4), h = (it / 4) % p.nH, j = it % 4;
+                if (type < 2) {   // RoPE on the pair (i, i+32), i = 8j + cg: llama.py:151-182; position = cur - pad (gpt.py:238-245)
+                    const float pos = (float)(cur - p.pad_len[p.b0 + b]);
+                    float sn, cs;
+                    sincosf(pos * p.inv_freq[j * 8 + cg], &sn, &cs);
+                    const float x1 = d0[cg] + d1[cg], x2 = d0[8 + cg] + d1[8 + cg];
+                    const float lo = x1 * cs - x2 * sn, hi = x2 * cs + x1 * sn;
+                    if (type == 0) {
+                        float* qd = p.q + (size_t)b * p.H + h * 64 + j * 8 + cg;
+                        qd[0] = lo;
+                        qd[32] = hi;
+                    } else {      // KV append, O(1) (replaces DynamicCache.update's torch.cat, llama.py:630-633)
+                        __half* kd = p.kv + (size_t)(2 * layer) * p.kv_plane + (((size_t)(p.b0 + b) * p.nH + h) * p.max_seq + cur) * HEAD_DIM + j * 8 + cg;
+                        kd[0] = __float2half_rn(lo);
+                        kd[32] = __float2half_rn(hi);
+                    }
+                } else {
+                    __half* vd = p.kv + (size_t)(2 * layer + 1) * p.kv_plane + (((size_t)(p.b0 + b) * p.nH + h) * p.max_seq + cur) * HEAD_DIM + j * 16 + 2 * cg;
+                    *reinterpret_cast<__half2*>(vd) = __floats2half2_rn(d0[2 * cg] + d1[2 * cg], d0[2 * cg + 1] + d1[2 * cg + 1]);
                 }
             } else {
-                float v[16];
-                tmem_ld_cols<16>(c.tmem, v);
-                if (live) {
-                    if (ph == PH_QKV) {
-                        const int type = it / (p.nH * 4), h = (it / 4) % p.nH, j = it % 4;
-                        if (type < 2) {   // RoPE on 8 (i, i+32) pairs: llama.py:151-182; position = cur - pad (gpt.py:238-245)
-                            const float pos = (float)(cur - p.pad_len[b]);
-                            float lo[8], hi[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                float sn, cs;
-                                sincosf(pos * p.inv_freq[j * 8 + i], &sn, &cs);
-                                lo[i] = v[i] * cs - v[8 + i] * sn;
-                                hi[i] = v[8 + i] * cs + v[i] * sn;
-                            }
-                            if (type == 0) {
-                                float* qd = p.q + (size_t)b * p.H + h * 64 + j * 8;
-                                *reinterpret_cast<float4*>(qd) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                                *reinterpret_cast<float4*>(qd + 4) = make_float4(lo[4], lo[5], lo[6], lo[7]);
-                                *reinterpret_cast<float4*>(qd + 32) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                                *reinterpret_cast<float4*>(qd + 36) = make_float4(hi[4], hi[5], hi[6], hi[7]);
-                            } else {      // KV append, O(1) (replaces DynamicCache.update's torch.cat, llama.py:630-633)
-                                __half* kd = p.kv + (size_t)(2 * layer) * p.kv_plane + (((size_t)b * p.nH + h) * p.max_seq + cur) * HEAD_DIM + j * 8;
-                                __half2 t0 = __floats2half2_rn(lo[0], lo[1]), t1 = __floats2half2_rn(lo[2], lo[3]);
-                                __half2 t2 = __floats2half2_rn(lo[4], lo[5]), t3 = __floats2half2_rn(lo[6], lo[7]);
-                                uint4 pk;
-                                pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-                                pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                                *reinterpret_cast<uint4*>(kd) = pk;
-                                t0 = __floats2half2_rn(hi[0], hi[1]); t1 = __floats2half2_rn(hi[2], hi[3]);
-                                t2 = __floats2half2_rn(hi[4], hi[5]); t3 = __floats2half2_rn(hi[6], hi[7]);
-                                pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-                                pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                                *reinterpret_cast<uint4*>(kd + 32) = pk;
-                            }
-                        } else {
-                            __half* vd = p.kv + (size_t)(2 * layer + 1) * p.kv_plane + (((size_t)b * p.nH + h) * p.max_seq + cur) * HEAD_DIM + j * 16;
-                            __half2 t[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) t[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-                            uint4 pk;
-                            pk.x = *reinterpret_cast<uint32_t*>(&t[0]); pk.y = *reinterpret_cast<uint32_t*>(&t[1]);
-                            pk.z = *reinterpret_cast<uint32_t*>(&t[2]); pk.w = *reinterpret_cast<uint32_t*>(&t[3]);
-                            *reinterpret_cast<uint4*>(vd) = pk;
-                            pk.x = *reinterpret_cast<uint32_t*>(&t[4]); pk.y = *reinterpret_cast<uint32_t*>(&t[5]);
-                            pk.z = *reinterpret_cast<uint32_t*>(&t[6]); pk.w = *reinterpret_cast<uint32_t*>(&t[7]);
-                            *reinterpret_cast<uint4*>(vd + 8) = pk;
-                        }
-                    } else if (ph == PH_O) {   // residual add, this CTA owns features [16 it, 16 it + 16) (llama.py:737)
-                        float* xd = p.x + (size_t)b * p.H + 16 * it;
-#pragma unroll
-                        for (int i = 0; i < 16; i += 4) {
-                            float4 o = __ldcg(reinterpret_cast<const float4*>(xd + i));
-                            o.x += v[i]; o.y += v[i + 1]; o.z += v[i + 2]; o.w += v[i + 3];
-                            *reinterpret_cast<float4*>(xd + i) = o;
-                        }
-                    } else if (ph == PH_DN) {  // split-K partial of down_proj added into the residual (llama.py:745)
-                        float* xd = p.x + (size_t)b * p.H + 16 * (it / DN_KSPLIT);
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) atomicAdd(xd + i, v[i]);
-                    } else {                   // heads (gpt.py:424-439): logits row layout b*(num_vq*A) + q*A + a
-                        const int F = p.num_vq * p.num_audio;
-                        float* ld = p.logits + (size_t)b * F + 16 * it;
-                        if (16 * it + 16 <= F) {
-#pragma unroll
-                            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(ld + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                        } else {
-                            for (int i = 0; i < 16; ++i)
-                                if (16 * it + i < F) ld[i] = v[i];
-                        }
-                    }
+                const float v0 = d0[2 * cg] + d1[2 * cg], v1 = d0[2 * cg + 1] + d1[2 * cg + 1];
+                if (ph == PH_O) {          // residual add, this CTA owns features [16 it, 16 it + 16) (llama.py:737)
+                    float* xd = p.x + (size_t)b * p.H + 16 * it + 2 * cg;
+                    float2 o = __ldcg(reinterpret_cast<const float2*>(xd));
+                    o.x += v0; o.y += v1;
+                    *reinterpret_cast<float2*>(xd) = o;
+                } else if (ph == PH_DN) {  // split-K partial of down_proj added into the residual (llama.py:745)
+                    float* xd = p.x + (size_t)b * p.H + 16 * (it / DN_KSPLIT) + 2 * cg;
+                    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(xd), "f"(v0), "f"(v1) : "memory");
+                } else {                   // heads (gpt.py:424-439): logits row layout b*(num_vq*A) + q*A + a
+                    const int F = p.num_vq * p.num_audio;
+                    float* ld = p.logits + (size_t)(p.b0 + b) * F + 16 * it + 2 * cg;
+                    if (16 * it + 2 * cg + 2 <= F) *reinterpret_cast<float2*>(ld) = make_float2(v0, v1);
+                    else if (16 * it + 2 * cg < F) ld[0] = v0;
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(c.acc_free);
         }
-        item++;
+        if (p.dbg && tid == 0) p.dbg[((size_t)c.cta * 128 + c.dbg_e) * 8 + 4] = clock64();
+        compute_sync();   // dbuf is reused by the next item / phase
     }
 }
 
-// Decode attention for this CTA's units over the KV tiles in the ring (SDPA q_len = 1, llama.py:653-661).
+// Decode attention (SDPA q_len = 1, llama.py:653-661) over the KV tiles in the ring.  Each warp owns whole units
+// (b, h): the k-th unit of this CTA goes to warp k % 8, so units proceed independently (no CTA-wide syncs); inside a warp
+// 4 groups of 8 lanes take positions round-robin, each lane holding 8 of the 64 head dims.
 __device__ void attention_phase(const StepParams& p, const StepCtx& c, uint32_t& idx, int layer) {
-    const int tid = threadIdx.x;   // 0..127
-    const int grp = tid >> 3, sub = tid & 7;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane >> 3, sub = lane & 7;
     const int cur = p.st->cur_len;
-    float* s_m = reinterpret_cast<float*>(c.areg);          // [16]
-    float* s_l = s_m + 16;                                   // [16]
-    float* s_o = s_l + 16;                                   // [16][65]
     const __half* kc = p.kv + (size_t)(2 * layer) * p.kv_plane;
     const __half* vc = p.kv + (size_t)(2 * layer + 1) * p.kv_plane;
     const int n_units = p.B * p.nH;
-    for (int u = c.cta; u < n_units; u += c.G) {
+    uint32_t base = idx;   // ring index of the first tile of the unit under consideration
+    int k = 0;
+    for (int u = c.cta; u < n_units; u += c.G, ++k) {
         const int b = u / p.nH, h = u % p.nH;
-        const int pad = p.pad_len[b];
+        const int pad = p.pad_len[p.b0 + b];
         const int n_old = cur - pad;
-        float q[8];
-        {
-            const float* qp = p.q + (size_t)b * p.H + h * 64 + sub * 8;
-            const float4 a = __ldcg(reinterpret_cast<const float4*>(qp)), bq = __ldcg(reinterpret_cast<const float4*>(qp + 4));
-            q[0] = a.x * 0.125f; q[1] = a.y * 0.125f; q[2] = a.z * 0.125f; q[3] = a.w * 0.125f;
-            q[4] = bq.x * 0.125f; q[5] = bq.y * 0.125f; q[6] = bq.z * 0.125f; q[7] = bq.w * 0.125f;
-        }
-        float m = -INFINITY, l = 0.f, o[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = 0.f;
-        auto accum = [&](const uint4& kr, const uint4& vr, bool valid) {
-            const __half2* k2 = reinterpret_cast<const __half2*>(&kr);
-            float s = 0.f;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 f = __half22float2(k2[i]);
-                s += q[2 * i] * f.x + q[2 * i + 1] * f.y;
+        const int n_tiles = att_tiles(n_old);
+        if ((k & 7) == warp) {
+            float q[8];
+            {
+                const float* qp = p.q + (size_t)b * p.H + h * 64 + sub * 8;
+                const float4 a = __ldcg(reinterpret_cast<const float4*>(qp)), bq = __ldcg(reinterpret_cast<const float4*>(qp + 4));
+                q[0] = a.x * 0.125f; q[1] = a.y * 0.125f; q[2] = a.z * 0.125f; q[3] = a.w * 0.125f;
+                q[4] = bq.x * 0.125f; q[5] = bq.y * 0.125f; q[6] = bq.z * 0.125f; q[7] = bq.w * 0.125f;
             }
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            s += __shfl_xor_sync(0xffffffffu, s, 4);
-            if (valid) {
-                const float mn = fmaxf(m, s);
-                const float corr = __expf(m - mn);
-                const float pr = __expf(s - mn);
-                l = l * corr + pr;
-                const __half2* v2 = reinterpret_cast<const __half2*>(&vr);
+            // the new token (slot cur, appended by this step's QKV phase): issue its loads early, consumed by group 0 last
+            const size_t off_new = (((size_t)(p.b0 + b) * p.nH + h) * p.max_seq + cur) * HEAD_DIM;
+            uint4 k_new = make_uint4(0, 0, 0, 0), v_new = make_uint4(0, 0, 0, 0);
+            if (grp == 0) {
+                k_new = __ldcg(reinterpret_cast<const uint4*>(kc + off_new + sub * 8));
+                v_new = __ldcg(reinterpret_cast<const uint4*>(vc + off_new + sub * 8));
+            }
+            float m = -INFINITY, l = 0.f, o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = 0.f;
+            auto dot8 = [&](const uint4& kr) {
+                const __half2* k2 = reinterpret_cast<const __half2*>(&kr);
+                float s = 0.f;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float2 f = __half22float2(v2[i]);
-                    o[2 * i] = o[2 * i] * corr + pr * f.x;
-                    o[2 * i + 1] = o[2 * i + 1] * corr + pr * f.y;
+                    const float2 f = __half22float2(k2[i]);
+                    s += q[2 * i] * f.x + q[2 * i + 1] * f.y;
+                }
+                return s;
+            };
+            // four positions per online-softmax rescale: the score chains are independent, one max/rescale per batch
+            auto accum4 = [&](const uint4 (&kr)[4], const uint4 (&vr)[4], const bool (&valid)[4]) {
+                float s[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) s[e] = dot8(kr[e]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) s[e] += __shfl_xor_sync(0xffffffffu, s[e], 1);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) s[e] += __shfl_xor_sync(0xffffffffu, s[e], 2);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) s[e] += __shfl_xor_sync(0xffffffffu, s[e], 4);
+                float mn = m;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (valid[e]) mn = fmaxf(mn, s[e]);
+                if (mn == -INFINITY) return;   // nothing valid yet (uniform within the 8-lane group)
+                const float corr = __expf(m - mn);
+                float pr[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) pr[e] = valid[e] ? __expf(s[e] - mn) : 0.f;
+                l = l * corr + (pr[0] + pr[1]) + (pr[2] + pr[3]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float a0 = o[2 * i] * corr, a1 = o[2 * i + 1] * corr;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 f = __half22float2(reinterpret_cast<const __half2*>(&vr[e])[i]);
+                        a0 += pr[e] * f.x;
+                        a1 += pr[e] * f.y;
+                    }
+                    o[2 * i] = a0;
+                    o[2 * i + 1] = a1;
                 }
                 m = mn;
-            }
-        };
-        for (int t = 0; t < att_tiles(n_old); ++t) {
-            const int n = min(64, n_old - t * 64);
-            wait_full(c, idx);
-            const uint8_t* sl = slot_ptr(c, idx);
+            };
+            for (int t = 0; t < n_tiles; ++t) {
+                const int n = min(64, n_old - t * 64);
+                wait_full(c, base + t);
+                const uint8_t* sl = slot_ptr(c, base + t);
+#pragma unroll 2
+                for (int r = 0; r < 4; ++r) {
+                    uint4 kr[4], vr[4];
+                    bool valid[4];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int j = grp + 16 * r;
-                const bool valid = j < n;
-                uint4 kr = make_uint4(0, 0, 0, 0), vr = make_uint4(0, 0, 0, 0);
-                if (valid) {
-                    kr = *reinterpret_cast<const uint4*>(sl + j * 128 + sub * 16);
-                    vr = *reinterpret_cast<const uint4*>(sl + 8192 + j * 128 + sub * 16);
+                    for (int e = 0; e < 4; ++e) {
+                        const int j = grp + 4 * (4 * r + e);
+                        valid[e] = j < n;
+                        kr[e] = make_uint4(0, 0, 0, 0);
+                        vr[e] = make_uint4(0, 0, 0, 0);
+                        if (valid[e]) {
+                            kr[e] = *reinterpret_cast<const uint4*>(sl + j * 128 + sub * 16);
+                            vr[e] = *reinterpret_cast<const uint4*>(sl + 8192 + j * 128 + sub * 16);
+                        }
+                    }
+                    accum4(kr, vr, valid);
                 }
-                accum(kr, vr, valid);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&c.empty[(base + t) % c.S]);   // this warp was the tile's only reader
             }
-            compute_sync();                       // all 128 threads are done with this slot
-            if (tid == 0) mbar_arrive(&c.empty[idx % c.S]);
-            ++idx;
-        }
-        {   // the new token (slot cur), appended by the QKV phase of this step: group 0 takes it from global memory
-            const size_t off = (((size_t)b * p.nH + h) * p.max_seq + cur) * HEAD_DIM;
-            const bool valid = grp == 0;
-            uint4 kr = make_uint4(0, 0, 0, 0), vr = make_uint4(0, 0, 0, 0);
-            if (valid) {
-                kr = __ldcg(reinterpret_cast<const uint4*>(kc + off + sub * 8));
-                vr = __ldcg(reinterpret_cast<const uint4*>(vc + off + sub * 8));
+            {   // the new token: group 0 only
+                uint4 kr[4] = {k_new, make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+                uint4 vr[4] = {v_new, make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+                const bool valid[4] = {grp == 0, false, false, false};
+                accum4(kr, vr, valid);
             }
-            accum(kr, vr, valid);
-        }
-        if (sub == 0) { s_m[grp] = m; s_l[grp] = l; }
+            // merge the 4 position groups (lanes with equal `sub` hold the same 8 dims)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s_o[grp * 65 + sub * 8 + i] = o[i];
-        compute_sync();
-        if (tid < 64) {
-            float M = -INFINITY;
+            for (int d = 8; d <= 16; d <<= 1) {
+                const float m2 = __shfl_xor_sync(0xffffffffu, m, d);
+                const float l2 = __shfl_xor_sync(0xffffffffu, l, d);
+                const float mn = fmaxf(m, m2);
+                const float w1 = (m == -INFINITY) ? 0.f : __expf(m - mn);
+                const float w2 = (m2 == -INFINITY) ? 0.f : __expf(m2 - mn);
 #pragma unroll
-            for (int g = 0; g < 16; ++g) M = fmaxf(M, s_m[g]);
-            float Ls = 0.f, O = 0.f;
-#pragma unroll
-            for (int g = 0; g < 16; ++g) {
-                const float w = (s_m[g] == -INFINITY) ? 0.f : __expf(s_m[g] - M);
-                Ls += s_l[g] * w;
-                O += s_o[g * 65 + tid] * w;
+                for (int i = 0; i < 8; ++i) {
+                    const float o2 = __shfl_xor_sync(0xffffffffu, o[i], d);
+                    o[i] = o[i] * w1 + o2 * w2;
+                }
+                l = l * w1 + l2 * w2;
+                m = mn;
             }
-            // packed A operand of o_proj: k-block h, row b, swizzled 16-byte chunks
-            const int cc = tid >> 3;
-            __half* dst = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(p.attn_p) + (size_t)h * A_KB_BYTES + b * 128 + ((cc ^ (b & 7)) << 4)) + (tid & 7);
-            *dst = __float2half_rn(O / Ls);
+            if (grp == 0) {   // packed A operand of o_proj: k-block h, row b, 16-byte chunk `sub`
+                float y[8];
+                const float inv = 1.0f / l;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) y[i] = o[i] * inv;
+                store_packed8(p.attn_p, b, h * 64 + sub * 8, y);
+            }
         }
-        compute_sync();
+        base += n_tiles;
     }
+    idx = base;
 }
 
-__device__ void step_compute(const StepParams& p, const StepCtx& c) {
-    uint32_t idx = 0, item = 0;
+__device__ void step_compute(const StepParams& p, StepCtx c) {
+    uint32_t idx = 0;
     const int tid = threadIdx.x;
     const int cur = p.st->cur_len;
     // ---- code embedding (gpt.py:398-407): CTA b builds x[b]
@@ -607,9 +685,10 @@ __device__ void step_compute(const StepParams& p, const StepCtx& c) {
         const int b = c.cta;
         __shared__ int sid[MAX_VQ];
         if (tid < p.num_vq)
-            sid[tid] = p.ids_ext ? p.ids_ext[b * p.num_vq + tid] : p.st->ids_buf[((size_t)b * p.st->max_new + (p.st->step - 1)) * p.num_vq + tid];
+            sid[tid] = p.ids_ext ? p.ids_ext[(p.b0 + b) * p.num_vq + tid]
+                                 : p.st->ids_buf[((size_t)(p.b0 + b) * p.st->max_new + (p.st->step - 1)) * p.num_vq + tid];
         compute_sync();
-        for (int k = tid; k < p.H; k += 128) {
+        for (int k = tid; k < p.H; k += NCOMP) {
             float v = 0.f;
             for (int qv = 0; qv < p.num_vq; ++qv) v += __half2float(p.emb_code[((size_t)qv * p.num_audio + sid[qv]) * p.H + k]);
             p.x[(size_t)b * p.H + k] = v;
@@ -619,41 +698,43 @@ __device__ void step_compute(const StepParams& p, const StepCtx& c) {
     auto count_att = [&]() { return att_slot_count(p, c, cur); };
     for (int l = 0; l < p.L; ++l) {
         // QKV
+        c.dbg_e = bar_id(l, 0);
         if (c.cta < phase_items(p, PH_QKV)) norm_prologue(p, c, p.ln1 + (size_t)l * p.H, nullptr, false);
-        gemm_epilogues(p, c, item, l, PH_QKV);
-        { uint32_t n = 0; const int nq = phase_items(p, PH_QKV); for (int it = c.cta; it < nq; it += c.G) n += make_item(p, l, PH_QKV, it).n_wslots; idx += n; }
+        gemm_phase(p, c, idx, l, PH_QKV);
         grid_barrier(p, c, bar_id(l, 0));
         // attention
         attention_phase(p, c, idx, l);
         grid_barrier(p, c, bar_id(l, 1));
         // o_proj
-        gemm_epilogues(p, c, item, l, PH_O);
-        { uint32_t n = 0; const int nq = phase_items(p, PH_O); for (int it = c.cta; it < nq; it += c.G) { const GemmItem g = make_item(p, l, PH_O, it); n += g.n_wslots + g.n_aslots; } idx += n; }
+        c.dbg_e = bar_id(l, 2);
+        gemm_phase(p, c, idx, l, PH_O);
         grid_barrier(p, c, bar_id(l, 2));
         // gate/up
+        c.dbg_e = bar_id(l, 3);
         if (c.cta < phase_items(p, PH_GU)) norm_prologue(p, c, p.ln2 + (size_t)l * p.H, nullptr, false);
-        gemm_epilogues(p, c, item, l, PH_GU);
-        { uint32_t n = 0; const int nq = phase_items(p, PH_GU); for (int it = c.cta; it < nq; it += c.G) n += make_item(p, l, PH_GU, it).n_wslots; idx += n; }
+        gemm_phase(p, c, idx, l, PH_GU);
         grid_barrier(p, c, bar_id(l, 3));
         // down
-        gemm_epilogues(p, c, item, l, PH_DN);
-        { uint32_t n = 0; const int nq = phase_items(p, PH_DN); for (int it = c.cta; it < nq; it += c.G) { const GemmItem g = make_item(p, l, PH_DN, it); n += g.n_wslots + g.n_aslots; } idx += n; }
+        c.dbg_e = bar_id(l, 4);
+        gemm_phase(p, c, idx, l, PH_DN);
         grid_barrier(p, c, bar_id(l, 4));
     }
     (void)count_att;
+    c.dbg_e = 1 + 5 * p.L;
     // final norm (llama.py:1002) -> hidden state of this step (gpt.py:422-423) + heads
     if (c.cta < phase_items(p, PH_HEAD) || c.cta == 0) {
         if (c.cta < phase_items(p, PH_HEAD)) norm_prologue(p, c, p.norm_f, c.cta == 0 ? p.hidden : nullptr, true);
     }
-    gemm_epilogues(p, c, item, 0, PH_HEAD);
+    gemm_phase(p, c, idx, 0, PH_HEAD);
     const int last_bar = 1 + 5 * p.L;
     grid_barrier(p, c, last_bar);
     if (p.do_sample) {
         if (c.cta < p.B) {
             SampleArgs sa{};
-            sa.logits = p.logits; sa.vocab = p.num_audio; sa.num_vq = p.num_vq; sa.rows = p.B * p.num_vq; sa.st = p.st;
+            sa.logits = p.logits; sa.vocab = p.num_audio; sa.num_vq = p.num_vq; sa.rows = p.st->B * p.num_vq; sa.st = p.st;
+            sa.b0 = p.b0;
             __shared__ int s_choice[MAX_VQ];
-            sample_block<true>(sa, c.cta, p.B, reinterpret_cast<float*>(c.ring), s_choice);
+            sample_block<true>(sa, p.b0 + c.cta, p.B, reinterpret_cast<float*>(c.ring), s_choice);
         }
     } else if (c.cta == 0 && tid == 0) {
         p.st->cur_len = cur + 1;
@@ -668,41 +749,26 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_decode_step(const StepParam
     c.S = p.ring_slots;
     c.ring = smem;
     c.areg = smem + (size_t)c.S * SLOT_BYTES;
-    const int areg_bytes = (p.H / 64) * A_KB_BYTES + A_OVERRUN;
+    const int areg_bytes = (p.H / 64) * A_KB_BYTES + DBUF_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(c.areg + areg_bytes);
     c.full = bars;
     c.empty = bars + MAX_RING;
-    c.a_ready = bars + 2 * MAX_RING;
-    c.acc_ready = c.a_ready + 1;
-    c.acc_free = c.a_ready + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c.a_ready + 3);
     c.cta = blockIdx.x;
     c.G = gridDim.x;
+    c.dbg_e = 0;
     c.bar_base = *p.bar_epoch;   // written only by the previous launch's last phase
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp == 4 && lane == 0) {
+    if (warp == NCOMP / 32 && lane == 0) {
         for (int s = 0; s < c.S; ++s) { mbar_init(&c.full[s], 1); mbar_init(&c.empty[s], 1); }
-        mbar_init(c.a_ready, 1);
-        mbar_init(c.acc_ready, 1);
-        mbar_init(c.acc_free, 1);
         fence_barrier_init();
         fence_proxy_async();
     }
-    if (warp == 5) tmem_alloc<64>(tmem_slot);
-    tc_fence_before();
     __syncthreads();
-    tc_fence_after();
-    c.tmem = *tmem_slot;
-    if (warp == 4) {
+    if (warp == NCOMP / 32) {
         if (lane == 0) step_producer(p, c);
-    } else if (warp == 5) {
-        if (lane == 0) step_mma(p, c);
     } else {
         step_compute(p, c);
     }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 5) tmem_dealloc<64>(c.tmem);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -100,7 +100,8 @@ def test_trunk_batch1_long_prompt_split_kv():
 def test_trunk_full_depth_config2_shape():
     """20 layers, B=32, L0=128 (BASELINE.json configs[1] shape), 4 teacher-forced steps."""
     cfg = synth.GPTConfig()
-    _teacher_forced(cfg, B=32, L0=128, steps=4, seed=40)
+    # 20 layers: split-K fp32 atomics make the last bits order-dependent; bound = SURVEY.md §8c (max-abs 2e-2, rel-RMS 5e-3)
+    _teacher_forced(cfg, B=32, L0=128, steps=4, seed=40, tol_rms=2e-3, tol_abs=2e-2)
 
 
 def test_trunk_full_depth_vs_unrounded_fp32_oracle():

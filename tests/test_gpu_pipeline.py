@@ -1,0 +1,131 @@
+"""End-to-end through the public API (ChatTTSPlusPipeline.infer, the call webui.py / tests/test_pipelines.py make) with a
+stand-in tokenizer and synthetic weights, checked against the CPU oracle run on the same ids / speaker / uniforms."""
+import json
+import os
+
+import pytest
+import torch
+
+from chatttsplus_b200 import synth
+from oracle import ctp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+class FakeTok:
+    vocab = {"[spk_emb]": 7, "[break_0]": 90, "[Ebreak]": 91, "[Stts]": 3, "[Ptts]": 4, "[empty_spk]": 5}
+
+    def __len__(self):
+        return 128
+
+    def convert_tokens_to_ids(self, t):
+        return self.vocab.get(t, 1)
+
+    def encode_plus(self, t, return_tensors="pt", add_special_tokens=False, padding=True):
+        ids, i = [], 0
+        while i < len(t):   # bracket tokens -> ids from the table, other characters -> 8..88
+            if t[i] == "[" and "]" in t[i:]:
+                j = t.index("]", i)
+                ids.append(self.vocab.get(t[i:j + 1], 6))
+                i = j + 1
+            else:
+                ids.append(ord(t[i]) % 80 + 8)
+                i += 1
+        ids = torch.tensor([ids])
+        return {"input_ids": ids, "attention_mask": torch.ones_like(ids)}
+
+    def batch_decode(self, x):
+        return [" ".join(str(int(i)) for i in r) for r in x]
+
+
+def _pipeline(layers=3):
+    from chatttsplus_b200.gpt import GPT
+    from chatttsplus_b200.pipeline import ChatTTSPlusPipeline
+    from chatttsplus_b200.tokenizer import Tokenizer
+    from chatttsplus_b200.vocoder import DVAE, Vocos
+    cfg = synth.GPTConfig(num_hidden_layers=layers, num_text_tokens=128)
+    sd = synth.make_gpt_state(cfg, seed=5)
+    gpt = GPT(dict(hidden_size=768, intermediate_size=3072, num_attention_heads=12, num_hidden_layers=layers), num_text_tokens=128, max_batch=4)
+    gpt.load_state_dict(sd)
+    gpt.to("cuda")
+    dcfg, vcfg = synth.DVAEConfig(n_layer=2), synth.VocosConfig(num_layers=2)
+    dsd, vsd = synth.make_dvae_state(dcfg, 6), synth.make_vocos_state(vcfg, 7)
+    d = DVAE(decoder_config=dict(idim=384, odim=384, hidden=512, n_layer=2, bn_dim=128), dim=384)
+    d.load_state_dict(dsd)
+    d.to("cuda")
+    v = Vocos(backbone_config=dict(input_channels=100, dim=512, intermediate_dim=1536, num_layers=2),
+              head_config=dict(dim=512, n_fft=1024, hop_length=256, padding="center"))
+    v.load_state_dict(vsd)
+    v.to("cuda")
+    pipe = ChatTTSPlusPipeline.from_models(Tokenizer(tokenizer=FakeTok()), gpt, d, v, spk_stat=synth.make_spk_stat())
+    return pipe, cfg, sd, dsd, vsd
+
+
+def _oracle(cfg, sd, dsd, vsd, texts, spk, u, max_new, min_new, temp, tok):
+    full = [f"[Stts][spk_emb][speed_5]{t} [uv_break][Ptts]" for t in texts]
+    ids, mask, text_mask = tok.encode(full, 4)
+    emb = O.gpt_embed({k: (v.half().float() if v.dim() > 1 and "parametrizations" not in k else v) for k, v in sd.items()}, ids, text_mask)
+    emb = O.apply_spk_emb(emb, spk, ids, 7)
+    osd = dict(sd)
+    r = O.generate(osd, emb, ids, torch.tensor([temp] * 4), 625, mask, n_layers=cfg.num_hidden_layers, n_heads=12, max_new_token=max_new,
+                   min_new_token=min_new, sampler="uniform", uniforms=u)
+    wavs = [O.vocos_decode(vsd, O.dvae_decode(dsd, h.permute(1, 0)[None], n_layer=2), num_layers=2)[0] for h in r.hiddens]
+    return r, wavs
+
+
+def test_infer_matches_oracle_with_speaker_file(tmp_path):
+    from chattts_plus.commons.utils import InferCodeParams, TorchSeedContext
+    pipe, cfg, sd, dsd, vsd = _pipeline()
+    spk_str = open(os.path.join(os.path.dirname(__file__), "golden", "speaker_2222.txt"), encoding="utf-8").read()
+    spk_path = str(tmp_path / "2222.pt")
+    torch.save(spk_str, spk_path)            # the shipped speaker files are torch-saved b14 strings
+    texts = ["hello there", "a considerably longer second sentence"]
+    max_new = 10
+    params = InferCodeParams(temperature=0.0003, max_new_token=max_new, min_new_token=max_new, show_tqdm=False)
+    with TorchSeedContext(42):
+        u = torch.rand(max_new, len(texts) * 4, device="cuda").cpu()   # the draw GPT.generate makes first
+    with TorchSeedContext(42):
+        gen = pipe.infer(texts, skip_refine_text=True, do_text_normalization=False, do_homophone_replacement=False,
+                         do_text_optimization=False, params_infer_code=params, speaker_emb_path=spk_path, slice_size=4)
+        wavs = []
+        for w in gen:
+            wavs.extend(w)
+    from chatttsplus_b200.tokenizer import Tokenizer
+    spk = torch.from_numpy(Tokenizer._decode_spk_emb(spk_str)).float()
+    ref, ref_wavs = _oracle(cfg, sd, dsd, vsd, texts, spk, u, max_new, max_new, 0.0003, pipe.models_dict["tokenizer"])
+    assert len(wavs) == 2
+    for w, rw in zip(wavs, ref_wavs):
+        assert w.shape == rw.shape == (256 * (2 * max_new - 1),)
+        err = float((w.cpu() - rw).pow(2).mean().sqrt())
+        assert err < 2e-3, err   # hiddens come from the fp16-weight trunk here, so the vocoder input is not bit-identical
+
+
+def test_infer_with_lora_dir_and_random_speaker(tmp_path):
+    from safetensors.torch import save_file
+    from chattts_plus.commons.utils import InferCodeParams, TorchSeedContext
+    pipe, cfg, sd, dsd, vsd = _pipeline(layers=2)
+    lora = {k: v * 3 for k, v in synth.make_lora_state(cfg, r=8, seed=9).items()}
+    d = tmp_path / "adapter"
+    d.mkdir()
+    json.dump({"r": 8, "lora_alpha": 16, "target_modules": ["q_proj", "k_proj", "v_proj", "o_proj"]}, open(d / "adapter_config.json", "w"))
+    save_file(lora, str(d / "adapter_model.safetensors"))
+    params = InferCodeParams(temperature=0.0003, max_new_token=6, min_new_token=6, show_tqdm=False)
+    outs = {}
+    for name, kw in [("base", {}), ("lora", {"lora_path": str(d)}), ("base2", {})]:
+        with TorchSeedContext(7):
+            w = []
+            for x in pipe.infer(["same text"], skip_refine_text=True, do_text_normalization=False, do_homophone_replacement=False,
+                                do_text_optimization=False, params_infer_code=params, speaker_save_dir=str(tmp_path), **kw):
+                w.extend(x)
+        outs[name] = w[0].cpu()
+    assert outs["base"].shape == (256 * 11,)
+    assert torch.allclose(outs["base"], outs["base2"], atol=1e-4), "LoRA must be unloaded after the call"
+    assert (outs["base"] - outs["lora"]).abs().max() > 1e-3, "the adapter changed nothing"
+    assert any(f.endswith(".pt") for f in os.listdir(tmp_path)), "random speaker must be saved (chattts_plus_pipeline.py:553-557)"
+
+
+def test_unbuilt_scope_rows_fail_loudly():
+    from chattts_plus.commons.utils import InferCodeParams
+    pipe, *_ = _pipeline(layers=1)
+    with pytest.raises(NotImplementedError):
+        next(pipe.infer("x", skip_refine_text=False, params_infer_code=InferCodeParams(show_tqdm=False)))
