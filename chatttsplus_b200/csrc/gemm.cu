@@ -74,9 +74,9 @@ int make_tmap_kmajor(CUtensorMap* out, const void* base, long long rows, long lo
 
 template <int BN>
 static int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, long long a_rows, long long b_rows, long long K,
-                     int split_k, const GemmEpilogue& epi, cudaStream_t stream, const void* pf_ptr, unsigned long long pf_bytes) {
+                     int split_k, const GemmEpilogue& epi, cudaStream_t stream, const void* pf_ptr, unsigned long long pf_bytes, bool pdl) {
     GemmShape shp;
-    shp.pf_ptr = pf_ptr; shp.pf_bytes = pf_bytes;
+    shp.pf_ptr = pf_ptr; shp.pf_bytes = pf_bytes; shp.a_independent = pdl ? 1 : 0;
     shp.k_blocks = (int)((K + GEMM_BK - 1) / GEMM_BK);
     shp.dbg = g_dbg;
     shp.desc_lbo = g_desc[0]; shp.desc_sbo = g_desc[1]; shp.desc_layout = g_desc[2]; shp.desc_kadv = g_desc[3];
@@ -87,9 +87,9 @@ static int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, long long a
         return CTP_ERR_INVALID;
     }
     dim3 grid((unsigned)((b_rows + BN - 1) / BN), (unsigned)((a_rows + GEMM_BM - 1) / GEMM_BM), (unsigned)split_k);
-    gemm_tcgen05_kernel<BN><<<grid, GEMM_THREADS, GemmSmem<BN>::TOTAL, stream>>>(tmA, tmB, shp, epi);
+    cudaError_t e = launch_k(gemm_tcgen05_kernel<BN>, grid, dim3(GEMM_THREADS), (size_t)GemmSmem<BN>::TOTAL, stream, pdl, tmA, tmB, shp, epi);
     ctp_count_launch();
-    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
         ctp_set_error("gemm launch failed: %s", cudaGetErrorString(e));
         return CTP_ERR_CUDA;
@@ -98,14 +98,14 @@ static int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, long long a
 }
 
 int gemm_launch_maps(const CUtensorMap& tmA, const CUtensorMap& tmB, long long a_rows, long long b_rows, long long K,
-                     int block_n, int split_k, const GemmEpilogue& epi, cudaStream_t stream, const void* pf_ptr, unsigned long long pf_bytes) {
+                     int block_n, int split_k, const GemmEpilogue& epi, cudaStream_t stream, const void* pf_ptr, unsigned long long pf_bytes, bool pdl) {
     int st = gemm_init();
     if (st) return st;
     switch (block_n) {
-        case 32: return launch_bn<32>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream, pf_ptr, pf_bytes);
-        case 64: return launch_bn<64>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream, pf_ptr, pf_bytes);
-        case 128: return launch_bn<128>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream, pf_ptr, pf_bytes);
-        case 256: return launch_bn<256>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream, pf_ptr, pf_bytes);
+        case 32: return launch_bn<32>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream, pf_ptr, pf_bytes, pdl);
+        case 64: return launch_bn<64>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream, pf_ptr, pf_bytes, pdl);
+        case 128: return launch_bn<128>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream, pf_ptr, pf_bytes, pdl);
+        case 256: return launch_bn<256>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream, pf_ptr, pf_bytes, pdl);
         default: ctp_set_error("gemm: unsupported block_n %d", block_n); return CTP_ERR_INVALID;
     }
 }

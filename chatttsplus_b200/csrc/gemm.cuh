@@ -34,6 +34,7 @@ struct GemmShape {
     // the CTP_DESC environment variable for bring-up diagnostics only
     uint32_t desc_lbo, desc_sbo, desc_layout, desc_kadv;
     long long* dbg;  // bring-up only: per-CTA clock64 stamps [cta][8], or null
+    int a_independent;        // PDL: the M operand (weights in the decode path) does not depend on the previous kernel
     const void* pf_ptr;       // optional: region the NEXT kernel will stream (its weights); every CTA prefetches a share into L2
     unsigned long long pf_bytes;
 };
@@ -162,6 +163,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int nkb = kb1 - kb0;
     long long* dbg = shp.dbg ? shp.dbg + ((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
     if (dbg && threadIdx.x == 0) dbg[0] = clock64();
+    pdl_launch_dependents();
 
     if (warp == 4 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -180,10 +182,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (dbg && threadIdx.x == 0) dbg[1] = clock64();
+    const bool early_a = shp.a_independent != 0;
+    if (!(early_a && warp == 4 && lane == 0)) pdl_wait();   // the producer thread waits after issuing the weight loads
 
     if (warp == 4) {
         if (lane == 0) {
-            for (int i = 0; i < nkb; ++i) {
+            int pre = 0;
+            if (early_a) {
+                // weights first (they do not depend on the previous kernel), then wait, then the activation halves
+                pre = nkb < STAGES ? nkb : STAGES;
+                for (int i = 0; i < pre; ++i) {
+                    mbar_expect_tx(&full_bar[i], S::STAGE_BYTES);
+                    tma_load_2d(&tmA, &full_bar[i], ring + i * S::STAGE_BYTES, (kb0 + i) * GEMM_BK, m0);
+                }
+                pdl_wait();
+                for (int i = 0; i < pre; ++i)
+                    tma_load_2d(&tmB, &full_bar[i], ring + i * S::STAGE_BYTES + S::A_BYTES, (kb0 + i) * GEMM_BK, n0);
+            }
+            for (int i = pre; i < nkb; ++i) {
                 const int s = i % STAGES;
                 const uint32_t ph = (i / STAGES) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
@@ -302,7 +318,7 @@ int gemm_launch(const GemmLaunch& g, cudaStream_t stream);
 // Variant with prebuilt tensor maps (decode path: maps are created once at bind time).
 int gemm_launch_maps(const CUtensorMap& tmA, const CUtensorMap& tmB, long long a_rows, long long b_rows, long long K,
                      int block_n, int split_k, const GemmEpilogue& epi, cudaStream_t stream, const void* pf_ptr = nullptr,
-                     unsigned long long pf_bytes = 0);
+                     unsigned long long pf_bytes = 0, bool pdl = false);
 int gemm_init();  // resolves cuTensorMapEncodeTiled, sets max dynamic smem attributes
 
 }  // namespace ctp

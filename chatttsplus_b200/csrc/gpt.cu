@@ -68,6 +68,7 @@ struct ctp_gpt {
     float* qbuf = nullptr; __half* attn_p = nullptr; __half* h_p = nullptr;
     unsigned long long* bar = nullptr;   // [0] arrivals counter, [1] epoch (arrivals completed by previous launches)
     int sm_count = 0, step_smem = 0, ring_slots = 0;
+    bool use_pdl = true;     // programmatic dependent launch between the kernels of the decode step graph (CTP_PDL=0 disables)
     bool fused_ok = false;
     bool use_fused = false;  // measured (profiles/README.md): the per-op graph path is faster today; CTP_DECODE_IMPL=fused selects the fused kernel
     // lanes: the batch is split into K contiguous row slices, each running its own fused-step kernel on its own stream over
@@ -181,6 +182,7 @@ extern "C" ctp_status ctp_gpt_create(ctp_gpt** out, const ctp_gpt_cfg* cfg) {
         h->step_smem = S * SLOT_BYTES + fixed;
         h->fused_ok = (S >= 7) && (I % 192 == 0) && (H % 64 == 0) && cfg->num_vq <= 4 && cfg->num_audio <= 640 && mb <= 32;
         if (const char* e = getenv("CTP_DECODE_IMPL")) h->use_fused = (strcmp(e, "fused") == 0);
+        if (const char* e = getenv("CTP_PDL")) h->use_pdl = atoi(e) != 0;
         if (h->fused_ok) {
             CK(cudaFuncSetAttribute(k_decode_step, cudaFuncAttributeMaxDynamicSharedMemorySize, h->step_smem));
             const size_t L = cfg->n_layers;
@@ -327,14 +329,14 @@ static int split_for(int k_blocks, int m_tiles, int target_ctas = 148) {
 #define LAUNCH_OK() do { ctp_count_launch(); cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { ctp_set_error("%s:%d launch: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); return CTP_ERR_CUDA; } } while (0)
 
 // heads: logits[b][q*A + a] = hidden_n[b] . head_code[q*A + a]   (gpt.py:424-439; weight_norm folded at bind)
-static int launch_heads(ctp_gpt* h, int B, cudaStream_t s) {
+static int launch_heads(ctp_gpt* h, int B, cudaStream_t s, bool pdl = false) {
     const ctp_gpt_cfg& c = h->cfg;
     const int F = c.num_vq * c.num_audio;
     const int bn = B <= 32 ? 32 : 64;
     const ActMaps& am = bn == 32 ? h->act32 : h->act64;
     const int m_tiles = (F + GEMM_BM - 1) / GEMM_BM;
     GemmEpilogue e = epi_swap_atomic(h->logits, F, B, F);
-    return gemm_launch_maps(h->head_map, am.xn, F, B, c.hidden, bn, split_for(c.hidden / 64, m_tiles), e, s);
+    return gemm_launch_maps(h->head_map, am.xn, F, B, c.hidden, bn, split_for(c.hidden / 64, m_tiles), e, s, nullptr, 0, pdl);
 }
 
 // bring-up hook (not in include/ctp.h): device buffer [n_cta][128][2] of clock64 stamps around every grid barrier
@@ -377,8 +379,11 @@ static int run_decode_fused_lane(ctp_gpt* h, int b0, int B, int grid, float* x, 
 }
 
 // One decode trunk step for B sequences (ids_ext == nullptr -> codes of the previous sample step).
+#define CTP_LAUNCH(kern, grid, block, smem, ...) do { cudaError_t _le = launch_k(kern, grid, block, (size_t)(smem), s, pdl, __VA_ARGS__); ctp_count_launch(); if (_le == cudaSuccess) _le = cudaGetLastError(); if (_le != cudaSuccess) { ctp_set_error("%s:%d launch %s: %s", __FILE__, __LINE__, #kern, cudaGetErrorString(_le)); return CTP_ERR_CUDA; } } while (0)
+
 static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, cudaStream_t s) {
     const ctp_gpt_cfg& c = h->cfg;
+    const bool pdl = h->use_pdl;
     const int H = c.hidden, I = c.inter;
     const int bn = B <= 32 ? 32 : 64;
     const ActMaps& am = bn == 32 ? h->act32 : h->act64;
@@ -388,65 +393,58 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
         na.x = h->x; na.w = h->w.ln1 + (size_t)l * H; na.xn = h->xn; na.H = H; na.eps = c.rms_eps;
         na.zero_buf = h->acc_qkv; na.zero_n = 3 * H;
         if (l == 0) { na.st = h->st; na.ids_ext = ids_ext; na.emb_code = (const __half*)h->w.emb_code; na.num_vq = c.num_vq; na.num_audio = c.num_audio; }
-        k_rmsnorm<<<B, 256, 0, s>>>(na);
-        LAUNCH_OK();
+        CTP_LAUNCH(k_rmsnorm, dim3(B), dim3(256), 0, na);
         {   // q,k,v projections as one GEMM (llama.py:619-621), weights are the M operand
             GemmEpilogue e = epi_swap_atomic(h->acc_qkv, 3 * H, B, 3 * H);
             if ((st = gemm_launch_maps(h->lmaps[l].wqkv, am.xn, 3 * H, B, H, bn, split_for(H / 64, 3 * H / GEMM_BM), e, s,
-                                       (const __half*)h->w.wo + (size_t)l * H * H, sizeof(__half) * (size_t)H * H))) return st;
+                                       (const __half*)h->w.wo + (size_t)l * H * H, sizeof(__half) * (size_t)H * H, pdl))) return st;
         }
         AttnDecArgs aa{};
         aa.qkv = h->acc_qkv; aa.kcache = h->kplane(l); aa.vcache = h->vplane(l); aa.out = h->attn; aa.part = h->attn_part;
         aa.counters = h->attn_cnt; aa.pad_len = h->pad_len; aa.st = h->st; aa.inv_freq = h->inv_freq;
         aa.H = H; aa.nH = c.n_heads; aa.max_seq = c.max_seq;
-        k_attn_decode<<<dim3(c.n_heads, B, nsplit), 128, 0, s>>>(aa);
-        LAUNCH_OK();
+        CTP_LAUNCH(k_attn_decode, dim3(c.n_heads, B, nsplit), dim3(128), 0, aa);
         {   // o_proj accumulated straight into the residual stream (llama.py:663-666,737)
             GemmEpilogue e = epi_swap_atomic(h->x, H, B, H);
             if ((st = gemm_launch_maps(h->lmaps[l].wo, am.attn, H, B, H, bn, split_for(H / 64, (H + GEMM_BM - 1) / GEMM_BM), e, s,
-                                       (const __half*)h->w.wgu + (size_t)l * 2 * I * H, sizeof(__half) * (size_t)2 * I * H))) return st;
+                                       (const __half*)h->w.wgu + (size_t)l * 2 * I * H, sizeof(__half) * (size_t)2 * I * H, pdl))) return st;
         }
         NormArgs nb{};
         nb.x = h->x; nb.w = h->w.ln2 + (size_t)l * H; nb.xn = h->xn; nb.H = H; nb.eps = c.rms_eps;
         nb.zero_buf = h->acc_gu; nb.zero_n = 2 * I;
-        k_rmsnorm<<<B, 256, 0, s>>>(nb);
-        LAUNCH_OK();
+        CTP_LAUNCH(k_rmsnorm, dim3(B), dim3(256), 0, nb);
         {   // gate_proj | up_proj (llama.py:214)
             GemmEpilogue e = epi_swap_atomic(h->acc_gu, 2 * I, B, 2 * I);
             if ((st = gemm_launch_maps(h->lmaps[l].wgu, am.xn, 2 * I, B, H, bn, split_for(H / 64, 2 * I / GEMM_BM), e, s,
-                                       (const __half*)h->w.wdown + (size_t)l * H * I, sizeof(__half) * (size_t)H * I))) return st;
+                                       (const __half*)h->w.wdown + (size_t)l * H * I, sizeof(__half) * (size_t)H * I, pdl))) return st;
         }
         {
             const long long total = (long long)B * I;
-            k_silu_mul<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(h->acc_gu, h->hmid, I, total);
-            LAUNCH_OK();
+            CTP_LAUNCH(k_silu_mul, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (const float*)h->acc_gu, h->hmid, I, total);
         }
         {   // down_proj accumulated into the residual stream (llama.py:214,745)
             GemmEpilogue e = epi_swap_atomic(h->x, H, B, H);
             const void* nxt = (l + 1 < c.n_layers) ? (const void*)((const __half*)h->w.wqkv + (size_t)(l + 1) * 3 * H * H) : h->w.head_code;
             const size_t nxt_bytes = (l + 1 < c.n_layers) ? sizeof(__half) * (size_t)3 * H * H : sizeof(__half) * (size_t)c.num_vq * c.num_audio * H;
-            if ((st = gemm_launch_maps(h->lmaps[l].wdown, am.hmid, H, B, I, bn, split_for(I / 64, (H + GEMM_BM - 1) / GEMM_BM), e, s, nxt, nxt_bytes))) return st;
+            if ((st = gemm_launch_maps(h->lmaps[l].wdown, am.hmid, H, B, I, bn, split_for(I / 64, (H + GEMM_BM - 1) / GEMM_BM), e, s, nxt, nxt_bytes, pdl))) return st;
         }
     }
     // final norm (llama.py:1002) -> hidden state of this step (gpt.py:422-423) + operand of the heads
     NormArgs nf{};
     nf.x = h->x; nf.w = h->w.norm_f; nf.xn = h->xn; nf.out_f32 = h->hidden; nf.H = H; nf.eps = c.rms_eps;
     nf.zero_buf = h->logits; nf.zero_n = c.num_vq * c.num_audio; nf.st = h->st; nf.write_hid = 1;
-    k_rmsnorm<<<B, 256, 0, s>>>(nf);
-    LAUNCH_OK();
-    if ((st = launch_heads(h, B, s))) return st;
-    k_advance_len<<<1, 1, 0, s>>>(h->st);
-    LAUNCH_OK();
+    CTP_LAUNCH(k_rmsnorm, dim3(B), dim3(256), 0, nf);
+    if ((st = launch_heads(h, B, s, pdl))) return st;
+    CTP_LAUNCH(k_advance_len, dim3(1), dim3(1), 0, h->st);
     return CTP_OK;
 }
 
-static int launch_sampler(ctp_gpt* h, int B, cudaStream_t s) {
+static int launch_sampler(ctp_gpt* h, int B, cudaStream_t s, bool pdl = false) {
     const ctp_gpt_cfg& c = h->cfg;
     SampleArgs sa{};
     sa.logits = h->logits; sa.vocab = c.num_audio; sa.num_vq = c.num_vq; sa.rows = B * c.num_vq; sa.st = h->st;
     const size_t smem = sizeof(float) * c.num_vq * ((c.num_audio + 31) & ~31);
-    k_sample<<<B, 32 * c.num_vq, smem, s>>>(sa);
-    LAUNCH_OK();
+    CTP_LAUNCH(k_sample, dim3(B), dim3(32 * c.num_vq), smem, sa);
     return CTP_OK;
 }
 
@@ -610,7 +608,7 @@ static int get_graph(ctp_gpt* h, int B, int nsplit, cudaGraphExec_t* out) {
     CTP_CUDA_OK(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
     ctp_count_capture_begin();
     int st = run_decode_trunk(h, B, nsplit, nullptr, h->cap_stream);
-    if (!st) st = launch_sampler(h, B, h->cap_stream);
+    if (!st) st = launch_sampler(h, B, h->cap_stream, h->use_pdl);
     const long long n_nodes = ctp_count_capture_end();
     cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
     if (st) { if (graph) cudaGraphDestroy(graph); return st; }

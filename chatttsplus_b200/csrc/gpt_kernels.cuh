@@ -76,6 +76,8 @@ struct NormArgs {
 };
 
 __global__ void __launch_bounds__(256) k_rmsnorm(NormArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x;
     __shared__ float red[8];
     __shared__ int sid[MAX_VQ];
@@ -126,6 +128,8 @@ __global__ void __launch_bounds__(256) k_rmsnorm(NormArgs a) {
 
 // h = silu(gate) * up   (llama.py:214), gate/up read from the fp32 accumulator [rows][2I]
 __global__ void k_silu_mul(const float* __restrict__ gu, __half* __restrict__ out, int I, long long total) {
+    pdl_launch_dependents();
+    pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const long long r = i / I;
@@ -155,6 +159,8 @@ struct AttnDecArgs {
 };
 
 __global__ void __launch_bounds__(128) k_attn_decode(AttnDecArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z, nsplit = gridDim.z;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cur = a.st->cur_len;  // new token's slot
@@ -597,12 +603,18 @@ __device__ __forceinline__ void sample_block(const SampleArgs& a, const int b, c
 
 // blockDim = 32 * num_vq; block b handles rows b*num_vq .. b*num_vq + num_vq-1.
 __global__ void k_sample(SampleArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float s_scores_dyn[];  // [num_vq][vocab_pad]
     __shared__ int s_choice[MAX_VQ];
     sample_block<false>(a, blockIdx.x, gridDim.x, s_scores_dyn, s_choice);
 }
 
 // cur_len += 1 after a trunk step (the new token's K/V now occupy slot cur_len)
-__global__ void k_advance_len(GenState* st) { st->cur_len += 1; }
+__global__ void k_advance_len(GenState* st) {
+    pdl_launch_dependents();
+    pdl_wait();
+    st->cur_len += 1;
+}
 
 }  // namespace ctp
