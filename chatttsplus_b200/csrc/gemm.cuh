@@ -48,8 +48,10 @@ struct GemmSmem {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
     static constexpr int B_BYTES = BN * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    // <= 200 KB of operand ring; leaves room for the barrier block and 1 KB alignment slack under 227 KB
-    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+    // <= 200 KB of operand ring; leaves room for the barrier block and 1 KB alignment slack under 227 KB.
+    // BN=32 is the decode path (<= 4 k-blocks per CTA after split-K): 4 stages = 83 KB so that two CTAs — e.g. of two
+    // independent half-batch chains — fit on one SM.
+    static constexpr int STAGES = BN == 32 ? 4 : ((200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES);
     static constexpr int BAR_BYTES = 256;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
 };

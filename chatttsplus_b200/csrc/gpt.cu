@@ -23,8 +23,8 @@ struct ActMaps {  // activation operands (N side) for one N-tile width
 };
 
 struct GraphKey {
-    int B, nsplit;
-    bool operator<(const GraphKey& o) const { return B != o.B ? B < o.B : nsplit < o.nsplit; }
+    int B, nsplit, text;
+    bool operator<(const GraphKey& o) const { return B != o.B ? B < o.B : (nsplit != o.nsplit ? nsplit < o.nsplit : text < o.text); }
 };
 
 }  // namespace
@@ -57,6 +57,9 @@ struct ctp_gpt {
 
     std::vector<LayerMaps> lmaps;
     CUtensorMap head_map{};
+    CUtensorMap head_text_map{};
+    bool have_head_text = false;
+    int text_mode = 0;       // current generation is the refine-text pass
     ActMaps act32{}, act64{};
     // decode activation maps point at the first max_batch rows of xn / attn / hmid
     std::map<GraphKey, cudaGraphExec_t> graphs;
@@ -151,7 +154,7 @@ extern "C" ctp_status ctp_gpt_create(ctp_gpt** out, const ctp_gpt_cfg* cfg) {
     CK(cudaMemset(h->kv, 0, kv_elems * sizeof(__half)));
     CK(cudaMalloc(&h->x_last, sizeof(float) * mb * H));
     CK(cudaMalloc(&h->hidden, sizeof(float) * mb * H));
-    const size_t lg = (size_t)mb * std::max(cfg->num_vq * cfg->num_audio, 1);
+    const size_t lg = (size_t)mb * std::max(cfg->num_vq * cfg->num_audio, cfg->num_text);
     CK(cudaMalloc(&h->logits, sizeof(float) * lg));
     CK(cudaMalloc(&h->attn_part, sizeof(float) * (size_t)mb * cfg->n_heads * h->max_splits * 66));
     CK(cudaMalloc(&h->attn_cnt, sizeof(int) * mb * cfg->n_heads));
@@ -163,6 +166,7 @@ extern "C" ctp_status ctp_gpt_create(ctp_gpt** out, const ctp_gpt_cfg* cfg) {
     CK(cudaMemset(h->st, 0, sizeof(GenState)));
     CK(cudaMallocHost(&h->st_pin, sizeof(GenState)));
     CK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    CK(cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     {
         // llama.py:98 — inv_freq = 1 / base^(2i/d), evaluated in fp32 like torch does
         float f[32];
@@ -269,6 +273,11 @@ extern "C" ctp_status ctp_gpt_bind_weights(ctp_gpt* h, const ctp_gpt_weights* w)
         if ((st = make_tmap_kmajor(&m.wdown, wd, H, I, I, GEMM_BM))) return (ctp_status)st;
     }
     if ((st = make_tmap_kmajor(&h->head_map, w->head_code, (long long)c.num_vq * c.num_audio, H, H, GEMM_BM))) return (ctp_status)st;
+    h->have_head_text = false;
+    if (w->head_text && w->emb_text) {
+        if ((st = make_tmap_kmajor(&h->head_text_map, w->head_text, (long long)c.num_text, H, H, GEMM_BM))) return (ctp_status)st;
+        h->have_head_text = true;
+    }
     if (h->fused_ok) {   // per-item pre-swizzled blobs for the fused step kernel (one bulk copy fills a ring slot)
         const int nH = c.n_heads, nkbH = (int)(H / 64), nkbI = (int)(I / 64);
         for (int l = 0; l < c.n_layers; ++l) {
@@ -331,12 +340,12 @@ static int split_for(int k_blocks, int m_tiles, int target_ctas = 148) {
 // heads: logits[b][q*A + a] = hidden_n[b] . head_code[q*A + a]   (gpt.py:424-439; weight_norm folded at bind)
 static int launch_heads(ctp_gpt* h, int B, cudaStream_t s, bool pdl = false) {
     const ctp_gpt_cfg& c = h->cfg;
-    const int F = c.num_vq * c.num_audio;
+    const int F = h->text_mode ? c.num_text : c.num_vq * c.num_audio;   // head_text (gpt.py:425-426) or the 4 code heads
     const int bn = B <= 32 ? 32 : 64;
     const ActMaps& am = bn == 32 ? h->act32 : h->act64;
     const int m_tiles = (F + GEMM_BM - 1) / GEMM_BM;
     GemmEpilogue e = epi_swap_atomic(h->logits, F, B, F);
-    return gemm_launch_maps(h->head_map, am.xn, F, B, c.hidden, bn, split_for(c.hidden / 64, m_tiles), e, s, nullptr, 0, pdl);
+    return gemm_launch_maps(h->text_mode ? h->head_text_map : h->head_map, am.xn, F, B, c.hidden, bn, split_for(c.hidden / 64, m_tiles), e, s, nullptr, 0, pdl);
 }
 
 // bring-up hook (not in include/ctp.h): device buffer [n_cta][128][2] of clock64 stamps around every grid barrier
@@ -392,7 +401,8 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
         NormArgs na{};
         na.x = h->x; na.w = h->w.ln1 + (size_t)l * H; na.xn = h->xn; na.H = H; na.eps = c.rms_eps;
         na.zero_buf = h->acc_qkv; na.zero_n = 3 * H;
-        if (l == 0) { na.st = h->st; na.ids_ext = ids_ext; na.emb_code = (const __half*)h->w.emb_code; na.num_vq = c.num_vq; na.num_audio = c.num_audio; }
+        if (l == 0) { na.st = h->st; na.ids_ext = ids_ext; na.emb_code = (const __half*)h->w.emb_code; na.num_vq = c.num_vq; na.num_audio = c.num_audio;
+                      na.emb_text = h->text_mode ? (const __half*)h->w.emb_text : nullptr; }
         CTP_LAUNCH(k_rmsnorm, dim3(B), dim3(256), 0, na);
         {   // q,k,v projections as one GEMM (llama.py:619-621), weights are the M operand
             GemmEpilogue e = epi_swap_atomic(h->acc_qkv, 3 * H, B, 3 * H);
@@ -432,7 +442,7 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
     // final norm (llama.py:1002) -> hidden state of this step (gpt.py:422-423) + operand of the heads
     NormArgs nf{};
     nf.x = h->x; nf.w = h->w.norm_f; nf.xn = h->xn; nf.out_f32 = h->hidden; nf.H = H; nf.eps = c.rms_eps;
-    nf.zero_buf = h->logits; nf.zero_n = c.num_vq * c.num_audio; nf.st = h->st; nf.write_hid = 1;
+    nf.zero_buf = h->logits; nf.zero_n = h->text_mode ? c.num_text : c.num_vq * c.num_audio; nf.st = h->st; nf.write_hid = 1;
     CTP_LAUNCH(k_rmsnorm, dim3(B), dim3(256), 0, nf);
     if ((st = launch_heads(h, B, s, pdl))) return st;
     CTP_LAUNCH(k_advance_len, dim3(1), dim3(1), 0, h->st);
@@ -442,9 +452,11 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
 static int launch_sampler(ctp_gpt* h, int B, cudaStream_t s, bool pdl = false) {
     const ctp_gpt_cfg& c = h->cfg;
     SampleArgs sa{};
-    sa.logits = h->logits; sa.vocab = c.num_audio; sa.num_vq = c.num_vq; sa.rows = B * c.num_vq; sa.st = h->st;
-    const size_t smem = sizeof(float) * c.num_vq * ((c.num_audio + 31) & ~31);
-    CTP_LAUNCH(k_sample, dim3(B), dim3(32 * c.num_vq), smem, sa);
+    const int cols = h->text_mode ? 1 : c.num_vq;
+    const int V = h->text_mode ? c.num_text : c.num_audio;
+    sa.logits = h->logits; sa.vocab = V; sa.num_vq = cols; sa.ids_cols = c.num_vq; sa.rows = B * cols; sa.st = h->st;
+    const size_t smem = sizeof(float) * cols * ((V + 31) & ~31);
+    CTP_LAUNCH(k_sample, dim3(B), dim3(32 * cols), smem, sa);
     return CTP_OK;
 }
 
@@ -460,7 +472,8 @@ static int nsplit_for(const ctp_gpt* h, int B, int ctx_len) {
 extern "C" ctp_status ctp_gpt_prefill(ctp_gpt* h, int32_t B, int32_t L0, const float* emb, const int32_t* pad_len_host,
                                       const ctp_gen_buffers* bufs, int32_t infer_text, ctp_stream stream) {
     CTP_REQUIRE(h && h->bound, "prefill: weights not bound");
-    CTP_REQUIRE(!infer_text, "prefill: infer_text (refine-text pass) is not built yet (SURVEY.md §8f row f1)");
+    CTP_REQUIRE(!infer_text || h->have_head_text, "prefill: infer_text needs emb_text / head_text bound");
+    h->text_mode = infer_text ? 1 : 0;
     const ctp_gpt_cfg& c = h->cfg;
     CTP_REQUIRE(B >= 1 && B <= c.max_batch, "prefill: batch %d outside [1,%d]", B, c.max_batch);
     CTP_REQUIRE(L0 >= 1 && L0 < c.max_seq, "prefill: prompt length %d does not fit max_seq %d", L0, c.max_seq);
@@ -481,7 +494,7 @@ extern "C" ctp_status ctp_gpt_prefill(ctp_gpt* h, int32_t B, int32_t L0, const f
     // generation state
     GenState gs{};
     gs.cur_len = L0; gs.step = 0; gs.B = B; gs.max_new = bufs->max_new; gs.ids_buf = bufs->ids; gs.hid_buf = bufs->hiddens;
-    gs.end_idx = bufs->end_idx; gs.finish = bufs->finish; gs.u_base = nullptr; gs.all_done = 0; gs.ticket = 0;
+    gs.end_idx = bufs->end_idx; gs.finish = bufs->finish; gs.u_base = nullptr; gs.all_done = 0; gs.ticket = 0; gs.text_mode = infer_text ? 1 : 0;
     CTP_CUDA_OK(cudaMemcpyAsync(h->st, &gs, sizeof(gs), cudaMemcpyHostToDevice, s));
     CTP_CUDA_OK(cudaMemsetAsync(bufs->end_idx, 0, sizeof(int) * B, s));
     CTP_CUDA_OK(cudaMemsetAsync(bufs->finish, 0, B, s));
@@ -547,7 +560,7 @@ extern "C" ctp_status ctp_gpt_prefill(ctp_gpt* h, int32_t B, int32_t L0, const f
     CTP_CUDA_OK(cudaMemcpyAsync(h->x, h->x_last, sizeof(float) * B * H, cudaMemcpyDeviceToDevice, s));
     NormArgs nf{};
     nf.x = h->x; nf.w = h->w.norm_f; nf.xn = h->xn; nf.out_f32 = h->hidden; nf.H = H; nf.eps = c.rms_eps;
-    nf.zero_buf = h->logits; nf.zero_n = c.num_vq * c.num_audio; nf.st = h->st; nf.write_hid = 1;
+    nf.zero_buf = h->logits; nf.zero_n = infer_text ? c.num_text : c.num_vq * c.num_audio; nf.st = h->st; nf.write_hid = 1;
     k_rmsnorm<<<B, 256, 0, s>>>(nf);
     LAUNCH_OK();
     if ((st = launch_heads(h, B, s))) return (ctp_status)st;
@@ -560,7 +573,7 @@ extern "C" ctp_status ctp_gpt_decode_step(ctp_gpt* h, const int32_t* ids, ctp_st
     CTP_REQUIRE(h->cur_len + 1 <= h->cfg.max_seq, "decode_step: KV cache full (%d slots)", h->cfg.max_seq);
     CTP_REQUIRE(ids != nullptr || h->step >= 1, "decode_step: no sampled codes yet and no ids given");
     int st;
-    if (h->fused_ok && h->use_fused && h->B <= 32) st = run_decode_fused(h, h->B, ids, 0, (cudaStream_t)stream);
+    if (h->fused_ok && h->use_fused && h->B <= 32 && !h->text_mode) st = run_decode_fused(h, h->B, ids, 0, (cudaStream_t)stream);
     else st = run_decode_trunk(h, h->B, nsplit_for(h, h->B, h->cur_len + 1), ids, (cudaStream_t)stream);
     if (st) return (ctp_status)st;
     h->cur_len += 1;
@@ -593,7 +606,7 @@ extern "C" ctp_status ctp_gpt_sample_step(ctp_gpt* h, const ctp_sample_cfg* cfg,
     if (st) return (ctp_status)st;
     cudaStream_t s = (cudaStream_t)stream;
     // single-step mode: u is [B*num_vq] for this step -> bias the base so that base + step*rows == u
-    const float* ubase = u ? u - (long long)h->step * h->B * h->cfg.num_vq : nullptr;
+    const float* ubase = u ? u - (long long)h->step * h->B * (h->text_mode ? 1 : h->cfg.num_vq) : nullptr;
     if ((st = upload_sample_state(h, cfg, ubase, s))) return (ctp_status)st;
     if ((st = launch_sampler(h, h->B, s))) return (ctp_status)st;
     h->step += 1;
@@ -601,7 +614,7 @@ extern "C" ctp_status ctp_gpt_sample_step(ctp_gpt* h, const ctp_sample_cfg* cfg,
 }
 
 static int get_graph(ctp_gpt* h, int B, int nsplit, cudaGraphExec_t* out) {
-    GraphKey key{B, nsplit};
+    GraphKey key{B, nsplit, h->text_mode};
     auto it = h->graphs.find(key);
     if (it != h->graphs.end()) { *out = it->second; return CTP_OK; }
     cudaGraph_t graph = nullptr;
@@ -640,7 +653,7 @@ extern "C" ctp_status ctp_gpt_generate(ctp_gpt* h, const ctp_sample_cfg* cfg, in
     CTP_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     bool pending = false;
     h->st_pin->all_done = 0;
-    const bool fused = h->fused_ok && h->use_fused && h->B <= 32;
+    const bool fused = h->fused_ok && h->use_fused && h->B <= 32 && !h->text_mode;
     int K = fused ? h->n_lanes : 1;
     while (K > 1 && (h->B < K || h->sm_count / K < 8)) K /= 2;
     if (fused && K > 1) {
@@ -700,7 +713,7 @@ extern "C" ctp_status ctp_gpt_generate(ctp_gpt* h, const ctp_sample_cfg* cfg, in
         } else {
             cudaGraphExec_t g;
             if ((st = get_graph(h, h->B, nsplit_for(h, h->B, h->cur_len + 1), &g))) { cudaEventDestroy(ev); return (ctp_status)st; }
-            ctp_count_launch((int)h->graph_nodes[GraphKey{h->B, nsplit_for(h, h->B, h->cur_len + 1)}]);
+            ctp_count_launch((int)h->graph_nodes[GraphKey{h->B, nsplit_for(h, h->B, h->cur_len + 1), h->text_mode}]);
             cudaError_t e = cudaGraphLaunch(g, s);
             if (e != cudaSuccess) { ctp_set_error("graph launch: %s", cudaGetErrorString(e)); cudaEventDestroy(ev); return CTP_ERR_CUDA; }
         }
@@ -728,7 +741,7 @@ extern "C" const float* ctp_gpt_hidden(ctp_gpt* h) { return h ? h->hidden : null
 extern "C" ctp_status ctp_gpt_copy_outputs(ctp_gpt* h, float* logits_out, float* hidden_out, ctp_stream stream) {
     CTP_REQUIRE(h && h->have_bufs, "copy_outputs: call prefill first");
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t nl = (size_t)h->B * h->cfg.num_vq * h->cfg.num_audio;
+    const size_t nl = (size_t)h->B * (h->text_mode ? h->cfg.num_text : h->cfg.num_vq * h->cfg.num_audio);
     if (logits_out) CTP_CUDA_OK(cudaMemcpyAsync(logits_out, h->logits, nl * sizeof(float), cudaMemcpyDeviceToDevice, s));
     if (hidden_out) CTP_CUDA_OK(cudaMemcpyAsync(hidden_out, h->hidden, (size_t)h->B * h->cfg.hidden * sizeof(float), cudaMemcpyDeviceToDevice, s));
     return CTP_OK;
@@ -755,8 +768,10 @@ extern "C" ctp_status ctp_sample(int32_t rows, int32_t vocab, int32_t num_vq, co
     SampleArgs sa{};
     sa.logits = logits; sa.vocab = vocab; sa.num_vq = num_vq; sa.rows = rows; sa.hist = history; sa.hist_stride = hist_stride;
     sa.hist_len = hist_len; sa.u = u; sa.step = step; sa.cfg = *cfg; sa.next_ids = next_ids; sa.probs_out = probs_out; sa.st = nullptr;
+    sa.ids_cols = num_vq;
     const size_t smem = sizeof(float) * num_vq * ((vocab + 31) & ~31);
-    CTP_REQUIRE(smem <= 48 * 1024, "sample: vocab %d too large for the warp sampler", vocab);
+    CTP_REQUIRE(smem <= 100 * 1024, "sample: vocab %d too large for the warp sampler", vocab);
+    CTP_CUDA_OK(cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     k_sample<<<rows / num_vq, 32 * num_vq, smem, (cudaStream_t)stream>>>(sa);
     ctp_count_launch();
     CTP_CUDA_OK(cudaGetLastError());

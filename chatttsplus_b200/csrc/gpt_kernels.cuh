@@ -23,6 +23,7 @@ struct GenState {
     const float* u_base;     // [max_new][B*num_vq] or null
     int all_done;            // set by the sampler when every sequence has finished
     int ticket;              // scratch counter
+    int text_mode;           // 1: refine-text pass (infer_text=True): text embedding in, head_text logits, one sampling column
     ctp_sample_cfg cfg;
 };
 
@@ -71,6 +72,7 @@ struct NormArgs {
     const GenState* st;       // null -> no embedding
     const int* ids_ext;       // [B][num_vq] or null (then ids_buf[b][step-1])
     const __half* emb_code;
+    const __half* emb_text;   // text mode: x = emb_text[ids[b][0]]  (gpt.py:400-401)
     int num_vq, num_audio;
     int write_hid;            // 1: also copy out_f32 row into st->hid_buf[b][step]
 };
@@ -96,8 +98,12 @@ __global__ void __launch_bounds__(256) k_rmsnorm(NormArgs a) {
     for (int c = threadIdx.x; c < a.H; c += 256, ++n) {
         float v;
         if (embed) {
-            v = 0.f;
-            for (int q = 0; q < a.num_vq; ++q) v += __half2float(a.emb_code[((long long)q * a.num_audio + sid[q]) * a.H + c]);
+            if (a.emb_text) {
+                v = __half2float(a.emb_text[(long long)sid[0] * a.H + c]);
+            } else {
+                v = 0.f;
+                for (int q = 0; q < a.num_vq; ++q) v += __half2float(a.emb_code[((long long)q * a.num_audio + sid[q]) * a.H + c]);
+            }
             x[c] = v;
         } else {
             v = x[c];
@@ -417,7 +423,8 @@ constexpr int SAMPLE_MAX_K = 32;
 
 struct SampleArgs {
     const float* logits;   // [rows][vocab]
-    int vocab, num_vq, rows;
+    int vocab, num_vq, rows;   // num_vq = sampling columns per batch row (1 in text mode)
+    int ids_cols;              // columns of the ids / history buffers per token (the model's num_vq)
     // history for the repetition penalty: row r looks at hist[r_b][t][r_q], t in [hist_len - window, hist_len)
     const int* hist;       // element (b, t, q) at hist[(b*hist_stride + t)*num_vq + q]
     int hist_stride;       // tokens per batch row in the history buffer
@@ -475,7 +482,7 @@ __device__ __forceinline__ void sample_block(const SampleArgs& a, const int b, c
     if (cfg.rep_penalty != 1.0f && row < cfg.rep_max_ids) {
         const int w = min(hist_len, cfg.rep_window);
         int my = -1;
-        if (lane < w) my = hist[((long long)b * hstride + (hist_len - w + lane)) * a.num_vq + warp];
+        if (lane < w) my = hist[((long long)b * hstride + (hist_len - w + lane)) * a.ids_cols + warp];
         int mult = 0;
         bool first = true;
         for (int t = 0; t < w; ++t) {
@@ -578,9 +585,10 @@ __device__ __forceinline__ void sample_block(const SampleArgs& a, const int b, c
         if (threadIdx.x == 0) {
             GenState* st = a.st;
             bool eos = false;
-            for (int q = 0; q < a.num_vq; ++q) {
-                eos |= (s_choice[q] == cfg.eos);
-                if (step < st->max_new) st->ids_buf[((long long)b * st->max_new + step) * a.num_vq + q] = s_choice[q];
+            for (int q = 0; q < a.num_vq; ++q) eos |= (s_choice[q] == cfg.eos);
+            if (step < st->max_new) {   // text mode: the sampled id goes to every VQ column (gpt.py:489-494)
+                for (int q = 0; q < a.ids_cols; ++q)
+                    st->ids_buf[((long long)b * st->max_new + step) * a.ids_cols + q] = s_choice[a.num_vq == 1 ? 0 : q];
             }
             const bool fin = (st->finish[b] != 0) || eos;   // gpt.py:486-487
             st->finish[b] = fin ? 1 : 0;

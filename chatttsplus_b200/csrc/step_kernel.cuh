@@ -732,7 +732,7 @@ __device__ void step_compute(const StepParams& p, StepCtx c) {
         if (c.cta < p.B) {
             SampleArgs sa{};
             sa.logits = p.logits; sa.vocab = p.num_audio; sa.num_vq = p.num_vq; sa.rows = p.st->B * p.num_vq; sa.st = p.st;
-            sa.b0 = p.b0;
+            sa.b0 = p.b0; sa.ids_cols = p.num_vq;
             __shared__ int s_choice[MAX_VQ];
             sample_block<true>(sa, p.b0 + c.cta, p.B, reinterpret_cast<float*>(c.ring), s_choice);
         }

@@ -332,9 +332,6 @@ class GPT:
         ``uniforms`` (extra, optional): fp32 [max_new_token, B*num_vq] in [0,1) consumed by the inverse-CDF draw;
         default = ``torch.rand`` on the CUDA generator (so ``TorchSeedContext`` / ``torch.manual_seed`` seed it).
         """
-        if infer_text:
-            raise NotImplementedError("infer_text=True (refine-text pass) is the next scope row (SURVEY.md §8f f1); "
-                                      "call the pipeline with skip_refine_text=True")
         if return_attn:
             raise NotImplementedError("return_attn is not supported by the fused attention kernels")
         if self._packed is None:
@@ -345,6 +342,7 @@ class GPT:
         B, L0, nq = inputs_ids.shape
         eos = int(eos_token)
         max_new = int(max_new_token)
+        cols = 1 if infer_text else nq   # refine-text pass: one sampling column per sequence (gpt.py:459-467)
         self._ensure_handle(B, L0 + max_new + 1)
         pads = self._pad_lens(attention_mask, B, L0)
         H = self.model_dim
@@ -362,14 +360,15 @@ class GPT:
             evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if self.record_timing else None
             if evs:
                 evs[0].record()
-            _lib.check(lib.ctp_gpt_prefill(self._handle, B, L0, _lib.ptr(emb32), pad_arr, C.byref(bufs), 0, strm), "ctp_gpt_prefill")
+            text_flag = 1 if infer_text else 0
+            _lib.check(lib.ctp_gpt_prefill(self._handle, B, L0, _lib.ptr(emb32), pad_arr, C.byref(bufs), text_flag, strm), "ctp_gpt_prefill")
 
             def draw_uniforms():
                 if uniforms is not None:
                     u = uniforms.to(dev, torch.float32).contiguous()
-                    assert u.shape == (max_new, B * nq), f"uniforms must be [{max_new}, {B * nq}]"
+                    assert u.shape == (max_new, B * cols), f"uniforms must be [{max_new}, {B * cols}]"
                     return u
-                return torch.rand(max_new, B * nq, device=dev, dtype=torch.float32)
+                return torch.rand(max_new, B * cols, device=dev, dtype=torch.float32)
 
             u = draw_uniforms()
             # step 0 (+ gpt.py:496-525: if any sequence ends immediately, draw again)
@@ -382,19 +381,21 @@ class GPT:
                 self.logger.info("unexpected end at index %s; regenerate in order to ensure non-empty"
                                  % str(finish.nonzero().flatten().tolist()))
                 # logits of the prompt are unchanged: rewind the generation state and redraw step 0
-                _lib.check(lib.ctp_gpt_prefill(self._handle, B, L0, _lib.ptr(emb32), pad_arr, C.byref(bufs), 0, strm), "ctp_gpt_prefill")
+                _lib.check(lib.ctp_gpt_prefill(self._handle, B, L0, _lib.ptr(emb32), pad_arr, C.byref(bufs), text_flag, strm), "ctp_gpt_prefill")
                 u = draw_uniforms()
 
             pbar = None
             if show_tqdm:
                 from tqdm import tqdm
-                pbar = tqdm(total=max_new, desc="code",
+                pbar = tqdm(total=max_new, desc="text" if infer_text else "code",
                             bar_format="{l_bar}{bar}| {n_fmt}/{total_fmt}(max) [{elapsed}, {rate_fmt}{postfix}]")
                 pbar.update(1)
 
             def outputs():
                 n = end_idx.to("cpu").tolist()
                 ids = [ids_buf[b, : n[b]].to(inputs_ids.dtype) for b in range(B)]
+                if infer_text:
+                    ids = [i[:, 0] for i in ids]   # gpt.py:298-299
                 hid = [hid_buf[b, : n[b]] for b in range(B)] if hid_buf is not None else []
                 return GPT.GenerationOutputs(ids=ids, attentions=[], hiddens=hid)
 
@@ -434,9 +435,10 @@ class GPT:
             yield outputs()
 
     # ---- low-level hooks used by the parity tests and bench ----------------------------------------------
-    def logits_view(self, B: int) -> torch.Tensor:
+    def logits_view(self, B: int, text: bool = False) -> torch.Tensor:
         """Copy of the handle's current logits as fp32 [B*num_vq, num_audio] (row = b*num_vq + q)."""
-        out = torch.empty(B * self.num_vq, self.num_audio_tokens, device=self.device, dtype=torch.float32)
+        shape = (B, self.cfg.num_text_tokens) if text else (B * self.num_vq, self.num_audio_tokens)
+        out = torch.empty(*shape, device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().ctp_gpt_copy_outputs(self._handle, _lib.ptr(out), None, _lib.stream_ptr()), "ctp_gpt_copy_outputs")
         return out

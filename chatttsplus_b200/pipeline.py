@@ -146,6 +146,24 @@ class ChatTTSPlusPipeline:
             result._wavs = wavs
             yield result
 
+    @torch.no_grad()
+    def _refine_text(self, text, params: RefineTextParams):
+        """Refine-text pass (chattts_plus_pipeline.py:237-277): text-token generation with head_text."""
+        gpt, tok = self.models_dict["gpt"], self.models_dict["tokenizer"]
+        text = [f"[Sbreak]{i}[Pbreak]{params.prompt}" for i in text]
+        input_ids, attention_mask, text_mask = tok.encode(text, gpt.num_vq, device="cpu")
+        warpers, procs = processors.gen_logits(num_code=tok.len, top_P=params.top_P, top_K=params.top_K,
+                                               repetition_penalty=params.repetition_penalty)
+        input_ids = input_ids.to(self.device)
+        emb = gpt(input_ids, text_mask.to(self.device))
+        result = None
+        for result in gpt.generate(emb, input_ids, temperature=torch.tensor([params.temperature]), eos_token=tok.eos_token,
+                                   attention_mask=attention_mask, max_new_token=params.max_new_token,
+                                   min_new_token=params.min_new_token, logits_warpers=warpers, logits_processors=procs,
+                                   infer_text=True, stream=False, show_tqdm=params.show_tqdm, ensure_non_empty=params.ensure_non_empty):
+            pass
+        return result
+
     @torch.inference_mode()
     def _decode_to_wavs(self, result_list, use_decoder: bool):
         self.logger.info("Start decode to wavs >>>>")
@@ -216,9 +234,16 @@ class ChatTTSPlusPipeline:
         gpt = self.models_dict["gpt"]
         for ii in range(0, len(text_in), slice_size):
             text = text_in[ii:ii + slice_size].copy()
-            if not skip_refine_text:
-                raise NotImplementedError("refine-text pass (infer_text=True) is the next scope row (SURVEY.md §8f f1): "
-                                          "call infer(..., skip_refine_text=True)")
+            if not skip_refine_text:   # chattts_plus_pipeline.py:399-411
+                self.logger.info("Process Text Refinement >>>")
+                tok = self.models_dict["tokenizer"]
+                refined = self._refine_text(text, params_refine_text)
+                text_tokens = [i[i.less(tok.break_0_ids)] for i in refined.ids]
+                text = tok.decode(text_tokens)
+                self.logger.info("Refine text: ")
+                self.logger.info(text)
+                if refine_text_only:
+                    yield text
             if refine_text_only:
                 continue
             for ti in range(len(text)):

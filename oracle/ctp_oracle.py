@@ -283,8 +283,10 @@ def generate(p: Dict[str, Tensor], emb: Tensor, inputs_ids: Tensor, temperature:
              rep_window: int = 16, top_p: Optional[float] = 0.7, top_k: Optional[int] = 20,
              sampler: str = "torch", uniforms: Optional[Tensor] = None, forced_ids: Optional[Tensor] = None,
              eps: float = 1e-6, theta: float = 10000.0, ensure_non_empty: bool = True,
-             max_steps: Optional[int] = None) -> GenerateResult:
-    """GPT.generate with infer_text=False, gpt.py:313-569 (stream=False).
+             max_steps: Optional[int] = None, infer_text: bool = False) -> GenerateResult:
+    """GPT.generate, gpt.py:313-569 (stream=False).  infer_text=True is the refine-text pass: text embedding of the
+    previous token (gpt.py:400-401), head_text logits (gpt.py:425-426), one sampling column per sequence, the sampled id
+    written to every VQ column (gpt.py:489-494), ids returned as 1-D tensors (gpt.py:298-299).
 
     sampler: 'torch' (torch.multinomial, consumes the global CPU generator exactly like the reference),
              'uniform' (inverse CDF with ``uniforms`` [max_new_token, B*num_vq]),
@@ -295,6 +297,7 @@ def generate(p: Dict[str, Tensor], emb: Tensor, inputs_ids: Tensor, temperature:
     end_idx = torch.zeros(B, dtype=torch.long)
     finish = torch.zeros(B, dtype=torch.bool)
     temp = temperature.float().unsqueeze(0).expand(B, -1).contiguous().view(-1, 1)  # gpt.py:346-351
+    ncol = 1 if infer_text else num_vq
     mask_cache = torch.ones(B, L0 + max_new_token, dtype=torch.bool)
     if attention_mask is not None:
         mask_cache[:, : attention_mask.shape[1]] = attention_mask.bool()
@@ -314,14 +317,17 @@ def generate(p: Dict[str, Tensor], emb: Tensor, inputs_ids: Tensor, temperature:
             x = emb
             pos = pos_full
         else:
-            x = code_embed(p, ids_buf[:, progress - 1: progress], num_vq)
+            if infer_text:
+                x = F.embedding(ids_buf[:, progress - 1: progress, 0], p["emb_text.weight"])
+            else:
+                x = code_embed(p, ids_buf[:, progress - 1: progress], num_vq)
             pos = pos_full[:, -1:]
         h = trunk_forward(p, x, cur_mask, pos, cache, n_layers, n_heads, eps, theta)
         h_last = h[:, -1]
         hiddens.append(h_last)
-        logits = head_code_logits(p, h_last, num_vq)  # [B*num_vq, A]
+        logits = head_text_logits(p, h_last) if infer_text else head_code_logits(p, h_last, num_vq)  # [B*ncol, V]
         all_logits.append(logits)
-        history = ids_buf[:, start_idx:progress].permute(0, 2, 1).reshape(B * num_vq, -1)
+        history = ids_buf[:, start_idx:progress, :ncol].permute(0, 2, 1).reshape(B * ncol, -1)
         scores = process_logits(logits, history, temp, rep_penalty=rep_penalty, rep_max_ids=eos_token,
                                 rep_window=rep_window, top_p=top_p, top_k=top_k,
                                 ban_eos=(i < min_new_token), eos_token=eos_token)
@@ -334,22 +340,24 @@ def generate(p: Dict[str, Tensor], emb: Tensor, inputs_ids: Tensor, temperature:
             idx_next = forced_ids[:, i].reshape(-1)
         else:
             raise ValueError(sampler)
-        idx_next = idx_next.view(-1, num_vq)
+        idx_next = idx_next.view(-1, ncol)
         finish |= idx_next.eq(eos_token).any(1)
-        ids_buf[:, progress] = idx_next
+        ids_buf[:, progress] = idx_next if not infer_text else idx_next.expand(-1, num_vq)
         if i == 0 and bool(finish.any()) and ensure_non_empty and sampler == "torch":
             # gpt.py:496-525 — regenerate from scratch (consumes more RNG)
             return generate(p, emb, inputs_ids, temperature, eos_token, attention_mask, n_layers=n_layers,
                             n_heads=n_heads, num_vq=num_vq, max_new_token=max_new_token,
                             min_new_token=min_new_token, rep_penalty=rep_penalty, rep_window=rep_window,
                             top_p=top_p, top_k=top_k, sampler=sampler, uniforms=uniforms, forced_ids=forced_ids,
-                            eps=eps, theta=theta, ensure_non_empty=ensure_non_empty, max_steps=max_steps)
+                            eps=eps, theta=theta, ensure_non_empty=ensure_non_empty, max_steps=max_steps, infer_text=infer_text)
         progress += 1
         end_idx += (~finish).long()
         steps += 1
         if bool(finish.all()):
             break
     ids = [ids_buf[b, start_idx: start_idx + int(end_idx[b])] for b in range(B)]
+    if infer_text:
+        ids = [i[:, 0] for i in ids]
     hs = torch.stack(hiddens, 1)
     hid = [hs[b, : int(end_idx[b])] for b in range(B)]
     return GenerateResult(ids=ids, hiddens=hid, logits=all_logits, steps=steps)

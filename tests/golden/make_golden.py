@@ -189,6 +189,14 @@ def gen_gpt(gpt_mod, processors):
         res[name] = {"temperature": temp, "max_new_token": maxn, "min_new_token": minn,
                      "ids": [t.clone() for t in out.ids], "hiddens": [t.clone() for t in out.hiddens]}
         print("gpt_generate", name, [tuple(t.shape) for t in out.ids])
+    # refine-text pass (infer_text=True): chattts_plus_pipeline.py:237-277 calls generate with head_text, one temperature
+    warpers_t, procs_t = processors.gen_logits(num_code=c.num_text_tokens, top_P=0.7, top_K=20, repetition_penalty=1.0)
+    torch.manual_seed(4321)
+    out = next(model.generate(emb.clone(), input_ids.clone(), temperature=torch.tensor([0.7]), eos_token=60, attention_mask=attn,
+                              max_new_token=9, min_new_token=0, logits_warpers=warpers_t, logits_processors=procs_t, infer_text=True,
+                              stream=False, show_tqdm=False, ensure_non_empty=True))
+    res["text"] = {"temperature": 0.7, "max_new_token": 9, "eos": 60, "ids": [t.clone() for t in out.ids]}
+    print("gpt_generate text", [tuple(t.shape) for t in out.ids])
     torch.save(res, os.path.join(HERE, "gpt_generate_ref.pt"))
 
 

@@ -23,6 +23,7 @@ def _prompt(cfg, B, L0, seed, pads=None, audio_tail=0):
     mask = torch.ones(B, L0, dtype=torch.long)
     for b, p in enumerate(pads or []):
         mask[b, :p] = 0
+        ids[b, :p] = 0   # the tokenizer pads with id 0 (tokenizer.py:87-101); padded rows go through the code tables
     text_mask = mask.bool().clone()
     if audio_tail:
         text_mask[:, -audio_tail:] = False
@@ -233,3 +234,34 @@ def test_lora_merge_matches_oracle():
     assert rel_rms(with_lora, first_logits(merged)) < 5e-3
     assert rel_rms(first_logits(merged), first_logits(osd)) > 2e-2, "adapter too weak to test anything"
     assert torch.allclose(base, back, atol=1e-4)  # split-K fp32 atomics: summation order varies run to run
+
+
+def test_refine_text_pass_matches_oracle_tokens():
+    """infer_text=True (scope row f1): text embedding in, head_text logits (21178-wide at full size; 256 here), one
+    sampling column, ids replicated over the VQ columns, 1-D outputs."""
+    from gpu_util import make_gpt, rel_rms
+    from chatttsplus_b200.processors import gen_logits
+    cfg = synth.GPTConfig(num_hidden_layers=3, num_text_tokens=2000)
+    gpt, osd = make_gpt(cfg, seed=90, max_batch=4)
+    # the text head is folded before fp16 rounding in the product path: give the oracle the same rounded matrix
+    W = O.weight_norm_fold(osd["head_text.parametrizations.weight.original0"], osd["head_text.parametrizations.weight.original1"]).half().float()
+    osd["head_text.parametrizations.weight.original0"] = W.norm(dim=1, keepdim=True)
+    osd["head_text.parametrizations.weight.original1"] = W
+    B, L0, max_new = 4, 9, 10
+    ids, mask, text_mask = _prompt(cfg, B, L0, seed=91, pads=[0, 2, 0, 5])
+    g = torch.Generator().manual_seed(92)
+    u = torch.rand(max_new, B, generator=g)
+    warpers, procs = gen_logits(num_code=cfg.num_text_tokens, top_P=0.7, top_K=20, repetition_penalty=1.0)
+    temp = torch.tensor([0.0003])
+    eos = 1999
+    emb = gpt(ids.cuda(), text_mask.cuda())
+    out = list(gpt.generate(emb, ids.cuda(), temp, eos, mask, max_new_token=max_new, min_new_token=0, logits_warpers=warpers,
+                            logits_processors=procs, infer_text=True, show_tqdm=False, uniforms=u))[-1]
+    emb_ref = O.gpt_embed(osd, ids, text_mask, cfg.num_vq)
+    ref = O.generate(osd, emb_ref, ids, temp, eos, mask, n_layers=3, n_heads=12, max_new_token=max_new, min_new_token=0,
+                     rep_penalty=None, sampler="uniform", uniforms=u, infer_text=True)
+    logits = gpt.logits_view(B, text=True).cpu()
+    assert rel_rms(logits, ref.logits[-1]) < 3e-3
+    for b in range(B):
+        assert out.ids[b].dim() == 1 and out.ids[b].shape == ref.ids[b].shape
+        assert torch.equal(out.ids[b].cpu().long(), ref.ids[b]), f"text tokens of sequence {b} differ"

@@ -124,8 +124,27 @@ def test_infer_with_lora_dir_and_random_speaker(tmp_path):
     assert any(f.endswith(".pt") for f in os.listdir(tmp_path)), "random speaker must be saved (chattts_plus_pipeline.py:553-557)"
 
 
-def test_unbuilt_scope_rows_fail_loudly():
+def test_refine_text_flow_through_infer(tmp_path):
+    """skip_refine_text=False: refine pass -> decoded text -> code pass -> wav (chattts_plus_pipeline.py:399-457);
+    refine_text_only=True yields the refined strings (webui.py:106-114)."""
+    from chattts_plus.commons.utils import InferCodeParams, RefineTextParams, TorchSeedContext
+    pipe, *_ = _pipeline(layers=2)
+    rp = RefineTextParams(max_new_token=6, show_tqdm=False)
+    with TorchSeedContext(3):
+        texts = list(pipe.infer(["hello"], skip_refine_text=False, refine_text_only=True, do_text_optimization=False,
+                                params_refine_text=rp, speaker_save_dir=str(tmp_path)))
+    assert len(texts) == 1 and isinstance(texts[0], list) and isinstance(texts[0][0], str)
+    with TorchSeedContext(3):
+        wavs = []
+        for w in pipe.infer(["hello"], skip_refine_text=False, do_text_optimization=False, params_refine_text=rp,
+                            params_infer_code=InferCodeParams(max_new_token=5, min_new_token=5, show_tqdm=False),
+                            speaker_save_dir=str(tmp_path)):
+            wavs.extend(w)
+    assert len(wavs) == 1 and wavs[0].shape == (256 * 9,)
+
+
+def test_unbuilt_scope_rows_fail_loudly(tmp_path):
     from chattts_plus.commons.utils import InferCodeParams
     pipe, *_ = _pipeline(layers=1)
     with pytest.raises(NotImplementedError):
-        next(pipe.infer("x", skip_refine_text=False, params_infer_code=InferCodeParams(show_tqdm=False)))
+        pipe.infer("x", speaker_audio_path=__file__, params_infer_code=InferCodeParams(show_tqdm=False))

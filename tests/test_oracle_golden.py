@@ -103,3 +103,18 @@ def test_gfsq_embed_shapes_and_digits():
     b = sd["vq_layer.quantizer.rvqs.0.project_out.bias"]
     exp = torch.nn.functional.linear(torch.full((4,), -1.0) + 0.25 * torch.full((4,), 1.0), w, b)
     assert torch.allclose(f[0, :512, 0], exp, atol=1e-6)
+
+
+def test_refine_text_pass_matches_reference_gpt(golden_dir):
+    """infer_text=True (scope row f1): oracle.generate reproduces the reference's text-token pass."""
+    g = _load(golden_dir, "gpt_generate_ref.pt")
+    cfg = synth.GPTConfig(num_hidden_layers=2, num_text_tokens=96)
+    sd = synth.make_gpt_state(cfg, seed=g["weight_seed"])
+    emb = O.gpt_embed(sd, g["input_ids"], g["text_mask"], cfg.num_vq)
+    c = g["text"]
+    torch.manual_seed(4321)
+    r = O.generate(sd, emb, g["input_ids"], torch.tensor([c["temperature"]]), c["eos"], g["attention_mask"],
+                   n_layers=cfg.num_hidden_layers, n_heads=cfg.num_attention_heads, max_new_token=c["max_new_token"], min_new_token=0,
+                   rep_penalty=None, sampler="torch", infer_text=True)
+    for a, b in zip(r.ids, c["ids"]):
+        assert a.shape == b.shape and torch.equal(a, b)
