@@ -390,7 +390,7 @@ static int run_decode_fused_lane(ctp_gpt* h, int b0, int B, int grid, float* x, 
 // One decode trunk step for B sequences (ids_ext == nullptr -> codes of the previous sample step).
 #define CTP_LAUNCH(kern, grid, block, smem, ...) do { cudaError_t _le = launch_k(kern, grid, block, (size_t)(smem), s, pdl, __VA_ARGS__); ctp_count_launch(); if (_le == cudaSuccess) _le = cudaGetLastError(); if (_le != cudaSuccess) { ctp_set_error("%s:%d launch %s: %s", __FILE__, __LINE__, #kern, cudaGetErrorString(_le)); return CTP_ERR_CUDA; } } while (0)
 
-static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, cudaStream_t s) {
+static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, cudaStream_t s, bool advance_in_sampler = false) {
     const ctp_gpt_cfg& c = h->cfg;
     const bool pdl = h->use_pdl;
     const int H = c.hidden, I = c.inter;
@@ -400,7 +400,6 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
     for (int l = 0; l < c.n_layers; ++l) {
         NormArgs na{};
         na.x = h->x; na.w = h->w.ln1 + (size_t)l * H; na.xn = h->xn; na.H = H; na.eps = c.rms_eps;
-        na.zero_buf = h->acc_qkv; na.zero_n = 3 * H;
         if (l == 0) { na.st = h->st; na.ids_ext = ids_ext; na.emb_code = (const __half*)h->w.emb_code; na.num_vq = c.num_vq; na.num_audio = c.num_audio;
                       na.emb_text = h->text_mode ? (const __half*)h->w.emb_text : nullptr; }
         CTP_LAUNCH(k_rmsnorm, dim3(B), dim3(256), 0, na);
@@ -421,7 +420,6 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
         }
         NormArgs nb{};
         nb.x = h->x; nb.w = h->w.ln2 + (size_t)l * H; nb.xn = h->xn; nb.H = H; nb.eps = c.rms_eps;
-        nb.zero_buf = h->acc_gu; nb.zero_n = 2 * I;
         CTP_LAUNCH(k_rmsnorm, dim3(B), dim3(256), 0, nb);
         {   // gate_proj | up_proj (llama.py:214)
             GemmEpilogue e = epi_swap_atomic(h->acc_gu, 2 * I, B, 2 * I);
@@ -430,7 +428,7 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
         }
         {
             const long long total = (long long)B * I;
-            CTP_LAUNCH(k_silu_mul, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (const float*)h->acc_gu, h->hmid, I, total);
+            CTP_LAUNCH(k_silu_mul, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, h->acc_gu, h->hmid, I, total, 1);
         }
         {   // down_proj accumulated into the residual stream (llama.py:214,745)
             GemmEpilogue e = epi_swap_atomic(h->x, H, B, H);
@@ -445,16 +443,16 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
     nf.zero_buf = h->logits; nf.zero_n = h->text_mode ? c.num_text : c.num_vq * c.num_audio; nf.st = h->st; nf.write_hid = 1;
     CTP_LAUNCH(k_rmsnorm, dim3(B), dim3(256), 0, nf);
     if ((st = launch_heads(h, B, s, pdl))) return st;
-    CTP_LAUNCH(k_advance_len, dim3(1), dim3(1), 0, h->st);
+    if (!advance_in_sampler) CTP_LAUNCH(k_advance_len, dim3(1), dim3(1), 0, h->st);
     return CTP_OK;
 }
 
-static int launch_sampler(ctp_gpt* h, int B, cudaStream_t s, bool pdl = false) {
+static int launch_sampler(ctp_gpt* h, int B, cudaStream_t s, bool pdl = false, bool advance_len = false) {
     const ctp_gpt_cfg& c = h->cfg;
     SampleArgs sa{};
     const int cols = h->text_mode ? 1 : c.num_vq;
     const int V = h->text_mode ? c.num_text : c.num_audio;
-    sa.logits = h->logits; sa.vocab = V; sa.num_vq = cols; sa.ids_cols = c.num_vq; sa.rows = B * cols; sa.st = h->st;
+    sa.logits = h->logits; sa.vocab = V; sa.num_vq = cols; sa.ids_cols = c.num_vq; sa.rows = B * cols; sa.st = h->st; sa.advance_len = advance_len ? 1 : 0;
     const size_t smem = sizeof(float) * cols * ((V + 31) & ~31);
     CTP_LAUNCH(k_sample, dim3(B), dim3(32 * cols), smem, sa);
     return CTP_OK;
@@ -542,7 +540,7 @@ extern "C" ctp_status ctp_gpt_prefill(ctp_gpt* h, int32_t B, int32_t L0, const f
         }
         {
             const long long total = T * I;
-            k_silu_mul<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(h->acc_gu, h->hmid, I, total);
+            k_silu_mul<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(h->acc_gu, h->hmid, I, total, 0);
             LAUNCH_OK();
         }
         {
@@ -564,6 +562,9 @@ extern "C" ctp_status ctp_gpt_prefill(ctp_gpt* h, int32_t B, int32_t L0, const f
     k_rmsnorm<<<B, 256, 0, s>>>(nf);
     LAUNCH_OK();
     if ((st = launch_heads(h, B, s))) return (ctp_status)st;
+    // the decode path accumulates into acc_qkv / acc_gu with fp32 atomics and their readers re-arm them: start from zero
+    CTP_CUDA_OK(cudaMemsetAsync(h->acc_qkv, 0, sizeof(float) * (size_t)c.max_batch * 3 * H, s));
+    CTP_CUDA_OK(cudaMemsetAsync(h->acc_gu, 0, sizeof(float) * (size_t)c.max_batch * 2 * I, s));
     h->B = B; h->cur_len = L0; h->step = 0; h->max_new = bufs->max_new; h->have_bufs = true;
     return CTP_OK;
 }
@@ -620,8 +621,8 @@ static int get_graph(ctp_gpt* h, int B, int nsplit, cudaGraphExec_t* out) {
     cudaGraph_t graph = nullptr;
     CTP_CUDA_OK(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
     ctp_count_capture_begin();
-    int st = run_decode_trunk(h, B, nsplit, nullptr, h->cap_stream);
-    if (!st) st = launch_sampler(h, B, h->cap_stream, h->use_pdl);
+    int st = run_decode_trunk(h, B, nsplit, nullptr, h->cap_stream, true);
+    if (!st) st = launch_sampler(h, B, h->cap_stream, h->use_pdl, true);
     const long long n_nodes = ctp_count_capture_end();
     cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
     if (st) { if (graph) cudaGraphDestroy(graph); return st; }

@@ -133,7 +133,9 @@ __global__ void __launch_bounds__(256) k_rmsnorm(NormArgs a) {
 }
 
 // h = silu(gate) * up   (llama.py:214), gate/up read from the fp32 accumulator [rows][2I]
-__global__ void k_silu_mul(const float* __restrict__ gu, __half* __restrict__ out, int I, long long total) {
+// zero_after: the split-K accumulator is consumed exactly once per step, so its reader re-arms it for the next step
+// (saves the 24 KB-per-row clear that used to sit in the RMSNorm kernel's critical path)
+__global__ void k_silu_mul(float* __restrict__ gu, __half* __restrict__ out, int I, long long total, int zero_after) {
     pdl_launch_dependents();
     pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -143,6 +145,7 @@ __global__ void k_silu_mul(const float* __restrict__ gu, __half* __restrict__ ou
     const float g = gu[r * 2 * I + c];
     const float u = gu[r * 2 * I + I + c];
     out[i] = __float2half_rn(silu(g) * u);
+    if (zero_after) { gu[r * 2 * I + c] = 0.f; gu[r * 2 * I + I + c] = 0.f; }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -152,7 +155,7 @@ __global__ void k_silu_mul(const float* __restrict__ gu, __half* __restrict__ ou
 // grid (nH, B, nsplit), 128 threads; split partials are merged by the last CTA to arrive for each (b, h).
 // ---------------------------------------------------------------------------------------------------------
 struct AttnDecArgs {
-    const float* qkv;       // [B][3H] fp32 accumulators of the QKV GEMM
+    float* qkv;             // [B][3H] fp32 accumulators of the QKV GEMM (re-armed to zero by their last reader)
     __half* kcache;         // this layer: [maxB][nH][maxS][64]
     __half* vcache;
     __half* out;            // [B][H] fp16
@@ -178,7 +181,7 @@ __global__ void __launch_bounds__(128) k_attn_decode(AttnDecArgs a) {
     __shared__ float s_o[16][HEAD_DIM + 1];
     __shared__ int s_last;
 
-    const float* qp = a.qkv + (long long)b * 3 * a.H + h * HEAD_DIM;
+    float* qp = a.qkv + (long long)b * 3 * a.H + h * HEAD_DIM;
     if (tid < 32) {
         const float pos = (float)(cur - pad);
         const float ang = pos * a.inv_freq[tid];
@@ -282,7 +285,10 @@ __global__ void __launch_bounds__(128) k_attn_decode(AttnDecArgs a) {
         }
     }
     if (nsplit == 1) {
-        if (tid < HEAD_DIM) a.out[(long long)b * a.H + h * HEAD_DIM + tid] = __float2half_rn(O / Lsum);
+        if (tid < HEAD_DIM) {
+            a.out[(long long)b * a.H + h * HEAD_DIM + tid] = __float2half_rn(O / Lsum);
+            qp[tid] = 0.f; qp[a.H + tid] = 0.f; qp[2 * a.H + tid] = 0.f;   // all reads of q,k,v happened before the first sync
+        }
         return;
     }
     float* pp = a.part + (((long long)b * a.nH + h) * nsplit + sp) * 66;
@@ -310,6 +316,7 @@ __global__ void __launch_bounds__(128) k_attn_decode(AttnDecArgs a) {
             OO += p0[s * 66 + tid] * w;
         }
         a.out[(long long)b * a.H + h * HEAD_DIM + tid] = __float2half_rn(OO / LL);
+        qp[tid] = 0.f; qp[a.H + tid] = 0.f; qp[2 * a.H + tid] = 0.f;   // every split has arrived (ticket): safe to re-arm
     }
 }
 
@@ -435,6 +442,7 @@ struct SampleArgs {
     int* next_ids;         // [rows] or null
     float* probs_out;      // [rows][vocab] or null
     GenState* st;          // generation mode: write ids_buf / finish / end_idx
+    int advance_len;       // graph path: the sampler's last block also advances cur_len (one kernel less per step)
     int b0;                // lanes: first global row handled by this launch (ticket / all_done cover rows [b0, b0 + n_blocks))
 };
 
@@ -603,7 +611,7 @@ __device__ __forceinline__ void sample_block(const SampleArgs& a, const int b, c
                 for (int i = 0; i < n_blocks; ++i) all &= (fin_v[a.b0 + i] != 0);
                 st->all_done = all;
                 st->step = step + 1;
-                if (FUSED) { st->cur_len += 1; }
+                if (FUSED || a.advance_len) { st->cur_len += 1; }
             }
         }
     }
