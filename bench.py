@@ -226,6 +226,67 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_vocoder(args):
+    """BASELINE.json configs[4]: vocoder-only throughput, pre-sampled inputs -> waveform.  5b (default product path): hiddens
+    [n, 768] -> Decoder.pt-shaped DVAE (hidden 512) -> Vocos;  5a (--codes): ids [n, 4] -> GFSQ embed -> DVAE_full-shaped decoder
+    (hidden 256) -> Vocos.  Dense contractions: the binding roof is the tensor pipe (157.4 / 81.5 MFLOP per code frame)."""
+    import torch.distributed as dist
+    from chatttsplus_b200.vocoder import DVAE, Vocos, VocoderEngine
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    codes = args.codes
+    dcfg = synth.DVAEConfig.codes_model() if codes else synth.DVAEConfig()
+    kw = dict(decoder_config=dict(idim=dcfg.idim, odim=dcfg.odim, hidden=dcfg.hidden, n_layer=12, bn_dim=128), dim=dcfg.dim)
+    if codes:
+        kw["vq_config"] = dict(dim=1024, levels=[5, 5, 5, 5], G=2, R=2)
+    d = DVAE(**kw); d.load_state_dict(synth.make_dvae_state(dcfg, seed=4321)); d.to(device)
+    v = Vocos(backbone_config=dict(input_channels=100, dim=512, intermediate_dim=1536, num_layers=8),
+              head_config=dict(dim=512, n_fft=1024, hop_length=256, padding="center"))
+    v.load_state_dict(synth.make_vocos_state(synth.VocosConfig(), seed=9876)); v.to(device)
+    eng = VocoderEngine(d, v, max_frames=1 << 16)
+    n_utt, nf = args.utts, args.gen
+    g = torch.Generator(device=device).manual_seed(7 + rank)
+    if codes:
+        items = [torch.randint(0, 625, (nf, 4), device=device, generator=g) for _ in range(n_utt)]
+    else:
+        items = [torch.randn(nf, 768, device=device, generator=g) for _ in range(n_utt)]
+    for _ in range(max(args.warmup, 3)):
+        eng.decode_batch(items[: min(n_utt, 64)])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        eng.decode_batch(items)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=device, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    frames = n_utt * nf * args.steps * world
+    flop = (81.5e6 if codes else 157.4e6) * frames
+    peak = 1707.5
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+    except Exception:
+        pass
+    tf = flop / (ms / 1e3) / 1e12
+    out = {"metric": "vocoder frames/s (codes/hiddens -> 24 kHz waveform)", "value": round(frames / (ms / 1e3), 1), "unit": "frames/s",
+           "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+           "config": {"workload": f"configs[4] ({'5a codes' if codes else '5b hiddens'}): {n_utt} utterances x {nf} frames per GPU -> wav",
+                      "x_realtime": round(frames * 512 / 24000.0 / (ms / 1e3), 1)},
+           "roofline": {"bound": "tensor", "achieved": round(tf, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(tf / peak, 4), "traffic": None}}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def cpu_baseline(B, sample_steps=2, voc_frames=32):
     """The oracle port (fp32 restatement of the reference's PyTorch CPU path) on the host cores, bounded sample:
     decode steps at the job's MEAN context (L = 128 + 256) with a pre-filled KV cache, plus the vocoder on one short
@@ -329,9 +390,14 @@ def main():
     ap.add_argument("--gen", type=int, default=512)
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="generate", choices=["generate", "vocoder"])
+    ap.add_argument("--codes", action="store_true", help="vocoder workload: config 5a (codes -> GFSQ -> DVAE_full decoder)")
+    ap.add_argument("--utts", type=int, default=256, help="vocoder workload: utterances per GPU per step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "vocoder":
+        run_vocoder(args)
     else:
         run_ours(args)
 

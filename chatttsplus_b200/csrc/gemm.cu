@@ -4,6 +4,7 @@
 #include "../../include/ctp.h"
 
 #include <cudaTypedefs.h>
+#include <algorithm>
 #include <mutex>
 #include <stdlib.h>
 
@@ -16,6 +17,8 @@ static EncodeTiledFn g_encode = nullptr;
 static std::once_flag g_once;
 static int g_init_status = 0;
 long long* g_dbg = nullptr;  // set by ctp_debug_gemm_stamps
+static int g_sm_count = 148;
+static bool g_persistent = true;   // CTP_GEMM_PERSISTENT=0 selects the one-tile-per-CTA kernel for the large GEMMs too
 static uint32_t g_desc[4] = {1, 64, 2, 2};  // LBO>>4, SBO>>4, layout type, K-advance per UMMA_K (in 16-byte units)
 
 template <int BN>
@@ -34,10 +37,15 @@ int gemm_init() {
             return;
         }
         g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+        if (const char* pe = getenv("CTP_GEMM_PERSISTENT")) g_persistent = atoi(pe) != 0;
         if (const char* d = getenv("CTP_DESC")) {  // bring-up diagnostics only
             unsigned a, b, c, e;
             if (sscanf(d, "%u,%u,%u,%u", &a, &b, &c, &e) == 4) { g_desc[0] = a; g_desc[1] = b; g_desc[2] = c; g_desc[3] = e; }
         }
+        cudaError_t pa = cudaFuncSetAttribute(gemm_tcgen05_persistent<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmPSmem<256>::TOTAL);
+        if (pa == cudaSuccess) pa = cudaFuncSetAttribute(gemm_tcgen05_persistent<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmPSmem<128>::TOTAL);
+        if (pa == cudaSuccess) { cudaDeviceProp prop; int dev = 0; cudaGetDevice(&dev); if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) g_sm_count = prop.multiProcessorCount; }
+        if (pa != cudaSuccess) { ctp_set_error("cudaFuncSetAttribute(persistent gemm smem): %s", cudaGetErrorString(pa)); g_init_status = CTP_ERR_CUDA; return; }
         cudaError_t a = set_smem_attr<32>();
         if (a == cudaSuccess) a = set_smem_attr<64>();
         if (a == cudaSuccess) a = set_smem_attr<128>();
@@ -101,6 +109,20 @@ int gemm_launch_maps(const CUtensorMap& tmA, const CUtensorMap& tmB, long long a
                      int block_n, int split_k, const GemmEpilogue& epi, cudaStream_t stream, const void* pf_ptr, unsigned long long pf_bytes, bool pdl) {
     int st = gemm_init();
     if (st) return st;
+    if (g_persistent && !epi.swap && !epi.atomic && split_k <= 1 && a_rows >= 512 && (block_n == 256 || block_n == 128)) {
+        GemmShape shp{};
+        shp.k_blocks = (int)((K + GEMM_BK - 1) / GEMM_BK);
+        shp.desc_lbo = g_desc[0]; shp.desc_sbo = g_desc[1]; shp.desc_layout = g_desc[2]; shp.desc_kadv = g_desc[3];
+        const int tiles_m = (int)((a_rows + GEMM_BM - 1) / GEMM_BM), tiles_n = (int)((b_rows + block_n - 1) / block_n);
+        const int grid = std::min(tiles_m * tiles_n, g_sm_count);
+        cudaError_t e;
+        if (block_n == 256) e = launch_k(gemm_tcgen05_persistent<256>, dim3(grid), dim3(GEMM_THREADS), (size_t)GemmPSmem<256>::TOTAL, stream, false, tmA, tmB, shp, epi, tiles_m, tiles_n);
+        else e = launch_k(gemm_tcgen05_persistent<128>, dim3(grid), dim3(GEMM_THREADS), (size_t)GemmPSmem<128>::TOTAL, stream, false, tmA, tmB, shp, epi, tiles_m, tiles_n);
+        ctp_count_launch();
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) { ctp_set_error("persistent gemm launch failed: %s", cudaGetErrorString(e)); return CTP_ERR_CUDA; }
+        return CTP_OK;
+    }
     switch (block_n) {
         case 32: return launch_bn<32>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream, pf_ptr, pf_bytes, pdl);
         case 64: return launch_bn<64>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream, pf_ptr, pf_bytes, pdl);

@@ -301,6 +301,186 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Persistent variant for the large, compute-bound GEMMs (prefill M = B*L0, vocoder M = mel frames): one CTA per SM loops
+// over output tiles (n-major so that concurrently running CTAs share the weight tile in L2); TWO accumulator tiles in TMEM
+// so the epilogue of tile i (TMEM -> registers -> bias / GELU / layer-scale / residual -> vectorised global stores) overlaps
+// the tcgen05.mma stream of tile i+1.  Normal orientation only (rows = tokens), no split-K.
+// ---------------------------------------------------------------------------------------------------------
+template <int BN>
+struct GemmPSmem {
+    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+    static constexpr int B_BYTES = BN * GEMM_BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;
+    static constexpr int VEC_BYTES = 2 * BN * 4;            // per-tile bias / gamma staging
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + VEC_BYTES + 256 + 1024;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape shp,
+                        const GemmEpilogue epi, const int tiles_m, const int tiles_n) {
+    using S = GemmPSmem<BN>;
+    constexpr int STAGES = S::STAGES;
+    constexpr uint32_t TMEM_COLS = 2 * BN;   // 512 (BN=256) or 256 (BN=128)
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* ring = smem;
+    float* s_bias = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES);
+    float* s_gamma = s_bias + BN;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES + S::VEC_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull = empty_bar + STAGES;    // [2] accumulator ready
+    uint64_t* tempty = tfull + 2;            // [2] accumulator drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = tiles_m * tiles_n;
+    const int nkb = shp.k_blocks;
+
+    if (warp == 4 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 5) tmem_alloc<TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int m0 = (t % tiles_m) * GEMM_BM, n0 = (t / tiles_m) * BN;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+                    uint8_t* a = ring + s * S::STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
+                    tma_load_2d(&tmA, &full_bar[s], a, kb * GEMM_BK, m0);
+                    tma_load_2d(&tmB, &full_bar[s], a + S::A_BYTES, kb * GEMM_BK, n0);
+                }
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, BN);
+            uint32_t it = 0;
+            int j = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++j) {
+                const int acc = j & 1;
+                mbar_wait(&tempty[acc], ((j >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&full_bar[s], (it / STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(ring + s * S::STAGE_BYTES);
+                    const uint64_t da = make_kmajor_desc(a_addr, shp.desc_lbo, shp.desc_sbo, shp.desc_layout);
+                    const uint64_t db = make_kmajor_desc(a_addr + S::A_BYTES, shp.desc_lbo, shp.desc_sbo, shp.desc_layout);
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k)
+                        umma_f16(d_tmem, da + (uint64_t)(shp.desc_kadv * k), db + (uint64_t)(shp.desc_kadv * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&tfull[acc]);
+            }
+        }
+    } else {
+        // epilogue warps 0..3 (128 threads): thread = one token row of the tile, 32 columns at a time
+        const int et = threadIdx.x;
+        int j = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++j) {
+            const int acc = j & 1;
+            const int m0 = (t % tiles_m) * GEMM_BM, n0 = (t / tiles_m) * BN;
+            // stage the per-feature vectors of this tile (previous tile's readers are past their last use: see bar below)
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int i = et; i < BN; i += 128) {
+                const int f = n0 + i;
+                s_bias[i] = (epi.bias && f < epi.F) ? epi.bias[f] : 0.f;
+                s_gamma[i] = (epi.gamma && f < epi.F) ? epi.gamma[f] : 1.f;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(&tfull[acc], (j >> 1) & 1);
+            tc_fence_after();
+            const int row = m0 + warp * 32 + lane;
+            const bool row_ok = row < epi.T;
+            const bool valid = row_ok && (epi.row_valid ? (epi.row_valid[row] != 0) : true);
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                float v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c), v);
+                if (c + 32 >= BN) {   // last read of this accumulator: hand it back to the MMA warp as early as possible
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[acc]);
+                }
+                if (!row_ok) continue;
+                const int f0 = n0 + c;
+                if (f0 >= epi.F) continue;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] += s_bias[c + i];
+                if (epi.act_gelu) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] *= s_gamma[c + i];
+                const bool full = (f0 + 32 <= epi.F);
+                if (epi.residual) {
+                    const float* rp = epi.residual + (long long)row * epi.ldr + f0;
+                    if (full && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 r4 = *reinterpret_cast<const float4*>(rp + i);
+                            v[i] += r4.x; v[i + 1] += r4.y; v[i + 2] += r4.z; v[i + 3] += r4.w;
+                        }
+                    } else {
+                        for (int i = 0; i < 32; ++i) if (f0 + i < epi.F) v[i] += rp[i];
+                    }
+                }
+                if (!valid) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+                }
+                if (epi.out_f16) {
+                    __half* o = reinterpret_cast<__half*>(epi.out) + (long long)row * epi.ldo + f0;
+                    if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            __half2 h0 = __floats2half2_rn(v[i], v[i + 1]), h1 = __floats2half2_rn(v[i + 2], v[i + 3]);
+                            __half2 h2 = __floats2half2_rn(v[i + 4], v[i + 5]), h3 = __floats2half2_rn(v[i + 6], v[i + 7]);
+                            uint4 pk;
+                            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                            *reinterpret_cast<uint4*>(o + i) = pk;
+                        }
+                    } else {
+                        for (int i = 0; i < 32; ++i) if (f0 + i < epi.F) o[i] = __float2half_rn(v[i]);
+                    }
+                } else {
+                    float* o = reinterpret_cast<float*>(epi.out) + (long long)row * epi.ldo + f0;
+                    if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    } else {
+                        for (int i = 0; i < 32; ++i) if (f0 + i < epi.F) o[i] = v[i];
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------------------
 // K-major fp16 matrix [rows, K] with row pitch `ld` elements -> 2-D tensor map, box = 64 x box_rows, 128B swizzle.

@@ -30,6 +30,8 @@ def _check(out, ref, tol_rel=2e-3, what=""):
     (200, 100, 728, 128),     # ragged M, N and K tail (vocos embed-like)
     (4096, 2304, 768, 256),   # prefill QKV shape
     (1024, 1026, 512, 128),   # vocos head shape
+    (20000, 520, 256, 256),   # persistent kernel: several tiles per CTA, ragged M and N
+    (19000, 1000, 768, 128),  # persistent kernel, BN=128, both TMEM accumulators cycle many times
 ])
 def test_gemm_normal(M, N, K, bn):
     from gpu_util import gemm
@@ -85,3 +87,16 @@ def test_gemm_overlapping_rows_im2col():
     _lib.check(st, "gemm im2col")
     win = torch.cat([x[0:T], x[1:T + 1], x[2:T + 2]], dim=1)
     _check(out, win.float() @ W.float().t(), what="im2col")
+
+
+@pytest.mark.parametrize("M,N,K,bn,f16", [(9000, 2048, 512, 256, True), (9000, 1027, 512, 128, True), (5000, 771, 320, 256, False)])
+def test_gemm_persistent_epilogue(M, N, K, bn, f16):
+    """Large-M shapes take the persistent double-buffered kernel; bias + GELU, aligned and unaligned output rows."""
+    from gpu_util import gemm
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.3).half()
+    B = (torch.randn(N, K, device="cuda", generator=g) * 0.05).half()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    out = gemm(A, B, out_f16=f16, gelu=True, bias=bias, block_n=bn)
+    ref = torch.nn.functional.gelu(_ref(A, B) + bias)
+    _check(out, ref, tol_rel=3e-3, what=f"persistent bias+gelu {M}x{N}x{K}")

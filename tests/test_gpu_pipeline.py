@@ -148,3 +148,21 @@ def test_unbuilt_scope_rows_fail_loudly(tmp_path):
     pipe, *_ = _pipeline(layers=1)
     with pytest.raises(NotImplementedError):
         pipe.infer("x", speaker_audio_path=__file__, params_infer_code=InferCodeParams(show_tqdm=False))
+
+
+def test_stream_mode_yields_growing_audio(tmp_path):
+    """stream=True (scope row f2, evident intent of chattts_plus_pipeline.py:417-464): one yield per stream_batch decode
+    steps, each the audio so far; the last equals the non-streamed result."""
+    from chattts_plus.commons.utils import InferCodeParams, TorchSeedContext
+    pipe, *_ = _pipeline(layers=2)
+    kw = dict(skip_refine_text=True, do_text_normalization=False, do_homophone_replacement=False, do_text_optimization=False,
+              speaker_save_dir=str(tmp_path))
+    params = InferCodeParams(temperature=0.0003, max_new_token=12, min_new_token=12, show_tqdm=False, stream_batch=4)
+    with TorchSeedContext(11):
+        chunks = [w[0].cpu() for w in pipe.infer(["streaming text"], stream=True, params_infer_code=params, **kw)]
+    with TorchSeedContext(11):
+        full = [w[0].cpu() for w in pipe.infer(["streaming text"], stream=False, params_infer_code=params, **kw)][-1]
+    assert len(chunks) >= 3
+    lens = [c.numel() for c in chunks]
+    assert lens == sorted(lens) and lens[-1] == full.numel() == 256 * 23
+    assert torch.allclose(chunks[-1], full, atol=1e-4)
