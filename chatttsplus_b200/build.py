@@ -17,7 +17,8 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_C")
 LIB = os.path.join(OUT_DIR, "libctp.so")
 SOURCES = ["ctp_capi_core.cu", "gemm.cu", "gpt.cu", "voc.cu"]
-NVCC_FLAGS = [
+_EXTRA = os.environ.get("CTP_NVCC_EXTRA", "").split()   # bring-up only (e.g. -DDG_PROBE=1)
+NVCC_FLAGS = _EXTRA + [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr",
 ]

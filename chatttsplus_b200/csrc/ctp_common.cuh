@@ -60,6 +60,26 @@ namespace ctp {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// ---- in-graph timeline (bring-up: CTP_TRACE=1): per kernel launch a record of 4 globaltimer stamps (ns) -------------------
+// [0] CTA 0 enters, [1] CTA 0 returns from griddepcontrol.wait, [2] CTA 0 leaves, [3] latest exit over all CTAs.
+// Stamps are absolute, so after a run the records describe the LAST replay of the step graph.
+__device__ __forceinline__ unsigned long long gtime_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ bool trace_cta0() { return blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0; }
+__device__ __forceinline__ void trace_mark(unsigned long long* rec, int slot) {
+    if (rec && trace_cta0()) rec[slot] = gtime_ns();
+}
+__device__ __forceinline__ void trace_end(unsigned long long* rec) {
+    if (rec) {
+        const unsigned long long t = gtime_ns();
+        if (trace_cta0()) rec[2] = t;
+        atomicMax(rec + 3, t);
+    }
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -202,7 +222,7 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
 }
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

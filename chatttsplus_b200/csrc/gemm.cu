@@ -83,7 +83,7 @@ int make_tmap_kmajor(CUtensorMap* out, const void* base, long long rows, long lo
 template <int BN>
 static int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, long long a_rows, long long b_rows, long long K,
                      int split_k, const GemmEpilogue& epi, cudaStream_t stream, const void* pf_ptr, unsigned long long pf_bytes, bool pdl) {
-    GemmShape shp;
+    GemmShape shp{};
     shp.pf_ptr = pf_ptr; shp.pf_bytes = pf_bytes; shp.a_independent = pdl ? 1 : 0;
     shp.k_blocks = (int)((K + GEMM_BK - 1) / GEMM_BK);
     shp.dbg = g_dbg;

@@ -2,6 +2,7 @@
 // C-ABI entry points are declared in include/ctp.h (each cites the reference interface it replaces).
 #include "gemm.cuh"
 #include "gpt_kernels.cuh"
+#include "decode_gemm.cuh"
 #include "step_kernel.cuh"
 
 #include <map>
@@ -72,6 +73,23 @@ struct ctp_gpt {
     unsigned long long* bar = nullptr;   // [0] arrivals counter, [1] epoch (arrivals completed by previous launches)
     int sm_count = 0, step_smem = 0, ring_slots = 0;
     bool use_pdl = true;     // programmatic dependent launch between the kernels of the decode step graph (CTP_PDL=0 disables)
+    // ---- cluster decode path (decode_gemm.cuh): split-K reduced through distributed shared memory, no L2 atomics ----------
+    bool attn_tma = true;      // TMA-staged decode attention (CTP_ATTN=ldg selects the per-thread-load kernel)
+    bool use_cluster = false;  // CTP_DECODE_GEMM=cluster: split-K reduced through DSMEM inside a thread-block cluster, 5 kernels per layer.
+                               // Parity-green but slower than the RED split-K path on B200 today (profiles/README.md), so opt-in.
+    bool kv_prefetch = true;   // the gate|up GEMM warms L2 with the next layer's K/V streams (CTP_KV_PREFETCH=0 disables)
+    unsigned long long kvpf_cap = 96 * 1024;   // per-stream prefetch cap in bytes (CTP_KV_PREFETCH_CAP, KiB)
+    int s_qkv = 8, s_o = 8, s_gu = 4, s_dn = 8;   // cluster sizes = split-K factors (CTP_S_QKV / CTP_S_O / CTP_S_GU / CTP_S_DN)
+    int attn_cta_target = 296;   // split the KV range until B*heads*nsplit reaches this many CTAs (CTP_ATTN_CTAS)
+    float* dec_buf = nullptr;    // one block: qkv [64][3H] | gate|up [64][2I] | ssA [8][64] | ssB [8][64]   (plain-stored, never accumulated)
+    float* qkv_dec() const { return dec_buf; }
+    float* gu_dec() const { return dec_buf + (size_t)64 * 3 * cfg.hidden; }
+    float* ss_a() const { return gu_dec() + (size_t)64 * 2 * cfg.inter; }   // sum(x^2) partials of the rows input_layernorm sees (written by down_proj)
+    float* ss_b() const { return ss_a() + 8 * 64; }                          // ... post_attention_layernorm sees (written by o_proj)
+    // bring-up: in-graph timeline (CTP_TRACE=1): one 8-stamp record per kernel of the step graph, in launch order
+    unsigned long long* trace = nullptr;
+    int trace_n = 0;
+    unsigned long long* trace_rec() { return trace ? trace + 8 * (size_t)(trace_n++ % 256) : nullptr; }
     bool fused_ok = false;
     bool use_fused = false;  // measured (profiles/README.md): the per-op graph path is faster today; CTP_DECODE_IMPL=fused selects the fused kernel
     // lanes: the batch is split into K contiguous row slices, each running its own fused-step kernel on its own stream over
@@ -187,6 +205,38 @@ extern "C" ctp_status ctp_gpt_create(ctp_gpt** out, const ctp_gpt_cfg* cfg) {
         h->fused_ok = (S >= 7) && (I % 192 == 0) && (H % 64 == 0) && cfg->num_vq <= 4 && cfg->num_audio <= 640 && mb <= 32;
         if (const char* e = getenv("CTP_DECODE_IMPL")) h->use_fused = (strcmp(e, "fused") == 0);
         if (const char* e = getenv("CTP_PDL")) h->use_pdl = atoi(e) != 0;
+        if (const char* e = getenv("CTP_DECODE_GEMM")) h->use_cluster = (strcmp(e, "cluster") == 0);
+        if (const char* e = getenv("CTP_ATTN")) h->attn_tma = (strcmp(e, "ldg") != 0);
+
+        CK(cudaFuncSetAttribute(k_attn_decode_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+        if (const char* e = getenv("CTP_KV_PREFETCH")) h->kv_prefetch = atoi(e) != 0;
+        if (const char* e = getenv("CTP_KV_PREFETCH_CAP")) h->kvpf_cap = (unsigned long long)atoi(e) * 1024ULL;
+        if (const char* e = getenv("CTP_ATTN_CTAS")) h->attn_cta_target = atoi(e);
+        if (const char* e = getenv("CTP_S_QKV")) h->s_qkv = atoi(e);
+        if (const char* e = getenv("CTP_S_O")) h->s_o = atoi(e);
+        if (const char* e = getenv("CTP_S_GU")) h->s_gu = atoi(e);
+        if (const char* e = getenv("CTP_S_DN")) h->s_dn = atoi(e);
+        for (int* sp : {&h->s_qkv, &h->s_o, &h->s_gu, &h->s_dn}) {   // cluster sizes: powers of two up to 16
+            int v = 1;
+            while (v * 2 <= *sp && v < 16) v *= 2;
+            *sp = v;
+        }
+        if (H % 128 != 0 || (2 * cfg->inter) % 128 != 0) h->use_cluster = false;
+        {
+            const size_t n = (size_t)64 * 3 * H + (size_t)64 * 2 * cfg->inter + 2 * 8 * 64;
+            CK(cudaMalloc(&h->dec_buf, sizeof(float) * n));
+            CK(cudaMemset(h->dec_buf, 0, sizeof(float) * n));
+            CK(cudaFuncSetAttribute(k_dec_gemm<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM));
+            CK(cudaFuncSetAttribute(k_dec_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM));
+            CK(cudaFuncSetAttribute(k_dec_gemm<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM));
+            CK(cudaFuncSetAttribute(k_dec_gemm<0>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            CK(cudaFuncSetAttribute(k_dec_gemm<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            CK(cudaFuncSetAttribute(k_dec_gemm<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        }
+        if (const char* e = getenv("CTP_TRACE")) if (atoi(e)) {
+            CK(cudaMalloc(&h->trace, sizeof(unsigned long long) * 8 * 256));
+            CK(cudaMemset(h->trace, 0, sizeof(unsigned long long) * 8 * 256));
+        }
         if (h->fused_ok) {
             CK(cudaFuncSetAttribute(k_decode_step, cudaFuncAttributeMaxDynamicSharedMemorySize, h->step_smem));
             const size_t L = cfg->n_layers;
@@ -236,6 +286,7 @@ extern "C" void ctp_gpt_destroy(ctp_gpt* h) {
     if (!h) return;
     for (auto& kvp : h->graphs) cudaGraphExecDestroy(kvp.second);
     cudaFree(h->x); cudaFree(h->xn); cudaFree(h->acc_qkv); cudaFree(h->attn); cudaFree(h->acc_gu); cudaFree(h->hmid);
+    cudaFree(h->dec_buf); cudaFree(h->trace);
     cudaFree(h->x_last); cudaFree(h->hidden); cudaFree(h->logits); cudaFree(h->kv); cudaFree(h->attn_part);
     cudaFree(h->attn_cnt); cudaFree(h->pad_len); cudaFree(h->inv_freq); cudaFree(h->st);
     cudaFree(h->wqkv_p); cudaFree(h->wo_p); cudaFree(h->wgu_p); cudaFree(h->wdn_p); cudaFree(h->whead_p);
@@ -328,7 +379,9 @@ static GemmEpilogue epi_swap_atomic(float* out, long long ldo, int T, int F) {
     return e;
 }
 
-static int split_for(int k_blocks, int m_tiles, int target_ctas = 148) {
+static int split_for(int k_blocks, int m_tiles, int target_ctas = 0) {
+    static const int env_target = getenv("CTP_GEMM_CTAS") ? atoi(getenv("CTP_GEMM_CTAS")) : 296;   // CTAs per decode GEMM: two per SM (83 KB of shared memory each) measured best
+    if (target_ctas <= 0) target_ctas = env_target;
     int s = target_ctas / m_tiles;
     if (s < 1) s = 1;
     if (s > k_blocks) s = k_blocks;
@@ -390,6 +443,89 @@ static int run_decode_fused_lane(ctp_gpt* h, int b0, int B, int grid, float* x, 
 // One decode trunk step for B sequences (ids_ext == nullptr -> codes of the previous sample step).
 #define CTP_LAUNCH(kern, grid, block, smem, ...) do { cudaError_t _le = launch_k(kern, grid, block, (size_t)(smem), s, pdl, __VA_ARGS__); ctp_count_launch(); if (_le == cudaSuccess) _le = cudaGetLastError(); if (_le != cudaSuccess) { ctp_set_error("%s:%d launch %s: %s", __FILE__, __LINE__, #kern, cudaGetErrorString(_le)); return CTP_ERR_CUDA; } } while (0)
 
+// ---- cluster decode path -------------------------------------------------------------------------------------------------
+// Per layer FIVE kernels (the reference runs ~40, llama.py:689-749): QKV GEMM (input_layernorm folded) -> attention (RoPE, KV
+// append, softmax.V) -> o_proj GEMM (+ residual) -> gate|up GEMM (post_attention_layernorm folded) -> down GEMM (SiLU gate
+// folded, + residual).  Every GEMM reduces its split-K inside a thread-block cluster and plain-stores final values.
+#define CTP_DEC_GEMM(MODE, tmA_, tmB_, args_, m_tiles_, S_) do { cudaError_t _le = launch_dec_gemm<MODE>(tmA_, tmB_, args_, m_tiles_, S_, s, pdl); ctp_count_launch(); if (_le == cudaSuccess) _le = cudaGetLastError(); if (_le != cudaSuccess) { ctp_set_error("%s:%d decode gemm launch: %s", __FILE__, __LINE__, cudaGetErrorString(_le)); return CTP_ERR_CUDA; } } while (0)
+
+static void set_kv_prefetch(ctp_gpt* h, DecGemmArgs& g, int layer, int B) {
+    const ctp_gpt_cfg& c = h->cfg;
+    g.kvpf_base = h->kplane(layer); g.kvpf_plane = sizeof(__half) * h->kv_plane_elems();
+    g.kvpf_stream = sizeof(__half) * (size_t)c.max_seq * HEAD_DIM; g.kvpf_streams = B * c.n_heads;
+    g.kvpf_len = &h->st->cur_len; g.kvpf_slot_bytes = HEAD_DIM * (int)sizeof(__half); g.kvpf_cap = h->kvpf_cap;
+}
+
+static int run_decode_trunk_cluster(ctp_gpt* h, int B, int nsplit, const int* ids_ext, cudaStream_t s) {
+    const ctp_gpt_cfg& c = h->cfg;
+    const bool pdl = h->use_pdl;
+    const int H = c.hidden, I = c.inter, L = c.n_layers;
+    const int mtH = H / DG_BM;
+    const ActMaps& am = h->act32;
+    const __half* wqkv = (const __half*)h->w.wqkv; const __half* wo = (const __half*)h->w.wo;
+    const __half* wgu = (const __half*)h->w.wgu; const __half* wdn = (const __half*)h->w.wdown;
+    h->trace_n = 0;
+    for (int l = 0; l < L; ++l) {
+        // layer 0 keeps the stand-alone RMSNorm kernel: it is also the code-embedding front end that writes the residual stream
+        const bool folded = l > 0;
+        if (!folded) {
+            NormArgs na{};
+            na.x = h->x; na.w = h->w.ln1; na.xn = h->xn; na.H = H; na.eps = c.rms_eps;
+            na.st = h->st; na.ids_ext = ids_ext; na.emb_code = (const __half*)h->w.emb_code; na.num_vq = c.num_vq; na.num_audio = c.num_audio;
+            na.emb_text = h->text_mode ? (const __half*)h->w.emb_text : nullptr;
+            na.trace = h->trace_rec();
+            CTP_LAUNCH(k_rmsnorm, dim3(B), dim3(256), 0, na);
+        }
+        {   // q,k,v projections as one GEMM (llama.py:619-621); input_layernorm (llama.py:718) folded: contracts x*w, attention applies the row factor
+            DecGemmArgs g{};
+            g.k_blocks = H / 64; g.T = B; g.out = h->qkv_dec(); g.ldo = 3 * H;
+            if (folded) { g.bsrc = h->x; g.ldbs = H; g.bw = h->w.ln1 + (size_t)l * H; }
+            g.pf_ptr = wo + (size_t)l * H * H; g.pf_bytes = sizeof(__half) * (size_t)H * H;
+            g.trace = h->trace_rec();
+            if (folded) CTP_DEC_GEMM(1, h->lmaps[l].wqkv, h->lmaps[l].wqkv, g, 3 * H / DG_BM, h->s_qkv);
+            else CTP_DEC_GEMM(0, h->lmaps[l].wqkv, am.xn, g, 3 * H / DG_BM, h->s_qkv);
+        }
+        AttnDecArgs aa{};
+        aa.qkv = h->qkv_dec(); aa.kcache = h->kplane(l); aa.vcache = h->vplane(l); aa.out = h->attn; aa.part = h->attn_part;
+        aa.counters = h->attn_cnt; aa.pad_len = h->pad_len; aa.st = h->st; aa.inv_freq = h->inv_freq;
+        aa.H = H; aa.nH = c.n_heads; aa.max_seq = c.max_seq; aa.rearm = 0; aa.eps = c.rms_eps;
+        if (folded) { aa.ss = h->ss_a(); aa.ss_parts = mtH; aa.ss_stride = 64; }
+        aa.trace = h->trace_rec();
+        if (h->attn_tma) CTP_LAUNCH(k_attn_decode_tma, dim3(c.n_heads, B, nsplit), dim3(AT_THREADS), AT_SMEM, aa);
+        else CTP_LAUNCH(k_attn_decode, dim3(c.n_heads, B, nsplit), dim3(128), 0, aa);
+        {   // o_proj + residual (llama.py:663-666,737): x = x + attn.Wo^T, plain-stored; leaves sum(x^2) partials for post_attention_layernorm
+            DecGemmArgs g{};
+            g.k_blocks = H / 64; g.T = B; g.out = h->x; g.ldo = H; g.residual = h->x; g.ldr = H;
+            g.ss_out = h->ss_b(); g.ss_out_stride = 64;
+            g.pf_ptr = wgu + (size_t)l * 2 * I * H; g.pf_bytes = sizeof(__half) * (size_t)2 * I * H;
+            g.trace = h->trace_rec();
+            CTP_DEC_GEMM(0, h->lmaps[l].wo, am.attn, g, mtH, h->s_o);
+        }
+        {   // gate_proj | up_proj (llama.py:214); post_attention_layernorm (llama.py:741) folded (row factor applied by the down GEMM's prologue)
+            DecGemmArgs g{};
+            g.k_blocks = H / 64; g.T = B; g.out = h->gu_dec(); g.ldo = 2 * I;
+            g.bsrc = h->x; g.ldbs = H; g.bw = h->w.ln2 + (size_t)l * H;
+            g.pf_ptr = wdn + (size_t)l * H * I; g.pf_bytes = sizeof(__half) * (size_t)H * I;
+            if (h->kv_prefetch && l + 1 < L) set_kv_prefetch(h, g, l + 1, B);
+            g.trace = h->trace_rec();
+            CTP_DEC_GEMM(1, h->lmaps[l].wgu, h->lmaps[l].wgu, g, 2 * I / DG_BM, h->s_gu);
+        }
+        {   // down_proj + residual (llama.py:214,745); silu(gate)*up folded into the token operand; leaves sum(x^2) partials for the next input_layernorm
+            DecGemmArgs g{};
+            g.k_blocks = I / 64; g.T = B; g.out = h->x; g.ldo = H; g.residual = h->x; g.ldr = H;
+            g.bsrc = h->gu_dec(); g.ldbs = 2 * I; g.bI = I;
+            g.ss_in = h->ss_b(); g.ss_parts = mtH; g.ss_stride = 64; g.ss_dim = (float)H; g.eps = c.rms_eps;
+            g.ss_out = h->ss_a(); g.ss_out_stride = 64;
+            if (l + 1 < L) { g.pf_ptr = wqkv + (size_t)(l + 1) * 3 * H * H; g.pf_bytes = sizeof(__half) * (size_t)3 * H * H; }
+            else { g.pf_ptr = h->w.head_code; g.pf_bytes = sizeof(__half) * (size_t)c.num_vq * c.num_audio * H; }
+            if (h->kv_prefetch && l + 1 == L) set_kv_prefetch(h, g, 0, B);   // the next step's first attention reads layer 0's streams
+            g.trace = h->trace_rec();
+            CTP_DEC_GEMM(2, h->lmaps[l].wdown, h->lmaps[l].wdown, g, mtH, h->s_dn);
+        }
+    }
+    return CTP_OK;
+}
+
 static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, cudaStream_t s, bool advance_in_sampler = false) {
     const ctp_gpt_cfg& c = h->cfg;
     const bool pdl = h->use_pdl;
@@ -397,12 +533,19 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
     const int bn = B <= 32 ? 32 : 64;
     const ActMaps& am = bn == 32 ? h->act32 : h->act64;
     int st;
-    for (int l = 0; l < c.n_layers; ++l) {
-        NormArgs na{};
-        na.x = h->x; na.w = h->w.ln1 + (size_t)l * H; na.xn = h->xn; na.H = H; na.eps = c.rms_eps;
-        if (l == 0) { na.st = h->st; na.ids_ext = ids_ext; na.emb_code = (const __half*)h->w.emb_code; na.num_vq = c.num_vq; na.num_audio = c.num_audio;
-                      na.emb_text = h->text_mode ? (const __half*)h->w.emb_text : nullptr; }
-        CTP_LAUNCH(k_rmsnorm, dim3(B), dim3(256), 0, na);
+    const bool cluster = h->use_cluster && B <= 32;
+    if (cluster) {
+        if ((st = run_decode_trunk_cluster(h, B, nsplit, ids_ext, s))) return st;
+    }
+    for (int l = 0; l < (cluster ? 0 : c.n_layers); ++l) {
+        {
+            NormArgs na{};
+            na.x = h->x; na.w = h->w.ln1 + (size_t)l * H; na.xn = h->xn; na.H = H; na.eps = c.rms_eps;
+            if (l == 0) { na.st = h->st; na.ids_ext = ids_ext; na.emb_code = (const __half*)h->w.emb_code; na.num_vq = c.num_vq; na.num_audio = c.num_audio;
+                          na.emb_text = h->text_mode ? (const __half*)h->w.emb_text : nullptr; }
+            na.trace = h->trace_rec();
+            CTP_LAUNCH(k_rmsnorm, dim3(B), dim3(256), 0, na);
+        }
         {   // q,k,v projections as one GEMM (llama.py:619-621), weights are the M operand
             GemmEpilogue e = epi_swap_atomic(h->acc_qkv, 3 * H, B, 3 * H);
             if ((st = gemm_launch_maps(h->lmaps[l].wqkv, am.xn, 3 * H, B, H, bn, split_for(H / 64, 3 * H / GEMM_BM), e, s,
@@ -411,16 +554,21 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
         AttnDecArgs aa{};
         aa.qkv = h->acc_qkv; aa.kcache = h->kplane(l); aa.vcache = h->vplane(l); aa.out = h->attn; aa.part = h->attn_part;
         aa.counters = h->attn_cnt; aa.pad_len = h->pad_len; aa.st = h->st; aa.inv_freq = h->inv_freq;
-        aa.H = H; aa.nH = c.n_heads; aa.max_seq = c.max_seq;
-        CTP_LAUNCH(k_attn_decode, dim3(c.n_heads, B, nsplit), dim3(128), 0, aa);
+        aa.H = H; aa.nH = c.n_heads; aa.max_seq = c.max_seq; aa.rearm = 1;
+        aa.trace = h->trace_rec();
+        if (h->attn_tma) CTP_LAUNCH(k_attn_decode_tma, dim3(c.n_heads, B, nsplit), dim3(AT_THREADS), AT_SMEM, aa);
+        else CTP_LAUNCH(k_attn_decode, dim3(c.n_heads, B, nsplit), dim3(128), 0, aa);
         {   // o_proj accumulated straight into the residual stream (llama.py:663-666,737)
             GemmEpilogue e = epi_swap_atomic(h->x, H, B, H);
             if ((st = gemm_launch_maps(h->lmaps[l].wo, am.attn, H, B, H, bn, split_for(H / 64, (H + GEMM_BM - 1) / GEMM_BM), e, s,
                                        (const __half*)h->w.wgu + (size_t)l * 2 * I * H, sizeof(__half) * (size_t)2 * I * H, pdl))) return st;
         }
-        NormArgs nb{};
-        nb.x = h->x; nb.w = h->w.ln2 + (size_t)l * H; nb.xn = h->xn; nb.H = H; nb.eps = c.rms_eps;
-        CTP_LAUNCH(k_rmsnorm, dim3(B), dim3(256), 0, nb);
+        {
+            NormArgs nb{};
+            nb.x = h->x; nb.w = h->w.ln2 + (size_t)l * H; nb.xn = h->xn; nb.H = H; nb.eps = c.rms_eps;
+            nb.trace = h->trace_rec();
+            CTP_LAUNCH(k_rmsnorm, dim3(B), dim3(256), 0, nb);
+        }
         {   // gate_proj | up_proj (llama.py:214)
             GemmEpilogue e = epi_swap_atomic(h->acc_gu, 2 * I, B, 2 * I);
             if ((st = gemm_launch_maps(h->lmaps[l].wgu, am.xn, 2 * I, B, H, bn, split_for(H / 64, 2 * I / GEMM_BM), e, s,
@@ -441,6 +589,7 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
     NormArgs nf{};
     nf.x = h->x; nf.w = h->w.norm_f; nf.xn = h->xn; nf.out_f32 = h->hidden; nf.H = H; nf.eps = c.rms_eps;
     nf.zero_buf = h->logits; nf.zero_n = h->text_mode ? c.num_text : c.num_vq * c.num_audio; nf.st = h->st; nf.write_hid = 1;
+    nf.trace = h->trace_rec();
     CTP_LAUNCH(k_rmsnorm, dim3(B), dim3(256), 0, nf);
     if ((st = launch_heads(h, B, s, pdl))) return st;
     if (!advance_in_sampler) CTP_LAUNCH(k_advance_len, dim3(1), dim3(1), 0, h->st);
@@ -453,6 +602,7 @@ static int launch_sampler(ctp_gpt* h, int B, cudaStream_t s, bool pdl = false, b
     const int cols = h->text_mode ? 1 : c.num_vq;
     const int V = h->text_mode ? c.num_text : c.num_audio;
     sa.logits = h->logits; sa.vocab = V; sa.num_vq = cols; sa.ids_cols = c.num_vq; sa.rows = B * cols; sa.st = h->st; sa.advance_len = advance_len ? 1 : 0;
+    sa.trace = h->trace_rec();
     const size_t smem = sizeof(float) * cols * ((V + 31) & ~31);
     CTP_LAUNCH(k_sample, dim3(B), dim3(32 * cols), smem, sa);
     return CTP_OK;
@@ -462,7 +612,7 @@ static int nsplit_for(const ctp_gpt* h, int B, int ctx_len) {
     // keep >= ~2 CTAs per SM worth of independent KV streams; one split per 512 slots beyond that
     int ns = 1;
     const int base = B * h->cfg.n_heads;
-    while (ns < h->max_splits && (base * ns < 296 || ctx_len / ns > 1024)) ns *= 2;
+    while (ns < h->max_splits && (base * ns < h->attn_cta_target || ctx_len / ns > 1024)) ns *= 2;
     if (ctx_len < ns * 8) ns = 1;
     return ns;
 }
@@ -735,6 +885,15 @@ extern "C" ctp_status ctp_gpt_generate(ctp_gpt* h, const ctp_sample_cfg* cfg, in
     CTP_CUDA_OK(cudaGetLastError());
     if (steps_done) *steps_done = done;
     return CTP_OK;
+}
+
+// bring-up hook (not in include/ctp.h): copies the timeline records (8 x u64 per kernel, launch order) to `out`; returns the count
+extern "C" __attribute__((visibility("default"))) int ctp_debug_trace(ctp_gpt* h, unsigned long long* out, int max_rec) {
+    if (!h || !h->trace) return 0;
+    const int n = h->trace_n < max_rec ? h->trace_n : max_rec;
+    cudaDeviceSynchronize();
+    cudaMemcpy(out, h->trace, sizeof(unsigned long long) * 8 * (size_t)n, cudaMemcpyDeviceToHost);
+    return n;
 }
 
 extern "C" const float* ctp_gpt_logits(ctp_gpt* h) { return h ? h->logits : nullptr; }

@@ -75,16 +75,24 @@ struct NormArgs {
     const __half* emb_text;   // text mode: x = emb_text[ids[b][0]]  (gpt.py:400-401)
     int num_vq, num_audio;
     int write_hid;            // 1: also copy out_f32 row into st->hid_buf[b][step]
+    unsigned long long* trace;
 };
 
 __global__ void __launch_bounds__(256) k_rmsnorm(NormArgs a) {
+    if (threadIdx.x == 0) trace_mark(a.trace, 0);
     pdl_launch_dependents();
-    pdl_wait();
     const int row = blockIdx.x;
     __shared__ float red[8];
     __shared__ int sid[MAX_VQ];
     float* x = a.x + (long long)row * a.H;
     const bool embed = (a.st != nullptr && a.emb_code != nullptr);
+    float wv[4];   // the norm weight does not depend on the previous kernel: loaded before the wait (H <= 1024 with 256 threads)
+    {
+        int n = 0;
+        for (int c = threadIdx.x; c < a.H; c += 256, ++n) wv[n] = __ldg(a.w + c);
+    }
+    pdl_wait();
+    if (threadIdx.x == 0) trace_mark(a.trace, 1);
     if (embed && threadIdx.x < a.num_vq) {
         int id;
         if (a.ids_ext) id = a.ids_ext[row * a.num_vq + threadIdx.x];
@@ -93,7 +101,7 @@ __global__ void __launch_bounds__(256) k_rmsnorm(NormArgs a) {
     }
     if (embed) __syncthreads();
     float ss = 0.f;
-    float vals[4];  // H <= 1024 with 256 threads
+    float vals[4];
     int n = 0;
     for (int c = threadIdx.x; c < a.H; c += 256, ++n) {
         float v;
@@ -112,6 +120,7 @@ __global__ void __launch_bounds__(256) k_rmsnorm(NormArgs a) {
         ss += v * v;
     }
     ss = warp_sum(ss);
+    if (threadIdx.x == 0) trace_mark(a.trace, 4);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
     __syncthreads();
     float tot = 0.f;
@@ -120,16 +129,18 @@ __global__ void __launch_bounds__(256) k_rmsnorm(NormArgs a) {
     const float rstd = rsqrtf(tot / (float)a.H + a.eps);
     n = 0;
     for (int c = threadIdx.x; c < a.H; c += 256, ++n) {
-        const float y = a.w[c] * (vals[n] * rstd);
+        const float y = wv[n] * (vals[n] * rstd);
         a.xn[(long long)row * a.H + c] = __float2half_rn(y);
         if (a.out_f32) a.out_f32[(long long)row * a.H + c] = y;
         if (a.write_hid && a.st->hid_buf && a.st->step < a.st->max_new)
             a.st->hid_buf[((long long)row * a.st->max_new + a.st->step) * a.H + c] = y;
     }
+    if (threadIdx.x == 0) trace_mark(a.trace, 6);
     if (a.zero_buf) {
         float* z = a.zero_buf + (long long)row * a.zero_n;
         for (int c = threadIdx.x; c < a.zero_n; c += 256) z[c] = 0.f;
     }
+    if (threadIdx.x == 0) trace_end(a.trace);
 }
 
 // h = silu(gate) * up   (llama.py:214), gate/up read from the fp32 accumulator [rows][2I]
@@ -165,11 +176,20 @@ struct AttnDecArgs {
     const GenState* st;
     const float* inv_freq;  // [32]
     int H, nH, max_seq;
+    // RMSNorm folded into the QKV GEMM (decode_gemm.cuh BMODE 1): the GEMM contracted x*w, the row factor
+    // rsqrt(sum(x^2)/H + eps) (llama.py:85) is applied here; sum(x^2) arrives as ss_parts partial sums per row
+    const float* ss;        // [ss_parts][ss_stride] or null (rows already normalised)
+    int ss_parts, ss_stride;
+    float eps;
+    int rearm;              // 1: qkv is a split-K RED accumulator that its last reader zeroes; 0: plain final values
+    unsigned long long* trace;
 };
 
 __global__ void __launch_bounds__(128) k_attn_decode(AttnDecArgs a) {
+    if (threadIdx.x == 0) trace_mark(a.trace, 0);
     pdl_launch_dependents();
     pdl_wait();
+    if (threadIdx.x == 0) trace_mark(a.trace, 1);
     const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z, nsplit = gridDim.z;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cur = a.st->cur_len;  // new token's slot
@@ -182,22 +202,33 @@ __global__ void __launch_bounds__(128) k_attn_decode(AttnDecArgs a) {
     __shared__ int s_last;
 
     float* qp = a.qkv + (long long)b * 3 * a.H + h * HEAD_DIM;
+    float rf = 1.f;   // deferred RMSNorm row factor (llama.py:85)
+    if (a.ss) {
+        float part[8];   // independent loads: one L2 round trip
+#pragma unroll
+        for (int p = 0; p < 8; ++p) part[p] = p < a.ss_parts ? __ldcg(a.ss + p * a.ss_stride + b) : 0.f;
+        float ssum = 0.f;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) ssum += part[p];
+        rf = rsqrtf(ssum / (float)a.H + a.eps);
+    }
     if (tid < 32) {
         const float pos = (float)(cur - pad);
         const float ang = pos * a.inv_freq[tid];
         float sn, cs;
         sincosf(ang, &sn, &cs);
-        const float q1 = qp[tid], q2 = qp[tid + 32];
-        const float k1 = qp[a.H + tid], k2 = qp[a.H + tid + 32];
+        const float q1 = qp[tid] * rf, q2 = qp[tid + 32] * rf;
+        const float k1 = qp[a.H + tid] * rf, k2 = qp[a.H + tid + 32] * rf;
         sq[tid] = (q1 * cs - q2 * sn) * 0.125f;  // 1/sqrt(64) folded into q
         sq[tid + 32] = (q2 * cs + q1 * sn) * 0.125f;
         sk_new[tid] = __float2half_rn(k1 * cs - k2 * sn);
         sk_new[tid + 32] = __float2half_rn(k2 * cs + k1 * sn);
     } else if (tid < 96) {
         const int d = tid - 32;
-        sv_new[d] = __float2half_rn(qp[2 * a.H + d]);
+        sv_new[d] = __float2half_rn(qp[2 * a.H + d] * rf);
     }
     __syncthreads();
+    if (tid == 0) trace_mark(a.trace, 4);
     const long long head_off = (((long long)b * a.nH + h) * a.max_seq) * HEAD_DIM;
     __half* kc = a.kcache + head_off;
     __half* vc = a.vcache + head_off;
@@ -269,6 +300,7 @@ __global__ void __launch_bounds__(128) k_attn_decode(AttnDecArgs a) {
         }
     }
     // merge the 16 groups
+    if (tid == 0) trace_mark(a.trace, 5);
     if (sub == 0) { s_m[grp] = m; s_l[grp] = l; }
 #pragma unroll
     for (int i = 0; i < 8; ++i) s_o[grp][sub * 8 + i] = o[i];
@@ -287,8 +319,9 @@ __global__ void __launch_bounds__(128) k_attn_decode(AttnDecArgs a) {
     if (nsplit == 1) {
         if (tid < HEAD_DIM) {
             a.out[(long long)b * a.H + h * HEAD_DIM + tid] = __float2half_rn(O / Lsum);
-            qp[tid] = 0.f; qp[a.H + tid] = 0.f; qp[2 * a.H + tid] = 0.f;   // all reads of q,k,v happened before the first sync
+            if (a.rearm) { qp[tid] = 0.f; qp[a.H + tid] = 0.f; qp[2 * a.H + tid] = 0.f; }   // all reads of q,k,v happened before the first sync
         }
+        if (tid == 0) trace_end(a.trace);
         return;
     }
     float* pp = a.part + (((long long)b * a.nH + h) * nsplit + sp) * 66;
@@ -302,6 +335,7 @@ __global__ void __launch_bounds__(128) k_attn_decode(AttnDecArgs a) {
         if (s_last) a.counters[b * a.nH + h] = 0;
     }
     __syncthreads();
+    if (tid == 0) trace_end(a.trace);
     if (!s_last) return;
     __threadfence();
     if (tid < HEAD_DIM) {
@@ -316,7 +350,259 @@ __global__ void __launch_bounds__(128) k_attn_decode(AttnDecArgs a) {
             OO += p0[s * 66 + tid] * w;
         }
         a.out[(long long)b * a.H + h * HEAD_DIM + tid] = __float2half_rn(OO / LL);
-        qp[tid] = 0.f; qp[a.H + tid] = 0.f; qp[2 * a.H + tid] = 0.f;   // every split has arrived (ticket): safe to re-arm
+        if (a.rearm) { qp[tid] = 0.f; qp[a.H + tid] = 0.f; qp[2 * a.H + tid] = 0.f; }   // every split has arrived (ticket): safe to re-arm
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Decode attention, TMA-staged (default): same math as k_attn_decode, but the cached K/V stream of this (b, head) is pulled
+// into a 4-stage shared-memory ring by 1-D bulk copies (cp.async.bulk, 8 KB K + 8 KB V per 64-slot tile, one elected
+// producer thread, mbarrier full/empty handshake) instead of per-thread 16-byte loads: few large requests keep HBM busy,
+// and — because cached slots do not depend on this step's QKV GEMM — the first ring pass is issued BEFORE
+// griddepcontrol.wait, so most of the KV stream overlaps the previous kernel (PDL).
+//   * pre-wait loads use a possibly one-step-old cur_len as a hint and only touch whole tiles below it (slots written by
+//     earlier steps / the prefill, complete long ago); the true length is read after the wait.
+//   * grid (nH, B, nsplit), 160 threads: warps 0-3 consume (16 groups x 8 lanes, online softmax per group), warp 4 produces.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int AT_TILE = 64, AT_STAGES = 4, AT_THREADS = 160;
+constexpr int AT_HALF_BYTES = AT_TILE * HEAD_DIM * 2;       // 8 KB: one K (or V) tile
+constexpr int AT_STAGE_BYTES = 2 * AT_HALF_BYTES;
+constexpr int AT_SMEM = AT_STAGES * AT_STAGE_BYTES + 128;
+
+__global__ void __launch_bounds__(AT_THREADS) k_attn_decode_tma(AttnDecArgs a) {
+    if (threadIdx.x == 0) trace_mark(a.trace, 0);
+    pdl_launch_dependents();
+    extern __shared__ uint8_t at_smem_raw[];
+    uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 127) & ~uintptr_t(127));
+    const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z, nsplit = gridDim.z;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ __align__(8) uint64_t full_bar[AT_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[AT_STAGES];
+    __shared__ float sq[HEAD_DIM];
+    __shared__ __align__(16) __half sk_new[HEAD_DIM];
+    __shared__ __align__(16) __half sv_new[HEAD_DIM];
+    __shared__ float s_m[16], s_l[16];
+    __shared__ float s_o[16][HEAD_DIM + 1];
+    __shared__ int s_last, s_pre;
+
+    const int pad = a.pad_len[b];   // fixed for the whole generation (uploaded by the prefill call)
+    const long long head_off = (((long long)b * a.nH + h) * a.max_seq) * HEAD_DIM;
+    __half* kc = a.kcache + head_off;
+    __half* vc = a.vcache + head_off;
+    if (tid == 0) {
+        for (int s = 0; s < AT_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 4); }
+        fence_barrier_init();
+        fence_proxy_async();
+        s_pre = 0;
+    }
+    __syncthreads();
+    int pre = 0;
+    if (warp == 4 && lane == 0 && nsplit == 1) {
+        const int hint = *reinterpret_cast<const volatile int*>(&a.st->cur_len);   // <= the true length (see header)
+        int n_full = (hint - pad) / AT_TILE;
+        pre = n_full < 0 ? 0 : (n_full > AT_STAGES ? AT_STAGES : n_full);
+        for (int i = 0; i < pre; ++i) {
+            uint8_t* st = ring + i * AT_STAGE_BYTES;
+            mbar_expect_tx(&full_bar[i], AT_STAGE_BYTES);
+            bulk_load_1d(st, kc + (long long)(pad + i * AT_TILE) * HEAD_DIM, AT_HALF_BYTES, &full_bar[i]);
+            bulk_load_1d(st + AT_HALF_BYTES, vc + (long long)(pad + i * AT_TILE) * HEAD_DIM, AT_HALF_BYTES, &full_bar[i]);
+        }
+        s_pre = pre;
+    }
+    pdl_wait();
+    if (tid == 0) trace_mark(a.trace, 1);
+    const int cur = a.st->cur_len;  // new token's slot
+    // cached slots this split covers: [j0, j1) within [pad, cur); the new token (slot cur) is taken from shared memory by the last split
+    const int n = cur - pad;
+    const int j0 = pad + (int)(((long long)n * sp) / nsplit);
+    const int j1 = pad + (int)(((long long)n * (sp + 1)) / nsplit);
+    int n_tiles = (j1 - j0 + AT_TILE - 1) / AT_TILE;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            for (int i = pre; i < n_tiles; ++i) {
+                const int s = i % AT_STAGES;
+                if (i >= AT_STAGES) mbar_wait(&empty_bar[s], ((i / AT_STAGES) & 1) ^ 1);
+                const int p0 = j0 + i * AT_TILE;
+                const int cnt = min(AT_TILE, j1 - p0);
+                const uint32_t bytes = (uint32_t)cnt * HEAD_DIM * 2;
+                uint8_t* st = ring + s * AT_STAGE_BYTES;
+                mbar_expect_tx(&full_bar[s], 2 * bytes);
+                bulk_load_1d(st, kc + (long long)p0 * HEAD_DIM, bytes, &full_bar[s]);
+                bulk_load_1d(st + AT_HALF_BYTES, vc + (long long)p0 * HEAD_DIM, bytes, &full_bar[s]);
+            }
+        }
+        if (tid == 128) trace_end(a.trace);   // (producer exit; records only the max-exit stamp when it is the latest)
+        return;
+    }
+
+    // ---- consumer warps (128 threads) ----
+    float* qp = a.qkv + (long long)b * 3 * a.H + h * HEAD_DIM;
+    float rf = 1.f;   // deferred RMSNorm row factor (llama.py:85)
+    if (a.ss) {
+        float part[8];
+#pragma unroll
+        for (int p = 0; p < 8; ++p) part[p] = p < a.ss_parts ? __ldcg(a.ss + p * a.ss_stride + b) : 0.f;
+        float ssum = 0.f;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) ssum += part[p];
+        rf = rsqrtf(ssum / (float)a.H + a.eps);
+    }
+    if (tid < 32) {
+        const float pos = (float)(cur - pad);
+        const float ang = pos * a.inv_freq[tid];
+        float sn, cs;
+        sincosf(ang, &sn, &cs);
+        const float q1 = qp[tid] * rf, q2 = qp[tid + 32] * rf;
+        const float k1 = qp[a.H + tid] * rf, k2 = qp[a.H + tid + 32] * rf;
+        sq[tid] = (q1 * cs - q2 * sn) * 0.125f;  // 1/sqrt(64) folded into q
+        sq[tid + 32] = (q2 * cs + q1 * sn) * 0.125f;
+        sk_new[tid] = __float2half_rn(k1 * cs - k2 * sn);
+        sk_new[tid + 32] = __float2half_rn(k2 * cs + k1 * sn);
+    } else if (tid < 96) {
+        const int d = tid - 32;
+        sv_new[d] = __float2half_rn(qp[2 * a.H + d] * rf);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (tid == 0) trace_mark(a.trace, 4);
+    if (sp == nsplit - 1 && tid < 16) {  // append (16 threads x 16 B = 64 halfs for K and for V)
+        reinterpret_cast<uint2*>(kc + (long long)cur * HEAD_DIM)[tid] = reinterpret_cast<const uint2*>(sk_new)[tid];
+        reinterpret_cast<uint2*>(vc + (long long)cur * HEAD_DIM)[tid] = reinterpret_cast<const uint2*>(sv_new)[tid];
+    }
+    const int pre_tiles = s_pre;                      // tiles whose bulk copies were issued before the wait
+    if (n_tiles < pre_tiles) n_tiles = pre_tiles;     // (never leave a copy in flight; cannot happen within a generation)
+
+    // 16 groups of 8 lanes; lane `sub` owns dims [8*sub, 8*sub+8)
+    const int grp = tid >> 3, sub = tid & 7;
+    float q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = sq[sub * 8 + i];
+    float m = -INFINITY, l = 0.f, o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = 0.f;
+
+    for (int it = 0; it < n_tiles; ++it) {
+        const int s = it % AT_STAGES;
+        mbar_wait(&full_bar[s], (it / AT_STAGES) & 1);
+        const int cnt = min(AT_TILE, j1 - (j0 + it * AT_TILE));   // may be <= 0 only in the defensive case above
+        const uint8_t* kt = ring + s * AT_STAGE_BYTES;
+        const uint8_t* vt = kt + AT_HALF_BYTES;
+        uint4 kr[4], vr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int p = grp + 16 * u;
+            kr[u] = reinterpret_cast<const uint4*>(kt + p * 128)[sub];
+            vr[u] = reinterpret_cast<const uint4*>(vt + p * 128)[sub];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);   // this warp's reads of the stage are in registers
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const bool valid = (grp + 16 * u) < cnt;
+            const __half2* k2 = reinterpret_cast<const __half2*>(&kr[u]);
+            float sc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(k2[i]);
+                sc += q[2 * i] * f.x + q[2 * i + 1] * f.y;
+            }
+            sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+            sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+            sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+            if (valid) {
+                const float mn = fmaxf(m, sc);
+                const float corr = __expf(m - mn);
+                const float p = __expf(sc - mn);
+                l = l * corr + p;
+                const __half2* v2 = reinterpret_cast<const __half2*>(&vr[u]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 f = __half22float2(v2[i]);
+                    o[2 * i] = o[2 * i] * corr + p * f.x;
+                    o[2 * i + 1] = o[2 * i + 1] * corr + p * f.y;
+                }
+                m = mn;
+            }
+        }
+    }
+    if (sp == nsplit - 1) {   // the new token (slot cur), group 0 takes it
+        const __half2* k2 = reinterpret_cast<const __half2*>(sk_new) + sub * 4;
+        float sc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(k2[i]);
+            sc += q[2 * i] * f.x + q[2 * i + 1] * f.y;
+        }
+        sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+        sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+        sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+        if (grp == 0) {
+            const float mn = fmaxf(m, sc);
+            const float corr = __expf(m - mn);
+            const float p = __expf(sc - mn);
+            l = l * corr + p;
+            const __half2* v2 = reinterpret_cast<const __half2*>(sv_new) + sub * 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(v2[i]);
+                o[2 * i] = o[2 * i] * corr + p * f.x;
+                o[2 * i + 1] = o[2 * i + 1] * corr + p * f.y;
+            }
+            m = mn;
+        }
+    }
+    // merge the 16 groups
+    if (tid == 0) trace_mark(a.trace, 5);
+    if (sub == 0) { s_m[grp] = m; s_l[grp] = l; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_o[grp][sub * 8 + i] = o[i];
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    float M = -INFINITY, Lsum = 0.f, O = 0.f;
+    if (tid < HEAD_DIM) {
+#pragma unroll
+        for (int g = 0; g < 16; ++g) M = fmaxf(M, s_m[g]);
+#pragma unroll
+        for (int g = 0; g < 16; ++g) {
+            const float w = (s_m[g] == -INFINITY) ? 0.f : __expf(s_m[g] - M);
+            Lsum += s_l[g] * w;
+            O += s_o[g][tid] * w;
+        }
+    }
+    if (nsplit == 1) {
+        if (tid < HEAD_DIM) {
+            a.out[(long long)b * a.H + h * HEAD_DIM + tid] = __float2half_rn(O / Lsum);
+            if (a.rearm) { qp[tid] = 0.f; qp[a.H + tid] = 0.f; qp[2 * a.H + tid] = 0.f; }   // all reads of q,k,v happened before the first barrier
+        }
+        if (tid == 0) trace_end(a.trace);
+        return;
+    }
+    float* pp = a.part + (((long long)b * a.nH + h) * nsplit + sp) * 66;
+    if (tid < HEAD_DIM) pp[tid] = O;
+    if (tid == 0) { pp[64] = M; pp[65] = Lsum; }
+    __threadfence();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (tid == 0) {
+        const int t = atomicAdd(&a.counters[b * a.nH + h], 1);
+        s_last = (t == nsplit - 1);
+        if (s_last) a.counters[b * a.nH + h] = 0;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (tid == 0) trace_end(a.trace);
+    if (!s_last) return;
+    __threadfence();
+    if (tid < HEAD_DIM) {
+        const float* p0 = a.part + (((long long)b * a.nH + h) * nsplit) * 66;
+        float MM = -INFINITY;
+        for (int s = 0; s < nsplit; ++s) MM = fmaxf(MM, p0[s * 66 + 64]);
+        float LL = 0.f, OO = 0.f;
+        for (int s = 0; s < nsplit; ++s) {
+            const float ms = p0[s * 66 + 64];
+            const float w = (ms == -INFINITY) ? 0.f : __expf(ms - MM);
+            LL += p0[s * 66 + 65] * w;
+            OO += p0[s * 66 + tid] * w;
+        }
+        a.out[(long long)b * a.H + h * HEAD_DIM + tid] = __float2half_rn(OO / LL);
+        if (a.rearm) { qp[tid] = 0.f; qp[a.H + tid] = 0.f; qp[2 * a.H + tid] = 0.f; }   // every split has arrived (ticket): safe to re-arm
     }
 }
 
@@ -443,6 +729,7 @@ struct SampleArgs {
     float* probs_out;      // [rows][vocab] or null
     GenState* st;          // generation mode: write ids_buf / finish / end_idx
     int advance_len;       // graph path: the sampler's last block also advances cur_len (one kernel less per step)
+    unsigned long long* trace;
     int b0;                // lanes: first global row handled by this launch (ticket / all_done cover rows [b0, b0 + n_blocks))
 };
 
@@ -486,6 +773,7 @@ __device__ __forceinline__ void sample_block(const SampleArgs& a, const int b, c
     const float* lg = a.logits + (long long)row * V;
     for (int v = lane; v < V; v += 32) sc[v] = (FUSED ? __ldcg(lg + v) : lg[v]) * inv_t;
     __syncwarp();
+    if (!FUSED && threadIdx.x == 0) trace_mark(a.trace, 4);
     // 2. windowed repetition penalty (processors.py:18-34)
     if (cfg.rep_penalty != 1.0f && row < cfg.rep_max_ids) {
         const int w = min(hist_len, cfg.rep_window);
@@ -507,6 +795,7 @@ __device__ __forceinline__ void sample_block(const SampleArgs& a, const int b, c
         }
         __syncwarp();
     }
+    if (!FUSED && threadIdx.x == 0) trace_mark(a.trace, 7);
     // full-row softmax normaliser (TopP works on probabilities of the whole row)
     float mx = -INFINITY;
     for (int v = lane; v < V; v += 32) mx = fmaxf(mx, sc[v]);
@@ -519,23 +808,51 @@ __device__ __forceinline__ void sample_block(const SampleArgs& a, const int b, c
     K = min(min(K, SAMPLE_MAX_K), V);
     float my_val = -INFINITY;  // lane k holds rank-k candidate
     int my_idx = -1;
-    for (int k = 0; k < K; ++k) {
-        float bv = -INFINITY;
-        int bi = 0x7fffffff;
-        for (int v = lane; v < V; v += 32) {
-            const float s = sc[v];
-            if (s > bv) { bv = s; bi = v; }
-        }
+    constexpr int REG_V = 20;   // audio vocab (626) fits 20 scores per lane: selection runs out of registers
+    if (V <= 32 * REG_V) {
+        // lane owns scores v = lane + 32*i.  Per round: warp arg-max over the lanes' local maxima with three redux.sync
+        // (max of an order-preserving integer key, then the smallest token id among the ties), the owner retires its entry
+        // and rescans its 20 registers.  ~2 us for K = 20 instead of ~13 us through shared memory (tests/prof_trace.py).
+        float vals[REG_V];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        for (int i = 0; i < REG_V; ++i) { const int v = lane + 32 * i; vals[i] = v < V ? sc[v] : -INFINITY; }
+        for (int k = 0; k < K; ++k) {
+            float lv = vals[0];
+            int li = 0;
+#pragma unroll
+            for (int i = 1; i < REG_V; ++i) if (vals[i] > lv) { lv = vals[i]; li = i; }
+            const unsigned u = __float_as_uint(lv);
+            const unsigned key = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+            const unsigned kmax = __reduce_max_sync(0xffffffffu, key);
+            const int cand = (key == kmax) ? (lane + 32 * li) : 0x7fffffff;
+            const int bi = __reduce_min_sync(0xffffffffu, cand);
+            const float bv = __shfl_sync(0xffffffffu, lv, bi & 31);
+            if (lane == k) { my_val = bv; my_idx = bi; }
+            if ((bi & 31) == lane) {
+#pragma unroll
+                for (int i = 0; i < REG_V; ++i) if (i == (bi >> 5)) vals[i] = -INFINITY;
+            }
         }
-        if (lane == k) { my_val = bv; my_idx = bi; }
-        if (lane == 0 && bi < V) sc[bi] = -INFINITY;  // remove from the pool
-        __syncwarp();
+    } else {
+        for (int k = 0; k < K; ++k) {
+            float bv = -INFINITY;
+            int bi = 0x7fffffff;
+            for (int v = lane; v < V; v += 32) {
+                const float s = sc[v];
+                if (s > bv) { bv = s; bi = v; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (lane == k) { my_val = bv; my_idx = bi; }
+            if (lane == 0 && bi < V) sc[bi] = -INFINITY;  // remove from the pool
+            __syncwarp();
+        }
     }
+    if (!FUSED && threadIdx.x == 0) trace_mark(a.trace, 5);
     // 4. TopP on rank order: token at rank k survives iff (mass strictly above it) < top_p, or k < min_keep.
     //    (reference: cumulative prob from the bottom <= 1 - top_p is removed.)
     const float pk = (lane < K && my_idx >= 0 && my_idx < V) ? __expf(my_val - mx) / z : 0.f;
@@ -587,6 +904,7 @@ __device__ __forceinline__ void sample_block(const SampleArgs& a, const int b, c
         if (keep) po[my_idx] = p;
     }
     if (a.next_ids && lane == 0) a.next_ids[row] = chosen;
+    if (!FUSED && threadIdx.x == 0) trace_mark(a.trace, 6);
     if (a.st) {
         if (lane == 0) s_choice[warp] = chosen;
         if (FUSED) asm volatile("bar.sync 1, 256;" ::: "memory"); else __syncthreads();
@@ -619,11 +937,14 @@ __device__ __forceinline__ void sample_block(const SampleArgs& a, const int b, c
 
 // blockDim = 32 * num_vq; block b handles rows b*num_vq .. b*num_vq + num_vq-1.
 __global__ void k_sample(SampleArgs a) {
+    if (threadIdx.x == 0) trace_mark(a.trace, 0);
     pdl_launch_dependents();
     pdl_wait();
+    if (threadIdx.x == 0) trace_mark(a.trace, 1);
     extern __shared__ float s_scores_dyn[];  // [num_vq][vocab_pad]
     __shared__ int s_choice[MAX_VQ];
     sample_block<false>(a, blockIdx.x, gridDim.x, s_scores_dyn, s_choice);
+    if (threadIdx.x == 0) trace_end(a.trace);
 }
 
 // cur_len += 1 after a trunk step (the new token's K/V now occupy slot cur_len)

@@ -98,6 +98,24 @@ def test_trunk_batch1_long_prompt_split_kv():
     _teacher_forced(cfg, B=1, L0=300, steps=4, seed=30)
 
 
+def test_trunk_long_context_wraps_kv_ring():
+    """B*heads >= 296 keeps the whole KV range in one CTA per (b, head): 330+ cached slots = 6 tiles of 64 through the 4-stage
+    bulk-copy ring of k_attn_decode_tma (first ring pass issued before griddepcontrol.wait), with ragged left padding."""
+    cfg = synth.GPTConfig(num_hidden_layers=2, num_text_tokens=256)
+    _teacher_forced(cfg, B=26, L0=330, steps=4, seed=35, pads=[0, 5, 64, 129, 200, 329] + [0] * 20)
+
+
+@pytest.mark.parametrize("env", [{"CTP_ATTN": "ldg"}, {"CTP_DECODE_GEMM": "cluster"}, {"CTP_DECODE_GEMM": "cluster", "CTP_S_DN": "16", "CTP_S_GU": "2"},
+                                 {"CTP_PDL": "0"}])
+def test_trunk_opt_in_variants(env, monkeypatch):
+    """The opt-in decode variants stay parity-green: per-thread-load attention, the cluster (DSMEM split-K, 5 kernels per layer)
+    GEMM path, and launches without programmatic dependent launch.  (Read at handle creation.)"""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    cfg = synth.GPTConfig(num_hidden_layers=3, num_text_tokens=256)
+    _teacher_forced(cfg, B=5, L0=70, steps=4, seed=21, pads=[0, 3, 9, 0, 60])
+
+
 def test_trunk_full_depth_config2_shape():
     """20 layers, B=32, L0=128 (BASELINE.json configs[1] shape), 4 teacher-forced steps."""
     cfg = synth.GPTConfig()
