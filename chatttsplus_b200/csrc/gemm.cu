@@ -50,6 +50,7 @@ int gemm_init() {
         if (a == cudaSuccess) a = set_smem_attr<64>();
         if (a == cudaSuccess) a = set_smem_attr<128>();
         if (a == cudaSuccess) a = set_smem_attr<256>();
+        if (a == cudaSuccess) a = cudaFuncSetAttribute(gemm_tcgen05_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<32, true>::TOTAL);
         if (a != cudaSuccess) {
             ctp_set_error("cudaFuncSetAttribute(gemm smem): %s", cudaGetErrorString(a));
             g_init_status = CTP_ERR_CUDA;
@@ -77,6 +78,49 @@ int make_tmap_kmajor(CUtensorMap* out, const void* base, long long rows, long lo
                       box_rows);
         return CTP_ERR_CUDA;
     }
+    return CTP_OK;
+}
+
+int make_tmap_f32(CUtensorMap* out, const void* base, long long rows, long long K, long long ld_elems, int box_rows) {
+    int st = gemm_init();
+    if (st) return st;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ((ld_elems * 4) & 15) != 0) {
+        ctp_set_error("tensor map: base %p / row pitch %lld elements must be 16-byte aligned", base, ld_elems);
+        return CTP_ERR_INVALID;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)(ld_elems * 4)};
+    cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        ctp_set_error("cuTensorMapEncodeTiled (fp32) failed (%d): rows=%lld K=%lld ld=%lld box_rows=%d", (int)r, rows, K, ld_elems, box_rows);
+        return CTP_ERR_CUDA;
+    }
+    return CTP_OK;
+}
+
+int gemm_launch_xnorm(const CUtensorMap& tmA, const CUtensorMap& tmX, long long a_rows, long long T, long long K, int split_k,
+                      const GemmEpilogue& epi, const float* norm_w, cudaStream_t stream, const void* pf_ptr, unsigned long long pf_bytes, bool pdl) {
+    int st = gemm_init();
+    if (st) return st;
+    if (T > 32 || (K % GEMM_BK) != 0 || !epi.swap || !epi.atomic || !norm_w) {
+        ctp_set_error("gemm_launch_xnorm: needs <= 32 token rows, K %% 64 == 0 and the swap/atomic decode epilogue");
+        return CTP_ERR_INVALID;
+    }
+    GemmShape shp{};
+    shp.pf_ptr = pf_ptr; shp.pf_bytes = pf_bytes; shp.a_independent = pdl ? 1 : 0; shp.norm_w = norm_w;
+    shp.k_blocks = (int)(K / GEMM_BK);
+    shp.desc_lbo = g_desc[0]; shp.desc_sbo = g_desc[1]; shp.desc_layout = g_desc[2]; shp.desc_kadv = g_desc[3];
+    if (split_k < 1) split_k = 1;
+    if (split_k > shp.k_blocks) split_k = shp.k_blocks;
+    dim3 grid(1, (unsigned)((a_rows + GEMM_BM - 1) / GEMM_BM), (unsigned)split_k);
+    cudaError_t e = launch_k(gemm_tcgen05_kernel<32, true>, grid, dim3(GEMM_THREADS), (size_t)GemmSmem<32, true>::TOTAL, stream, pdl, tmA, tmX, shp, epi);
+    ctp_count_launch();
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { ctp_set_error("xnorm gemm launch failed: %s", cudaGetErrorString(e)); return CTP_ERR_CUDA; }
     return CTP_OK;
 }
 

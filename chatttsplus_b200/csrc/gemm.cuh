@@ -37,23 +37,30 @@ struct GemmShape {
     int a_independent;        // PDL: the M operand (weights in the decode path) does not depend on the previous kernel
     const void* pf_ptr;       // optional: region the NEXT kernel will stream (its weights); every CTA prefetches a share into L2
     unsigned long long pf_bytes;
+    // XNORM variant (decode): the token operand is built in the kernel from the fp32 residual stream, B[t][k] = fp16(x[t][k] * w[k])
+    // (RMSNorm folded into the GEMM, llama.py:82-87).  tmB is then an fp32 tensor map over x; the contraction is linear in the row
+    // factor rsqrt(mean(x[t]^2) + eps), which the CONSUMER of the accumulator applies (it recomputes it from x[t], 3 KB per row).
+    const float* norm_w;      // [K]
 };
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 192;
 
-template <int BN>
+template <int BN, bool XNORM = false>
 struct GemmSmem {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
     static constexpr int B_BYTES = BN * GEMM_BK * 2;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int X_BYTES = XNORM ? BN * GEMM_BK * 4 : 0;   // fp32 landing tile of the residual stream (TMA, no swizzle)
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES + X_BYTES;
     // <= 200 KB of operand ring; leaves room for the barrier block and 1 KB alignment slack under 227 KB.
     // BN=32 is the decode path (<= 4 k-blocks per CTA after split-K): 4 stages = 83 KB so that two CTAs — e.g. of two
     // independent half-batch chains — fit on one SM.
-    static constexpr int STAGES = BN == 32 ? 4 : ((200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES);
+    // XNORM: 3 stages of 28 KB (<= 2 k-blocks per CTA after split-K) keep two CTAs per SM as well.
+    static constexpr int STAGES = XNORM ? 3 : (BN == 32 ? 4 : ((200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES));
     static constexpr int BAR_BYTES = 256;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+    static_assert(!XNORM || BN == 32, "the in-kernel RMSNorm operand is built for the 32-token decode tile");
 };
 
 template <int BN>
@@ -139,12 +146,14 @@ __device__ __forceinline__ void gemm_epilogue_store(const GemmEpilogue& e, int r
     }
 }
 
-template <int BN>
+template <int BN, bool XNORM = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmShape shp, const GemmEpilogue epi) {
-    using S = GemmSmem<BN>;
+    using S = GemmSmem<BN, XNORM>;
     constexpr int STAGES = S::STAGES;
+    constexpr uint32_t FULL_COUNT = XNORM ? 5 : 1;                       // weight TMA (arrive.expect_tx) + 4 converter warps
+    constexpr uint32_t TX_BYTES = XNORM ? S::A_BYTES : S::A_BYTES + S::B_BYTES;
     constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128B-swizzle atoms
@@ -153,7 +162,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* accum_bar = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    uint64_t* x_bar = accum_bar + 1;                                     // [STAGES] fp32 tile landed (XNORM only)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_bar + STAGES);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -171,8 +181,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
+            mbar_init(&full_bar[s], FULL_COUNT);
             mbar_init(&empty_bar[s], 1);
+            if (XNORM) mbar_init(&x_bar[s], 1);
         }
         mbar_init(accum_bar, 1);
         fence_barrier_init();
@@ -194,12 +205,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 // weights first (they do not depend on the previous kernel), then wait, then the activation halves
                 pre = nkb < STAGES ? nkb : STAGES;
                 for (int i = 0; i < pre; ++i) {
-                    mbar_expect_tx(&full_bar[i], S::STAGE_BYTES);
+                    mbar_expect_tx(&full_bar[i], TX_BYTES);
                     tma_load_2d(&tmA, &full_bar[i], ring + i * S::STAGE_BYTES, (kb0 + i) * GEMM_BK, m0);
                 }
                 pdl_wait();
-                for (int i = 0; i < pre; ++i)
-                    tma_load_2d(&tmB, &full_bar[i], ring + i * S::STAGE_BYTES + S::A_BYTES, (kb0 + i) * GEMM_BK, n0);
+                for (int i = 0; i < pre; ++i) {
+                    if (XNORM) {
+                        mbar_expect_tx(&x_bar[i], S::X_BYTES);
+                        tma_load_2d(&tmB, &x_bar[i], ring + i * S::STAGE_BYTES + S::A_BYTES + S::B_BYTES, (kb0 + i) * GEMM_BK, n0);
+                    } else {
+                        tma_load_2d(&tmB, &full_bar[i], ring + i * S::STAGE_BYTES + S::A_BYTES, (kb0 + i) * GEMM_BK, n0);
+                    }
+                }
             }
             for (int i = pre; i < nkb; ++i) {
                 const int s = i % STAGES;
@@ -207,9 +224,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t* a = ring + s * S::STAGE_BYTES;
                 uint8_t* b = a + S::A_BYTES;
-                mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
+                mbar_expect_tx(&full_bar[s], TX_BYTES);
                 tma_load_2d(&tmA, &full_bar[s], a, (kb0 + i) * GEMM_BK, m0);
-                tma_load_2d(&tmB, &full_bar[s], b, (kb0 + i) * GEMM_BK, n0);
+                if (XNORM) {
+                    mbar_expect_tx(&x_bar[s], S::X_BYTES);
+                    tma_load_2d(&tmB, &x_bar[s], b + S::B_BYTES, (kb0 + i) * GEMM_BK, n0);
+                } else {
+                    tma_load_2d(&tmB, &full_bar[s], b, (kb0 + i) * GEMM_BK, n0);
+                }
             }
             if (shp.pf_ptr) {   // after our own loads are in flight: warm L2 with the next GEMM's weights
                 const unsigned long long n_cta = (unsigned long long)gridDim.x * gridDim.y * gridDim.z;
@@ -254,6 +276,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else {
         // epilogue warps 0..3: TMEM lanes [32*warp, 32*warp+32)
+        if (XNORM) {
+            // converter: fp32 x tile (TMA, [32 rows][64 k] row-major) -> fp16(x * w) in the 128B-swizzled K-major layout the MMA
+            // reads (16-byte chunk c of row r at r*128 + ((c ^ (r & 7)) << 4)).  Thread (c16 = et & 15, r0 = et >> 4) owns k columns
+            // 4*c16..+3 of rows r0 + 8j: shared-memory reads are conflict-free, each thread fills half a chunk.
+            const int et = threadIdx.x, c16 = et & 15, r0 = et >> 4;
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES;
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(shp.norm_w + (kb0 + i) * GEMM_BK + c16 * 4));
+                mbar_wait(&x_bar[s], (i / STAGES) & 1);
+                uint8_t* bt = ring + s * S::STAGE_BYTES + S::A_BYTES;
+                const float* xt = reinterpret_cast<const float*>(bt + S::B_BYTES);
+#pragma unroll
+                for (int rr = 0; rr < BN / 8; ++rr) {
+                    const int r = rr * 8 + r0;
+                    const float4 a4 = *reinterpret_cast<const float4*>(xt + r * GEMM_BK + c16 * 4);
+                    __half2 h0 = __floats2half2_rn(a4.x * w4.x, a4.y * w4.y), h1 = __floats2half2_rn(a4.z * w4.z, a4.w * w4.w);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                    *reinterpret_cast<uint2*>(bt + r * 128 + (((c16 >> 1) ^ (r & 7)) << 4) + ((c16 & 1) << 3)) = pk;
+                }
+                fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_bar[s]);
+            }
+        }
         if (nkb > 0) {
             mbar_wait(accum_bar, 0);
             if (dbg && threadIdx.x == 0) dbg[4] = clock64();
@@ -501,6 +548,11 @@ int gemm_launch(const GemmLaunch& g, cudaStream_t stream);
 int gemm_launch_maps(const CUtensorMap& tmA, const CUtensorMap& tmB, long long a_rows, long long b_rows, long long K,
                      int block_n, int split_k, const GemmEpilogue& epi, cudaStream_t stream, const void* pf_ptr = nullptr,
                      unsigned long long pf_bytes = 0, bool pdl = false);
+// Decode QKV / gate|up GEMM with RMSNorm folded in (XNORM kernel): tmX is an fp32 map over the residual stream (make_tmap_f32).
+int gemm_launch_xnorm(const CUtensorMap& tmA, const CUtensorMap& tmX, long long a_rows, long long T, long long K, int split_k,
+                      const GemmEpilogue& epi, const float* norm_w, cudaStream_t stream, const void* pf_ptr, unsigned long long pf_bytes, bool pdl);
+// fp32 matrix [rows, K] with row pitch `ld` elements -> 2-D tensor map, box = 64 x box_rows, no swizzle.
+int make_tmap_f32(CUtensorMap* out, const void* base, long long rows, long long K, long long ld_elems, int box_rows);
 int gemm_init();  // resolves cuTensorMapEncodeTiled, sets max dynamic smem attributes
 
 }  // namespace ctp

@@ -74,6 +74,8 @@ struct ctp_gpt {
     int sm_count = 0, step_smem = 0, ring_slots = 0;
     bool use_pdl = true;     // programmatic dependent launch between the kernels of the decode step graph (CTP_PDL=0 disables)
     // ---- cluster decode path (decode_gemm.cuh): split-K reduced through distributed shared memory, no L2 atomics ----------
+    bool fuse_norm = true;     // RMSNorm folded into the QKV / gate|up GEMMs (XNORM kernel); CTP_FUSE_NORM=0: stand-alone norm kernels
+    CUtensorMap x_map{};       // fp32 map over the first 64 rows of the residual stream
     bool attn_tma = true;      // TMA-staged decode attention (CTP_ATTN=ldg selects the per-thread-load kernel)
     bool use_cluster = false;  // CTP_DECODE_GEMM=cluster: split-K reduced through DSMEM inside a thread-block cluster, 5 kernels per layer.
                                // Parity-green but slower than the RED split-K path on B200 today (profiles/README.md), so opt-in.
@@ -139,6 +141,7 @@ static int ensure_workspace(ctp_gpt* h, long long rows) {
         if ((st = make_tmap_kmajor(&am.attn, h->attn, mb, H, H, bn))) return st;
         if ((st = make_tmap_kmajor(&am.hmid, h->hmid, mb, I, I, bn))) return st;
     }
+    if ((st = make_tmap_f32(&h->x_map, h->x, mb, H, H, 32))) return st;
     // captured graphs hold the old pointers
     for (auto& kvp : h->graphs) cudaGraphExecDestroy(kvp.second);
     h->graphs.clear();
@@ -207,6 +210,8 @@ extern "C" ctp_status ctp_gpt_create(ctp_gpt** out, const ctp_gpt_cfg* cfg) {
         if (const char* e = getenv("CTP_PDL")) h->use_pdl = atoi(e) != 0;
         if (const char* e = getenv("CTP_DECODE_GEMM")) h->use_cluster = (strcmp(e, "cluster") == 0);
         if (const char* e = getenv("CTP_ATTN")) h->attn_tma = (strcmp(e, "ldg") != 0);
+        if (const char* e = getenv("CTP_FUSE_NORM")) h->fuse_norm = atoi(e) != 0;
+        if (cfg->inter % 256 != 0) h->fuse_norm = false;   // k_silu_mul: one token row per block
 
         CK(cudaFuncSetAttribute(k_attn_decode_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
         if (const char* e = getenv("CTP_KV_PREFETCH")) h->kv_prefetch = atoi(e) != 0;
@@ -537,8 +542,11 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
     if (cluster) {
         if ((st = run_decode_trunk_cluster(h, B, nsplit, ids_ext, s))) return st;
     }
+    // RMSNorm folded into the GEMM that consumes it (batch <= 32, TMA-staged attention): 6 kernels per layer instead of 8.
+    const bool fnorm = h->fuse_norm && h->attn_tma && B <= 32;
     for (int l = 0; l < (cluster ? 0 : c.n_layers); ++l) {
-        {
+        const bool f1 = fnorm && l > 0;   // layer 0 keeps the norm kernel: it is also the code-embedding front end
+        if (!f1) {
             NormArgs na{};
             na.x = h->x; na.w = h->w.ln1 + (size_t)l * H; na.xn = h->xn; na.H = H; na.eps = c.rms_eps;
             if (l == 0) { na.st = h->st; na.ids_ext = ids_ext; na.emb_code = (const __half*)h->w.emb_code; na.num_vq = c.num_vq; na.num_audio = c.num_audio;
@@ -548,13 +556,17 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
         }
         {   // q,k,v projections as one GEMM (llama.py:619-621), weights are the M operand
             GemmEpilogue e = epi_swap_atomic(h->acc_qkv, 3 * H, B, 3 * H);
-            if ((st = gemm_launch_maps(h->lmaps[l].wqkv, am.xn, 3 * H, B, H, bn, split_for(H / 64, 3 * H / GEMM_BM), e, s,
-                                       (const __half*)h->w.wo + (size_t)l * H * H, sizeof(__half) * (size_t)H * H, pdl))) return st;
+            if (f1) st = gemm_launch_xnorm(h->lmaps[l].wqkv, h->x_map, 3 * H, B, H, split_for(H / 64, 3 * H / GEMM_BM), e, h->w.ln1 + (size_t)l * H, s,
+                                           (const __half*)h->w.wo + (size_t)l * H * H, sizeof(__half) * (size_t)H * H, pdl);
+            else st = gemm_launch_maps(h->lmaps[l].wqkv, am.xn, 3 * H, B, H, bn, split_for(H / 64, 3 * H / GEMM_BM), e, s,
+                                       (const __half*)h->w.wo + (size_t)l * H * H, sizeof(__half) * (size_t)H * H, pdl);
+            if (st) return st;
         }
         AttnDecArgs aa{};
         aa.qkv = h->acc_qkv; aa.kcache = h->kplane(l); aa.vcache = h->vplane(l); aa.out = h->attn; aa.part = h->attn_part;
         aa.counters = h->attn_cnt; aa.pad_len = h->pad_len; aa.st = h->st; aa.inv_freq = h->inv_freq;
-        aa.H = H; aa.nH = c.n_heads; aa.max_seq = c.max_seq; aa.rearm = 1;
+        aa.H = H; aa.nH = c.n_heads; aa.max_seq = c.max_seq; aa.rearm = 1; aa.eps = c.rms_eps;
+        if (f1) aa.xrow = h->x;   // input_layernorm's row factor (llama.py:718), deferred from the QKV GEMM
         aa.trace = h->trace_rec();
         if (h->attn_tma) CTP_LAUNCH(k_attn_decode_tma, dim3(c.n_heads, B, nsplit), dim3(AT_THREADS), AT_SMEM, aa);
         else CTP_LAUNCH(k_attn_decode, dim3(c.n_heads, B, nsplit), dim3(128), 0, aa);
@@ -563,20 +575,24 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
             if ((st = gemm_launch_maps(h->lmaps[l].wo, am.attn, H, B, H, bn, split_for(H / 64, (H + GEMM_BM - 1) / GEMM_BM), e, s,
                                        (const __half*)h->w.wgu + (size_t)l * 2 * I * H, sizeof(__half) * (size_t)2 * I * H, pdl))) return st;
         }
-        {
+        if (!fnorm) {
             NormArgs nb{};
             nb.x = h->x; nb.w = h->w.ln2 + (size_t)l * H; nb.xn = h->xn; nb.H = H; nb.eps = c.rms_eps;
             nb.trace = h->trace_rec();
             CTP_LAUNCH(k_rmsnorm, dim3(B), dim3(256), 0, nb);
         }
-        {   // gate_proj | up_proj (llama.py:214)
+        {   // gate_proj | up_proj (llama.py:214); post_attention_layernorm (llama.py:741) folded in when fnorm
             GemmEpilogue e = epi_swap_atomic(h->acc_gu, 2 * I, B, 2 * I);
-            if ((st = gemm_launch_maps(h->lmaps[l].wgu, am.xn, 2 * I, B, H, bn, split_for(H / 64, 2 * I / GEMM_BM), e, s,
-                                       (const __half*)h->w.wdown + (size_t)l * H * I, sizeof(__half) * (size_t)H * I, pdl))) return st;
+            if (fnorm) st = gemm_launch_xnorm(h->lmaps[l].wgu, h->x_map, 2 * I, B, H, split_for(H / 64, 2 * I / GEMM_BM), e, h->w.ln2 + (size_t)l * H, s,
+                                              (const __half*)h->w.wdown + (size_t)l * H * I, sizeof(__half) * (size_t)H * I, pdl);
+            else st = gemm_launch_maps(h->lmaps[l].wgu, am.xn, 2 * I, B, H, bn, split_for(H / 64, 2 * I / GEMM_BM), e, s,
+                                       (const __half*)h->w.wdown + (size_t)l * H * I, sizeof(__half) * (size_t)H * I, pdl);
+            if (st) return st;
         }
         {
             const long long total = (long long)B * I;
-            CTP_LAUNCH(k_silu_mul, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, h->acc_gu, h->hmid, I, total, 1);
+            CTP_LAUNCH(k_silu_mul, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, h->acc_gu, h->hmid, I, total, 1,
+                       fnorm ? (const float*)h->x : (const float*)nullptr, H, c.rms_eps);
         }
         {   // down_proj accumulated into the residual stream (llama.py:214,745)
             GemmEpilogue e = epi_swap_atomic(h->x, H, B, H);
@@ -690,7 +706,7 @@ extern "C" ctp_status ctp_gpt_prefill(ctp_gpt* h, int32_t B, int32_t L0, const f
         }
         {
             const long long total = T * I;
-            k_silu_mul<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(h->acc_gu, h->hmid, I, total, 0);
+            k_silu_mul<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(h->acc_gu, h->hmid, I, total, 0, nullptr, 0, 0.f);
             LAUNCH_OK();
         }
         {

@@ -146,15 +146,33 @@ __global__ void __launch_bounds__(256) k_rmsnorm(NormArgs a) {
 // h = silu(gate) * up   (llama.py:214), gate/up read from the fp32 accumulator [rows][2I]
 // zero_after: the split-K accumulator is consumed exactly once per step, so its reader re-arms it for the next step
 // (saves the 24 KB-per-row clear that used to sit in the RMSNorm kernel's critical path)
-__global__ void k_silu_mul(float* __restrict__ gu, __half* __restrict__ out, int I, long long total, int zero_after) {
+// xrow != null: the gate|up GEMM contracted the un-normalised residual stream (RMSNorm folded, gemm.cuh XNORM); this block's
+// elements share one token row (I % blockDim == 0), whose factor rsqrt(mean(x^2) + eps) (llama.py:85) is recomputed here.
+__global__ void __launch_bounds__(256) k_silu_mul(float* __restrict__ gu, __half* __restrict__ out, int I, long long total, int zero_after,
+                                                  const float* __restrict__ xrow, int H, float eps) {
     pdl_launch_dependents();
     pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float rf = 1.f;
+    if (xrow) {
+        __shared__ float s_ss[8];
+        const long long r0 = ((long long)blockIdx.x * blockDim.x) / I;
+        const float* xr = xrow + r0 * H;
+        float ssq = 0.f;
+        for (int c = threadIdx.x; c < H; c += 256) { const float v = xr[c]; ssq += v * v; }
+        ssq = warp_sum(ssq);
+        if ((threadIdx.x & 31) == 0) s_ss[threadIdx.x >> 5] = ssq;
+        __syncthreads();
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) tot += s_ss[w];
+        rf = rsqrtf(tot / (float)H + eps);
+    }
     if (i >= total) return;
     const long long r = i / I;
     const int c = (int)(i % I);
-    const float g = gu[r * 2 * I + c];
-    const float u = gu[r * 2 * I + I + c];
+    const float g = gu[r * 2 * I + c] * rf;
+    const float u = gu[r * 2 * I + I + c] * rf;
     out[i] = __float2half_rn(silu(g) * u);
     if (zero_after) { gu[r * 2 * I + c] = 0.f; gu[r * 2 * I + I + c] = 0.f; }
 }
@@ -180,6 +198,7 @@ struct AttnDecArgs {
     // rsqrt(sum(x^2)/H + eps) (llama.py:85) is applied here; sum(x^2) arrives as ss_parts partial sums per row
     const float* ss;        // [ss_parts][ss_stride] or null (rows already normalised)
     int ss_parts, ss_stride;
+    const float* xrow;      // [B][H] or null: the residual stream the QKV GEMM contracted un-normalised; the row factor is recomputed here
     float eps;
     int rearm;              // 1: qkv is a split-K RED accumulator that its last reader zeroes; 0: plain final values
     unsigned long long* trace;
@@ -439,6 +458,16 @@ __global__ void __launch_bounds__(AT_THREADS) k_attn_decode_tma(AttnDecArgs a) {
     // ---- consumer warps (128 threads) ----
     float* qp = a.qkv + (long long)b * 3 * a.H + h * HEAD_DIM;
     float rf = 1.f;   // deferred RMSNorm row factor (llama.py:85)
+    if (a.xrow) {     // sum(x[b]^2) over the 3 KB row: loads overlap the q/k/v loads below
+        const float* xr = a.xrow + (long long)b * a.H;
+        float ssq = 0.f;
+        for (int c = tid; c < a.H; c += 128) { const float v = xr[c]; ssq += v * v; }
+        ssq = warp_sum(ssq);
+        if (lane == 0) s_m[warp] = ssq;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        rf = rsqrtf((s_m[0] + s_m[1] + s_m[2] + s_m[3]) / (float)a.H + a.eps);
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // s_m is reused by the group merge
+    }
     if (a.ss) {
         float part[8];
 #pragma unroll
