@@ -50,7 +50,8 @@ int gemm_init() {
         if (a == cudaSuccess) a = set_smem_attr<64>();
         if (a == cudaSuccess) a = set_smem_attr<128>();
         if (a == cudaSuccess) a = set_smem_attr<256>();
-        if (a == cudaSuccess) a = cudaFuncSetAttribute(gemm_tcgen05_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<32, true>::TOTAL);
+        if (a == cudaSuccess) a = cudaFuncSetAttribute(gemm_tcgen05_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<32, 1>::TOTAL);
+        if (a == cudaSuccess) a = cudaFuncSetAttribute(gemm_tcgen05_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<32, 2>::TOTAL);
         if (a != cudaSuccess) {
             ctp_set_error("cudaFuncSetAttribute(gemm smem): %s", cudaGetErrorString(a));
             g_init_status = CTP_ERR_CUDA;
@@ -102,33 +103,38 @@ int make_tmap_f32(CUtensorMap* out, const void* base, long long rows, long long 
     return CTP_OK;
 }
 
-int gemm_launch_xnorm(const CUtensorMap& tmA, const CUtensorMap& tmX, long long a_rows, long long T, long long K, int split_k,
-                      const GemmEpilogue& epi, const float* norm_w, cudaStream_t stream, const void* pf_ptr, unsigned long long pf_bytes, bool pdl) {
+int gemm_launch_x(int xmode, const CUtensorMap& tmA, const CUtensorMap& tmX, long long a_rows, long long T, long long K, int split_k,
+                  const GemmEpilogue& epi, const GemmShape& extra, cudaStream_t stream, bool pdl) {
     int st = gemm_init();
     if (st) return st;
-    if (T > 32 || (K % GEMM_BK) != 0 || !epi.swap || !epi.atomic || !norm_w) {
-        ctp_set_error("gemm_launch_xnorm: needs <= 32 token rows, K %% 64 == 0 and the swap/atomic decode epilogue");
+    if (T > 32 || (K % GEMM_BK) != 0 || !epi.swap || !epi.atomic || (xmode == 1 && !extra.norm_w) || (xmode != 1 && xmode != 2)) {
+        ctp_set_error("gemm_launch_x: needs <= 32 token rows, K %% 64 == 0, the swap/atomic decode epilogue and mode 1 (norm_w) or 2");
         return CTP_ERR_INVALID;
     }
-    GemmShape shp{};
-    shp.pf_ptr = pf_ptr; shp.pf_bytes = pf_bytes; shp.a_independent = pdl ? 1 : 0; shp.norm_w = norm_w;
+    GemmShape shp = extra;
+    shp.a_independent = pdl ? 1 : 0;
+    shp.dbg = nullptr;
     shp.k_blocks = (int)(K / GEMM_BK);
     shp.desc_lbo = g_desc[0]; shp.desc_sbo = g_desc[1]; shp.desc_layout = g_desc[2]; shp.desc_kadv = g_desc[3];
     if (split_k < 1) split_k = 1;
     if (split_k > shp.k_blocks) split_k = shp.k_blocks;
     dim3 grid(1, (unsigned)((a_rows + GEMM_BM - 1) / GEMM_BM), (unsigned)split_k);
-    cudaError_t e = launch_k(gemm_tcgen05_kernel<32, true>, grid, dim3(GEMM_THREADS), (size_t)GemmSmem<32, true>::TOTAL, stream, pdl, tmA, tmX, shp, epi);
+    cudaError_t e;
+    if (xmode == 1) e = launch_k(gemm_tcgen05_kernel<32, 1>, grid, dim3(GEMM_THREADS), (size_t)GemmSmem<32, 1>::TOTAL, stream, pdl, tmA, tmX, shp, epi);
+    else e = launch_k(gemm_tcgen05_kernel<32, 2>, grid, dim3(GEMM_THREADS), (size_t)GemmSmem<32, 2>::TOTAL, stream, pdl, tmA, tmX, shp, epi);
     ctp_count_launch();
     if (e == cudaSuccess) e = cudaGetLastError();
-    if (e != cudaSuccess) { ctp_set_error("xnorm gemm launch failed: %s", cudaGetErrorString(e)); return CTP_ERR_CUDA; }
+    if (e != cudaSuccess) { ctp_set_error("decode gemm (in-kernel operand) launch failed: %s", cudaGetErrorString(e)); return CTP_ERR_CUDA; }
     return CTP_OK;
 }
 
 template <int BN>
 static int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, long long a_rows, long long b_rows, long long K,
-                     int split_k, const GemmEpilogue& epi, cudaStream_t stream, const void* pf_ptr, unsigned long long pf_bytes, bool pdl) {
+                     int split_k, const GemmEpilogue& epi, cudaStream_t stream, const void* pf_ptr, unsigned long long pf_bytes, bool pdl,
+                     float* zero_ptr, unsigned long long zero_f4) {
     GemmShape shp{};
     shp.pf_ptr = pf_ptr; shp.pf_bytes = pf_bytes; shp.a_independent = pdl ? 1 : 0;
+    shp.zero_ptr = zero_ptr; shp.zero_f4 = zero_f4;
     shp.k_blocks = (int)((K + GEMM_BK - 1) / GEMM_BK);
     shp.dbg = g_dbg;
     shp.desc_lbo = g_desc[0]; shp.desc_sbo = g_desc[1]; shp.desc_layout = g_desc[2]; shp.desc_kadv = g_desc[3];
@@ -150,7 +156,8 @@ static int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, long long a
 }
 
 int gemm_launch_maps(const CUtensorMap& tmA, const CUtensorMap& tmB, long long a_rows, long long b_rows, long long K,
-                     int block_n, int split_k, const GemmEpilogue& epi, cudaStream_t stream, const void* pf_ptr, unsigned long long pf_bytes, bool pdl) {
+                     int block_n, int split_k, const GemmEpilogue& epi, cudaStream_t stream, const void* pf_ptr, unsigned long long pf_bytes, bool pdl,
+                     float* zero_ptr, unsigned long long zero_f4) {
     int st = gemm_init();
     if (st) return st;
     if (g_persistent && !epi.swap && !epi.atomic && split_k <= 1 && a_rows >= 512 && (block_n == 256 || block_n == 128)) {
@@ -168,10 +175,10 @@ int gemm_launch_maps(const CUtensorMap& tmA, const CUtensorMap& tmB, long long a
         return CTP_OK;
     }
     switch (block_n) {
-        case 32: return launch_bn<32>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream, pf_ptr, pf_bytes, pdl);
-        case 64: return launch_bn<64>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream, pf_ptr, pf_bytes, pdl);
-        case 128: return launch_bn<128>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream, pf_ptr, pf_bytes, pdl);
-        case 256: return launch_bn<256>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream, pf_ptr, pf_bytes, pdl);
+        case 32: return launch_bn<32>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream, pf_ptr, pf_bytes, pdl, zero_ptr, zero_f4);
+        case 64: return launch_bn<64>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream, pf_ptr, pf_bytes, pdl, zero_ptr, zero_f4);
+        case 128: return launch_bn<128>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream, pf_ptr, pf_bytes, pdl, zero_ptr, zero_f4);
+        case 256: return launch_bn<256>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream, pf_ptr, pf_bytes, pdl, zero_ptr, zero_f4);
         default: ctp_set_error("gemm: unsupported block_n %d", block_n); return CTP_ERR_INVALID;
     }
 }

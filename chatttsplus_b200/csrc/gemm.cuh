@@ -41,26 +41,38 @@ struct GemmShape {
     // (RMSNorm folded into the GEMM, llama.py:82-87).  tmB is then an fp32 tensor map over x; the contraction is linear in the row
     // factor rsqrt(mean(x[t]^2) + eps), which the CONSUMER of the accumulator applies (it recomputes it from x[t], 3 KB per row).
     const float* norm_w;      // [K]
+    float* ss_out;            // XNORM, optional: [T] += sum over this CTA's k-slice of x[t][k]^2 (m-tile 0 only, fp32 atomics)
+    // XSILU variant (decode down_proj): B[t][k] = fp16(silu(r*g[t][k]) * (r*u[t][k])) (llama.py:214) built from the fp32 gate|up
+    // accumulator (tmB: fp32 map over [T][2I], gate tile at column k, up tile at column up_off + k); r[t] = rsqrt(ss_in[t]/ss_dim + eps)
+    // is the RMSNorm row factor deferred from the gate|up GEMM (null: r = 1)
+    const float* ss_in;
+    float ss_dim, eps;
+    int up_off;
+    // any mode: a 16-byte aligned scratch region this kernel re-arms to zero after griddepcontrol.wait (dealt over the CTAs);
+    // its last readers ran in an earlier kernel of the step
+    float* zero_ptr;
+    unsigned long long zero_f4;
 };
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 192;
 
-template <int BN, bool XNORM = false>
+// XMODE: 0 = token operand by TMA (fp16 matrix), 1 = XNORM, 2 = XSILU (see GemmShape)
+template <int BN, int XMODE = 0>
 struct GemmSmem {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
     static constexpr int B_BYTES = BN * GEMM_BK * 2;
-    static constexpr int X_BYTES = XNORM ? BN * GEMM_BK * 4 : 0;   // fp32 landing tile of the residual stream (TMA, no swizzle)
+    static constexpr int X_BYTES = XMODE * BN * GEMM_BK * 4;   // fp32 landing tile(s): x (XNORM) or gate and up (XSILU); TMA, no swizzle
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES + X_BYTES;
     // <= 200 KB of operand ring; leaves room for the barrier block and 1 KB alignment slack under 227 KB.
     // BN=32 is the decode path (<= 4 k-blocks per CTA after split-K): 4 stages = 83 KB so that two CTAs — e.g. of two
     // independent half-batch chains — fit on one SM.
-    // XNORM: 3 stages of 28 KB (<= 2 k-blocks per CTA after split-K) keep two CTAs per SM as well.
-    static constexpr int STAGES = XNORM ? 3 : (BN == 32 ? 4 : ((200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES));
+    // XNORM: 3 stages of 28 KB, XSILU: 2 stages of 36 KB (<= 2 k-blocks per CTA after split-K): two CTAs per SM as well.
+    static constexpr int STAGES = XMODE == 1 ? 3 : XMODE == 2 ? 2 : (BN == 32 ? 4 : ((200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES));
     static constexpr int BAR_BYTES = 256;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
-    static_assert(!XNORM || BN == 32, "the in-kernel RMSNorm operand is built for the 32-token decode tile");
+    static_assert(XMODE == 0 || BN == 32, "the in-kernel token operands are built for the 32-token decode tile");
 };
 
 template <int BN>
@@ -146,14 +158,15 @@ __device__ __forceinline__ void gemm_epilogue_store(const GemmEpilogue& e, int r
     }
 }
 
-template <int BN, bool XNORM = false>
+template <int BN, int XMODE = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmShape shp, const GemmEpilogue epi) {
-    using S = GemmSmem<BN, XNORM>;
+    using S = GemmSmem<BN, XMODE>;
+    constexpr bool XNORM = XMODE == 1, XSILU = XMODE == 2;
     constexpr int STAGES = S::STAGES;
-    constexpr uint32_t FULL_COUNT = XNORM ? 5 : 1;                       // weight TMA (arrive.expect_tx) + 4 converter warps
-    constexpr uint32_t TX_BYTES = XNORM ? S::A_BYTES : S::A_BYTES + S::B_BYTES;
+    constexpr uint32_t FULL_COUNT = XMODE ? 5 : 1;                       // weight TMA (arrive.expect_tx) + 4 converter warps
+    constexpr uint32_t TX_BYTES = XMODE ? S::A_BYTES : S::A_BYTES + S::B_BYTES;
     constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128B-swizzle atoms
@@ -183,7 +196,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], FULL_COUNT);
             mbar_init(&empty_bar[s], 1);
-            if (XNORM) mbar_init(&x_bar[s], 1);
+            if (XMODE) mbar_init(&x_bar[s], 1);
         }
         mbar_init(accum_bar, 1);
         fence_barrier_init();
@@ -210,9 +223,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 pdl_wait();
                 for (int i = 0; i < pre; ++i) {
-                    if (XNORM) {
+                    if (XMODE) {
+                        uint8_t* xt = ring + i * S::STAGE_BYTES + S::A_BYTES + S::B_BYTES;
                         mbar_expect_tx(&x_bar[i], S::X_BYTES);
-                        tma_load_2d(&tmB, &x_bar[i], ring + i * S::STAGE_BYTES + S::A_BYTES + S::B_BYTES, (kb0 + i) * GEMM_BK, n0);
+                        tma_load_2d(&tmB, &x_bar[i], xt, (kb0 + i) * GEMM_BK, n0);
+                        if (XSILU) tma_load_2d(&tmB, &x_bar[i], xt + S::X_BYTES / 2, shp.up_off + (kb0 + i) * GEMM_BK, n0);
                     } else {
                         tma_load_2d(&tmB, &full_bar[i], ring + i * S::STAGE_BYTES + S::A_BYTES, (kb0 + i) * GEMM_BK, n0);
                     }
@@ -226,9 +241,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 uint8_t* b = a + S::A_BYTES;
                 mbar_expect_tx(&full_bar[s], TX_BYTES);
                 tma_load_2d(&tmA, &full_bar[s], a, (kb0 + i) * GEMM_BK, m0);
-                if (XNORM) {
+                if (XMODE) {
                     mbar_expect_tx(&x_bar[s], S::X_BYTES);
                     tma_load_2d(&tmB, &x_bar[s], b + S::B_BYTES, (kb0 + i) * GEMM_BK, n0);
+                    if (XSILU) tma_load_2d(&tmB, &x_bar[s], b + S::B_BYTES + S::X_BYTES / 2, shp.up_off + (kb0 + i) * GEMM_BK, n0);
                 } else {
                     tma_load_2d(&tmB, &full_bar[s], b, (kb0 + i) * GEMM_BK, n0);
                 }
@@ -276,14 +292,32 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else {
         // epilogue warps 0..3: TMEM lanes [32*warp, 32*warp+32)
-        if (XNORM) {
-            // converter: fp32 x tile (TMA, [32 rows][64 k] row-major) -> fp16(x * w) in the 128B-swizzled K-major layout the MMA
-            // reads (16-byte chunk c of row r at r*128 + ((c ^ (r & 7)) << 4)).  Thread (c16 = et & 15, r0 = et >> 4) owns k columns
-            // 4*c16..+3 of rows r0 + 8j: shared-memory reads are conflict-free, each thread fills half a chunk.
+        if (shp.zero_ptr) {
+            const unsigned long long n_cta = (unsigned long long)gridDim.x * gridDim.y * gridDim.z;
+            const unsigned long long cta = ((unsigned long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+            const unsigned long long per = (shp.zero_f4 + n_cta - 1) / n_cta;
+            const unsigned long long lo = cta * per, hi = (lo + per < shp.zero_f4) ? lo + per : shp.zero_f4;
+            float4* z = reinterpret_cast<float4*>(shp.zero_ptr);
+            for (unsigned long long q = lo + threadIdx.x; q < hi; q += 128) z[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (XMODE) {
+            // converter: fp32 tile(s) landed by TMA ([32 rows][64 k] row-major) -> fp16 operand in the 128B-swizzled K-major layout
+            // the MMA reads (16-byte chunk c of row r at r*128 + ((c ^ (r & 7)) << 4)).  Thread (c16 = et & 15, r0 = et >> 4) owns k
+            // columns 4*c16..+3 of rows r0 + 8j: shared-memory reads are conflict-free, each thread fills half a chunk.
             const int et = threadIdx.x, c16 = et & 15, r0 = et >> 4;
+            float rf[BN / 8], ssacc[BN / 8];
+#pragma unroll
+            for (int rr = 0; rr < BN / 8; ++rr) {
+                ssacc[rr] = 0.f;
+                rf[rr] = 1.f;
+                const int t = n0 + rr * 8 + r0;
+                if (XSILU && shp.ss_in && t < epi.T) rf[rr] = rsqrtf(__ldcg(shp.ss_in + t) / shp.ss_dim + shp.eps);
+            }
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % STAGES;
-                const float4 w4 = __ldg(reinterpret_cast<const float4*>(shp.norm_w + (kb0 + i) * GEMM_BK + c16 * 4));
+                float4 w4 = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (XNORM) w4 = __ldg(reinterpret_cast<const float4*>(shp.norm_w + (kb0 + i) * GEMM_BK + c16 * 4));
+                if (i >= STAGES) mbar_wait(&empty_bar[s], ((i / STAGES) & 1) ^ 1);   // the MMAs that read this B tile have retired
                 mbar_wait(&x_bar[s], (i / STAGES) & 1);
                 uint8_t* bt = ring + s * S::STAGE_BYTES + S::A_BYTES;
                 const float* xt = reinterpret_cast<const float*>(bt + S::B_BYTES);
@@ -291,7 +325,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int rr = 0; rr < BN / 8; ++rr) {
                     const int r = rr * 8 + r0;
                     const float4 a4 = *reinterpret_cast<const float4*>(xt + r * GEMM_BK + c16 * 4);
-                    __half2 h0 = __floats2half2_rn(a4.x * w4.x, a4.y * w4.y), h1 = __floats2half2_rn(a4.z * w4.z, a4.w * w4.w);
+                    float v0, v1, v2, v3;
+                    if (XNORM) {
+                        ssacc[rr] += a4.x * a4.x + a4.y * a4.y + a4.z * a4.z + a4.w * a4.w;
+                        v0 = a4.x * w4.x; v1 = a4.y * w4.y; v2 = a4.z * w4.z; v3 = a4.w * w4.w;
+                    } else {
+                        const float4 u4 = *reinterpret_cast<const float4*>(xt + BN * GEMM_BK + r * GEMM_BK + c16 * 4);
+                        const float q = rf[rr];
+                        v0 = silu(a4.x * q) * (u4.x * q); v1 = silu(a4.y * q) * (u4.y * q);
+                        v2 = silu(a4.z * q) * (u4.z * q); v3 = silu(a4.w * q) * (u4.w * q);
+                    }
+                    __half2 h0 = __floats2half2_rn(v0, v1), h1 = __floats2half2_rn(v2, v3);
                     uint2 pk;
                     pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
                     *reinterpret_cast<uint2*>(bt + r * 128 + (((c16 >> 1) ^ (r & 7)) << 4) + ((c16 & 1) << 3)) = pk;
@@ -299,6 +343,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full_bar[s]);
+            }
+            if (XNORM && shp.ss_out && blockIdx.y == 0) {   // every split adds its k-slice of sum(x^2) once
+#pragma unroll
+                for (int rr = 0; rr < BN / 8; ++rr) {
+                    float v = ssacc[rr];
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    v += __shfl_xor_sync(0xffffffffu, v, 8);
+                    const int t = n0 + rr * 8 + r0;
+                    if (c16 == 0 && t < epi.T) atomicAdd(shp.ss_out + t, v);
+                }
             }
         }
         if (nkb > 0) {
@@ -547,10 +603,12 @@ int gemm_launch(const GemmLaunch& g, cudaStream_t stream);
 // Variant with prebuilt tensor maps (decode path: maps are created once at bind time).
 int gemm_launch_maps(const CUtensorMap& tmA, const CUtensorMap& tmB, long long a_rows, long long b_rows, long long K,
                      int block_n, int split_k, const GemmEpilogue& epi, cudaStream_t stream, const void* pf_ptr = nullptr,
-                     unsigned long long pf_bytes = 0, bool pdl = false);
+                     unsigned long long pf_bytes = 0, bool pdl = false, float* zero_ptr = nullptr, unsigned long long zero_f4 = 0);
 // Decode QKV / gate|up GEMM with RMSNorm folded in (XNORM kernel): tmX is an fp32 map over the residual stream (make_tmap_f32).
-int gemm_launch_xnorm(const CUtensorMap& tmA, const CUtensorMap& tmX, long long a_rows, long long T, long long K, int split_k,
-                      const GemmEpilogue& epi, const float* norm_w, cudaStream_t stream, const void* pf_ptr, unsigned long long pf_bytes, bool pdl);
+// `extra` carries norm_w (+ ss_out) for xmode 1, ss_in / ss_dim / eps / up_off for xmode 2 (XSILU: tmX maps the gate|up
+// accumulator), zero_ptr / zero_f4 for either, and the L2 prefetch region.
+int gemm_launch_x(int xmode, const CUtensorMap& tmA, const CUtensorMap& tmX, long long a_rows, long long T, long long K, int split_k,
+                  const GemmEpilogue& epi, const GemmShape& extra, cudaStream_t stream, bool pdl);
 // fp32 matrix [rows, K] with row pitch `ld` elements -> 2-D tensor map, box = 64 x box_rows, no swizzle.
 int make_tmap_f32(CUtensorMap* out, const void* base, long long rows, long long K, long long ld_elems, int box_rows);
 int gemm_init();  // resolves cuTensorMapEncodeTiled, sets max dynamic smem attributes

@@ -76,6 +76,10 @@ struct ctp_gpt {
     // ---- cluster decode path (decode_gemm.cuh): split-K reduced through distributed shared memory, no L2 atomics ----------
     bool fuse_norm = true;     // RMSNorm folded into the QKV / gate|up GEMMs (XNORM kernel); CTP_FUSE_NORM=0: stand-alone norm kernels
     CUtensorMap x_map{};       // fp32 map over the first 64 rows of the residual stream
+    CUtensorMap gu_map{};      // fp32 map over the decode gate|up accumulator
+    float* dec_gu = nullptr;   // decode only, one re-armable block: ss2[64] (sum(x^2) seen by the gate|up GEMM) | gate|up accumulator [64][2I]
+    float* ss2() const { return dec_gu; }
+    float* gu_acc() const { return dec_gu + 64; }
     bool attn_tma = true;      // TMA-staged decode attention (CTP_ATTN=ldg selects the per-thread-load kernel)
     bool use_cluster = false;  // CTP_DECODE_GEMM=cluster: split-K reduced through DSMEM inside a thread-block cluster, 5 kernels per layer.
                                // Parity-green but slower than the RED split-K path on B200 today (profiles/README.md), so opt-in.
@@ -142,6 +146,7 @@ static int ensure_workspace(ctp_gpt* h, long long rows) {
         if ((st = make_tmap_kmajor(&am.hmid, h->hmid, mb, I, I, bn))) return st;
     }
     if ((st = make_tmap_f32(&h->x_map, h->x, mb, H, H, 32))) return st;
+    if (h->dec_gu && (st = make_tmap_f32(&h->gu_map, h->gu_acc(), mb, 2 * I, 2 * I, 32))) return st;
     // captured graphs hold the old pointers
     for (auto& kvp : h->graphs) cudaGraphExecDestroy(kvp.second);
     h->graphs.clear();
@@ -211,7 +216,8 @@ extern "C" ctp_status ctp_gpt_create(ctp_gpt** out, const ctp_gpt_cfg* cfg) {
         if (const char* e = getenv("CTP_DECODE_GEMM")) h->use_cluster = (strcmp(e, "cluster") == 0);
         if (const char* e = getenv("CTP_ATTN")) h->attn_tma = (strcmp(e, "ldg") != 0);
         if (const char* e = getenv("CTP_FUSE_NORM")) h->fuse_norm = atoi(e) != 0;
-        if (cfg->inter % 256 != 0) h->fuse_norm = false;   // k_silu_mul: one token row per block
+        CK(cudaMalloc(&h->dec_gu, sizeof(float) * (64 + (size_t)64 * 2 * cfg->inter)));
+        CK(cudaMemset(h->dec_gu, 0, sizeof(float) * (64 + (size_t)64 * 2 * cfg->inter)));
 
         CK(cudaFuncSetAttribute(k_attn_decode_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
         if (const char* e = getenv("CTP_KV_PREFETCH")) h->kv_prefetch = atoi(e) != 0;
@@ -291,7 +297,7 @@ extern "C" void ctp_gpt_destroy(ctp_gpt* h) {
     if (!h) return;
     for (auto& kvp : h->graphs) cudaGraphExecDestroy(kvp.second);
     cudaFree(h->x); cudaFree(h->xn); cudaFree(h->acc_qkv); cudaFree(h->attn); cudaFree(h->acc_gu); cudaFree(h->hmid);
-    cudaFree(h->dec_buf); cudaFree(h->trace);
+    cudaFree(h->dec_buf); cudaFree(h->trace); cudaFree(h->dec_gu);
     cudaFree(h->x_last); cudaFree(h->hidden); cudaFree(h->logits); cudaFree(h->kv); cudaFree(h->attn_part);
     cudaFree(h->attn_cnt); cudaFree(h->pad_len); cudaFree(h->inv_freq); cudaFree(h->st);
     cudaFree(h->wqkv_p); cudaFree(h->wo_p); cudaFree(h->wgu_p); cudaFree(h->wdn_p); cudaFree(h->whead_p);
@@ -542,10 +548,13 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
     if (cluster) {
         if ((st = run_decode_trunk_cluster(h, B, nsplit, ids_ext, s))) return st;
     }
-    // RMSNorm folded into the GEMM that consumes it (batch <= 32, TMA-staged attention): 6 kernels per layer instead of 8.
-    const bool fnorm = h->fuse_norm && h->attn_tma && B <= 32;
+    // Batch <= 32 with the TMA-staged attention: RMSNorm is folded into the QKV / gate|up GEMMs and silu(gate)*up into down_proj
+    // (in-kernel token operands, gemm.cuh XNORM / XSILU): FIVE kernels per layer instead of eight.
+    const bool fuse = h->fuse_norm && h->attn_tma && B <= 32;
+    float* gu = fuse ? h->gu_acc() : h->acc_gu;
+    const unsigned long long rearm_f4 = (unsigned long long)(64 + (size_t)B * 2 * I) / 4;   // ss2 | gate|up rows of the live batch
     for (int l = 0; l < (cluster ? 0 : c.n_layers); ++l) {
-        const bool f1 = fnorm && l > 0;   // layer 0 keeps the norm kernel: it is also the code-embedding front end
+        const bool f1 = fuse && l > 0;   // layer 0 keeps the norm kernel: it is also the code-embedding front end
         if (!f1) {
             NormArgs na{};
             na.x = h->x; na.w = h->w.ln1 + (size_t)l * H; na.xn = h->xn; na.H = H; na.eps = c.rms_eps;
@@ -554,12 +563,19 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
             na.trace = h->trace_rec();
             CTP_LAUNCH(k_rmsnorm, dim3(B), dim3(256), 0, na);
         }
-        {   // q,k,v projections as one GEMM (llama.py:619-621), weights are the M operand
+        {   // q,k,v projections as one GEMM (llama.py:619-621), weights are the M operand; input_layernorm (llama.py:718) folded in
+            // when f1 (attention applies the row factor).  Also re-arms ss2 / gate|up, last read by the previous layer's down GEMM.
             GemmEpilogue e = epi_swap_atomic(h->acc_qkv, 3 * H, B, 3 * H);
-            if (f1) st = gemm_launch_xnorm(h->lmaps[l].wqkv, h->x_map, 3 * H, B, H, split_for(H / 64, 3 * H / GEMM_BM), e, h->w.ln1 + (size_t)l * H, s,
-                                           (const __half*)h->w.wo + (size_t)l * H * H, sizeof(__half) * (size_t)H * H, pdl);
-            else st = gemm_launch_maps(h->lmaps[l].wqkv, am.xn, 3 * H, B, H, bn, split_for(H / 64, 3 * H / GEMM_BM), e, s,
-                                       (const __half*)h->w.wo + (size_t)l * H * H, sizeof(__half) * (size_t)H * H, pdl);
+            const void* pf = (const __half*)h->w.wo + (size_t)l * H * H;
+            const size_t pfb = sizeof(__half) * (size_t)H * H;
+            if (f1) {
+                GemmShape ex{};
+                ex.pf_ptr = pf; ex.pf_bytes = pfb; ex.norm_w = h->w.ln1 + (size_t)l * H; ex.zero_ptr = h->dec_gu; ex.zero_f4 = rearm_f4;
+                st = gemm_launch_x(1, h->lmaps[l].wqkv, h->x_map, 3 * H, B, H, split_for(H / 64, 3 * H / GEMM_BM), e, ex, s, pdl);
+            } else {
+                st = gemm_launch_maps(h->lmaps[l].wqkv, am.xn, 3 * H, B, H, bn, split_for(H / 64, 3 * H / GEMM_BM), e, s, pf, pfb, pdl,
+                                      fuse ? h->dec_gu : nullptr, fuse ? rearm_f4 : 0);
+            }
             if (st) return st;
         }
         AttnDecArgs aa{};
@@ -575,30 +591,42 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
             if ((st = gemm_launch_maps(h->lmaps[l].wo, am.attn, H, B, H, bn, split_for(H / 64, (H + GEMM_BM - 1) / GEMM_BM), e, s,
                                        (const __half*)h->w.wgu + (size_t)l * 2 * I * H, sizeof(__half) * (size_t)2 * I * H, pdl))) return st;
         }
-        if (!fnorm) {
+        if (!fuse) {
             NormArgs nb{};
             nb.x = h->x; nb.w = h->w.ln2 + (size_t)l * H; nb.xn = h->xn; nb.H = H; nb.eps = c.rms_eps;
             nb.trace = h->trace_rec();
             CTP_LAUNCH(k_rmsnorm, dim3(B), dim3(256), 0, nb);
         }
-        {   // gate_proj | up_proj (llama.py:214); post_attention_layernorm (llama.py:741) folded in when fnorm
-            GemmEpilogue e = epi_swap_atomic(h->acc_gu, 2 * I, B, 2 * I);
-            if (fnorm) st = gemm_launch_xnorm(h->lmaps[l].wgu, h->x_map, 2 * I, B, H, split_for(H / 64, 2 * I / GEMM_BM), e, h->w.ln2 + (size_t)l * H, s,
-                                              (const __half*)h->w.wdown + (size_t)l * H * I, sizeof(__half) * (size_t)H * I, pdl);
-            else st = gemm_launch_maps(h->lmaps[l].wgu, am.xn, 2 * I, B, H, bn, split_for(H / 64, 2 * I / GEMM_BM), e, s,
-                                       (const __half*)h->w.wdown + (size_t)l * H * I, sizeof(__half) * (size_t)H * I, pdl);
+        {   // gate_proj | up_proj (llama.py:214); post_attention_layernorm (llama.py:741) folded in when fused: the GEMM contracts x*w
+            // and leaves sum(x^2) per row in ss2 for the down GEMM's prologue
+            GemmEpilogue e = epi_swap_atomic(gu, 2 * I, B, 2 * I);
+            const void* pf = (const __half*)h->w.wdown + (size_t)l * H * I;
+            const size_t pfb = sizeof(__half) * (size_t)H * I;
+            if (fuse) {
+                GemmShape ex{};
+                ex.pf_ptr = pf; ex.pf_bytes = pfb; ex.norm_w = h->w.ln2 + (size_t)l * H; ex.ss_out = h->ss2();
+                st = gemm_launch_x(1, h->lmaps[l].wgu, h->x_map, 2 * I, B, H, split_for(H / 64, 2 * I / GEMM_BM), e, ex, s, pdl);
+            } else {
+                st = gemm_launch_maps(h->lmaps[l].wgu, am.xn, 2 * I, B, H, bn, split_for(H / 64, 2 * I / GEMM_BM), e, s, pf, pfb, pdl);
+            }
             if (st) return st;
         }
-        {
+        if (!fuse) {
             const long long total = (long long)B * I;
-            CTP_LAUNCH(k_silu_mul, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, h->acc_gu, h->hmid, I, total, 1,
-                       fnorm ? (const float*)h->x : (const float*)nullptr, H, c.rms_eps);
+            CTP_LAUNCH(k_silu_mul, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, gu, h->hmid, I, total, 1);
         }
-        {   // down_proj accumulated into the residual stream (llama.py:214,745)
+        {   // down_proj accumulated into the residual stream (llama.py:214,745); silu(gate)*up folded into its token operand when fused
             GemmEpilogue e = epi_swap_atomic(h->x, H, B, H);
             const void* nxt = (l + 1 < c.n_layers) ? (const void*)((const __half*)h->w.wqkv + (size_t)(l + 1) * 3 * H * H) : h->w.head_code;
             const size_t nxt_bytes = (l + 1 < c.n_layers) ? sizeof(__half) * (size_t)3 * H * H : sizeof(__half) * (size_t)c.num_vq * c.num_audio * H;
-            if ((st = gemm_launch_maps(h->lmaps[l].wdown, am.hmid, H, B, I, bn, split_for(I / 64, (H + GEMM_BM - 1) / GEMM_BM), e, s, nxt, nxt_bytes, pdl))) return st;
+            if (fuse) {
+                GemmShape ex{};
+                ex.pf_ptr = nxt; ex.pf_bytes = nxt_bytes; ex.ss_in = h->ss2(); ex.ss_dim = (float)H; ex.eps = c.rms_eps; ex.up_off = I;
+                st = gemm_launch_x(2, h->lmaps[l].wdown, h->gu_map, H, B, I, split_for(I / 64, (H + GEMM_BM - 1) / GEMM_BM), e, ex, s, pdl);
+            } else {
+                st = gemm_launch_maps(h->lmaps[l].wdown, am.hmid, H, B, I, bn, split_for(I / 64, (H + GEMM_BM - 1) / GEMM_BM), e, s, nxt, nxt_bytes, pdl);
+            }
+            if (st) return st;
         }
     }
     // final norm (llama.py:1002) -> hidden state of this step (gpt.py:422-423) + operand of the heads
@@ -706,7 +734,7 @@ extern "C" ctp_status ctp_gpt_prefill(ctp_gpt* h, int32_t B, int32_t L0, const f
         }
         {
             const long long total = T * I;
-            k_silu_mul<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(h->acc_gu, h->hmid, I, total, 0, nullptr, 0, 0.f);
+            k_silu_mul<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(h->acc_gu, h->hmid, I, total, 0);
             LAUNCH_OK();
         }
         {
@@ -731,6 +759,7 @@ extern "C" ctp_status ctp_gpt_prefill(ctp_gpt* h, int32_t B, int32_t L0, const f
     // the decode path accumulates into acc_qkv / acc_gu with fp32 atomics and their readers re-arm them: start from zero
     CTP_CUDA_OK(cudaMemsetAsync(h->acc_qkv, 0, sizeof(float) * (size_t)c.max_batch * 3 * H, s));
     CTP_CUDA_OK(cudaMemsetAsync(h->acc_gu, 0, sizeof(float) * (size_t)c.max_batch * 2 * I, s));
+    CTP_CUDA_OK(cudaMemsetAsync(h->dec_gu, 0, sizeof(float) * (64 + (size_t)64 * 2 * I), s));
     h->B = B; h->cur_len = L0; h->step = 0; h->max_new = bufs->max_new; h->have_bufs = true;
     return CTP_OK;
 }

@@ -146,33 +146,15 @@ __global__ void __launch_bounds__(256) k_rmsnorm(NormArgs a) {
 // h = silu(gate) * up   (llama.py:214), gate/up read from the fp32 accumulator [rows][2I]
 // zero_after: the split-K accumulator is consumed exactly once per step, so its reader re-arms it for the next step
 // (saves the 24 KB-per-row clear that used to sit in the RMSNorm kernel's critical path)
-// xrow != null: the gate|up GEMM contracted the un-normalised residual stream (RMSNorm folded, gemm.cuh XNORM); this block's
-// elements share one token row (I % blockDim == 0), whose factor rsqrt(mean(x^2) + eps) (llama.py:85) is recomputed here.
-__global__ void __launch_bounds__(256) k_silu_mul(float* __restrict__ gu, __half* __restrict__ out, int I, long long total, int zero_after,
-                                                  const float* __restrict__ xrow, int H, float eps) {
+__global__ void k_silu_mul(float* __restrict__ gu, __half* __restrict__ out, int I, long long total, int zero_after) {
     pdl_launch_dependents();
     pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    float rf = 1.f;
-    if (xrow) {
-        __shared__ float s_ss[8];
-        const long long r0 = ((long long)blockIdx.x * blockDim.x) / I;
-        const float* xr = xrow + r0 * H;
-        float ssq = 0.f;
-        for (int c = threadIdx.x; c < H; c += 256) { const float v = xr[c]; ssq += v * v; }
-        ssq = warp_sum(ssq);
-        if ((threadIdx.x & 31) == 0) s_ss[threadIdx.x >> 5] = ssq;
-        __syncthreads();
-        float tot = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) tot += s_ss[w];
-        rf = rsqrtf(tot / (float)H + eps);
-    }
     if (i >= total) return;
     const long long r = i / I;
     const int c = (int)(i % I);
-    const float g = gu[r * 2 * I + c] * rf;
-    const float u = gu[r * 2 * I + I + c] * rf;
+    const float g = gu[r * 2 * I + c];
+    const float u = gu[r * 2 * I + I + c];
     out[i] = __float2half_rn(silu(g) * u);
     if (zero_after) { gu[r * 2 * I + c] = 0.f; gu[r * 2 * I + I + c] = 0.f; }
 }

@@ -116,6 +116,18 @@ def test_trunk_opt_in_variants(env, monkeypatch):
     _teacher_forced(cfg, B=5, L0=70, steps=4, seed=21, pads=[0, 3, 9, 0, 60])
 
 
+def test_trunk_batch_above_32_uses_64_wide_tiles():
+    """Batches of 33..64 rows run the 64-token N tile with stand-alone norm / SiLU kernels (the in-kernel operands are built for <= 32 rows)."""
+    cfg = synth.GPTConfig(num_hidden_layers=2, num_text_tokens=256)
+    _teacher_forced(cfg, B=40, L0=20, steps=3, seed=22, pads=[0, 3] + [0] * 38)
+
+
+def test_trunk_odd_batch_sizes():
+    cfg = synth.GPTConfig(num_hidden_layers=2, num_text_tokens=256)
+    for B in (1, 7, 31):
+        _teacher_forced(cfg, B=B, L0=9, steps=3, seed=23 + B)
+
+
 def test_trunk_full_depth_config2_shape():
     """20 layers, B=32, L0=128 (BASELINE.json configs[1] shape), 4 teacher-forced steps."""
     cfg = synth.GPTConfig()
