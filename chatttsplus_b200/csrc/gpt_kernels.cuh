@@ -761,10 +761,13 @@ __device__ __forceinline__ uint32_t philox_mix(uint64_t seed, uint32_t a, uint32
 
 // One warp per (b, q) row: warps 0..num_vq-1 of the calling block handle rows b*num_vq + warp.
 // FUSED: called from the persistent step kernel (compute warps only: named barrier 1 over 256 threads, n_blocks = B).
-template <bool FUSED>
+// PDL_INSIDE: the function itself executes griddepcontrol.wait, after everything that does not depend on the logits (sampling
+// configuration, history window and repetition counts, the uniform) has been loaded — that part overlaps the heads GEMM.
+template <bool FUSED, bool PDL_INSIDE = false>
 __device__ __forceinline__ void sample_block(const SampleArgs& a, const int b, const int n_blocks, float* s_scores, int* s_choice) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp >= a.num_vq) {
+        if (PDL_INSIDE) pdl_wait();
         if (a.st) { if (FUSED) asm volatile("bar.sync 1, 256;" ::: "memory"); else __syncthreads(); }
         return;
     }
@@ -772,23 +775,27 @@ __device__ __forceinline__ void sample_block(const SampleArgs& a, const int b, c
     const int V = a.vocab;
     const int vpad = (V + 31) & ~31;
     float* sc = s_scores + warp * vpad;
-    const ctp_sample_cfg& cfg = a.st ? a.st->cfg : a.cfg;
+    const ctp_sample_cfg* cfgp = a.st ? &a.st->cfg : &a.cfg;
+    // scalar copies: the configuration lives in device memory (GenState) and must not be re-read inside the loops below
+    struct { float rep_penalty, top_p; int rep_window, rep_max_ids, top_k, min_keep, eos, min_new; unsigned long long seed; } cfg;
+    cfg.rep_penalty = cfgp->rep_penalty; cfg.top_p = cfgp->top_p; cfg.rep_window = cfgp->rep_window; cfg.rep_max_ids = cfgp->rep_max_ids;
+    cfg.top_k = cfgp->top_k; cfg.min_keep = cfgp->min_keep; cfg.eos = cfgp->eos; cfg.min_new = cfgp->min_new; cfg.seed = cfgp->seed;
+    const float inv_t = 1.0f / cfgp->temperature[warp];
     const int step = a.st ? a.st->step : a.step;
     const int hist_len = a.st ? a.st->step : a.hist_len;
     const int* hist = a.st ? a.st->ids_buf : a.hist;
     const int hstride = a.st ? a.st->max_new : a.hist_stride;
     const float* u_ptr = a.st ? (a.st->u_base ? a.st->u_base + (long long)step * a.rows : nullptr) : a.u;
-
-    // 1. temperature (gpt.py:469)
-    const float inv_t = 1.0f / cfg.temperature[warp];
-    const float* lg = a.logits + (long long)row * V;
-    for (int v = lane; v < V; v += 32) sc[v] = (FUSED ? __ldcg(lg + v) : lg[v]) * inv_t;
-    __syncwarp();
-    if (!FUSED && threadIdx.x == 0) trace_mark(a.trace, 4);
-    // 2. windowed repetition penalty (processors.py:18-34)
-    if (cfg.rep_penalty != 1.0f && row < cfg.rep_max_ids) {
+    float uu;
+    if (u_ptr) uu = u_ptr[row];
+    else uu = (float)(philox_mix(cfg.seed, (uint32_t)step, (uint32_t)row) >> 8) * (1.0f / 16777216.0f);
+    // windowed repetition counts (processors.py:18-34): which token this lane penalises and by how much
+    const bool rep_on = cfg.rep_penalty != 1.0f && row < cfg.rep_max_ids;
+    int my = -1;
+    float alpha = 1.f;
+    bool rep_apply = false;
+    if (rep_on) {
         const int w = min(hist_len, cfg.rep_window);
-        int my = -1;
         if (lane < w) my = hist[((long long)b * hstride + (hist_len - w + lane)) * a.ids_cols + warp];
         int mult = 0;
         bool first = true;
@@ -799,8 +806,22 @@ __device__ __forceinline__ void sample_block(const SampleArgs& a, const int b, c
                 if (t < lane) first = false;
             }
         }
-        if (lane < w && first && my >= 0 && my < V) {
-            const float alpha = powf(cfg.rep_penalty, (float)mult);
+        rep_apply = lane < w && first && my >= 0 && my < V;
+        if (rep_apply) alpha = powf(cfg.rep_penalty, (float)mult);
+    }
+    if (PDL_INSIDE) {
+        pdl_wait();
+        if (threadIdx.x == 0) trace_mark(a.trace, 1);
+    }
+
+    // 1. temperature (gpt.py:469)
+    const float* lg = a.logits + (long long)row * V;
+    for (int v = lane; v < V; v += 32) sc[v] = (FUSED ? __ldcg(lg + v) : lg[v]) * inv_t;
+    __syncwarp();
+    if (!FUSED && threadIdx.x == 0) trace_mark(a.trace, 4);
+    // 2. windowed repetition penalty (processors.py:18-34)
+    if (rep_on) {
+        if (rep_apply) {
             const float s = sc[my];
             sc[my] = (s < 0.f) ? s * alpha : s / alpha;
         }
@@ -828,10 +849,20 @@ __device__ __forceinline__ void sample_block(const SampleArgs& a, const int b, c
 #pragma unroll
         for (int i = 0; i < REG_V; ++i) { const int v = lane + 32 * i; vals[i] = v < V ? sc[v] : -INFINITY; }
         for (int k = 0; k < K; ++k) {
-            float lv = vals[0];
-            int li = 0;
+            // local arg-max as four independent chains of five, then merged (ties keep the smaller index)
+            float cv[4];
+            int ci[4];
 #pragma unroll
-            for (int i = 1; i < REG_V; ++i) if (vals[i] > lv) { lv = vals[i]; li = i; }
+            for (int c = 0; c < 4; ++c) {
+                cv[c] = vals[5 * c]; ci[c] = 5 * c;
+#pragma unroll
+                for (int i = 1; i < 5; ++i) if (vals[5 * c + i] > cv[c]) { cv[c] = vals[5 * c + i]; ci[c] = 5 * c + i; }
+            }
+            if (cv[1] > cv[0]) { cv[0] = cv[1]; ci[0] = ci[1]; }
+            if (cv[3] > cv[2]) { cv[2] = cv[3]; ci[2] = ci[3]; }
+            float lv = cv[0];
+            int li = ci[0];
+            if (cv[2] > lv) { lv = cv[2]; li = ci[2]; }
             const unsigned u = __float_as_uint(lv);
             const unsigned key = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
             const unsigned kmax = __reduce_max_sync(0xffffffffu, key);
@@ -893,9 +924,6 @@ __device__ __forceinline__ void sample_block(const SampleArgs& a, const int b, c
         const float op = __shfl_sync(0xffffffffu, p, t);
         if (oi < my_idx) cdf_before += op;
     }
-    float uu;
-    if (u_ptr) uu = u_ptr[row];
-    else uu = (float)(philox_mix(cfg.seed, (uint32_t)step, (uint32_t)row) >> 8) * (1.0f / 16777216.0f);
     // chosen = survivor with cdf_before <= u < cdf_before + p; fall back to the largest id survivor
     const bool hit = keep && (cdf_before <= uu) && (uu < cdf_before + p);
     unsigned ballot = __ballot_sync(0xffffffffu, hit);
@@ -950,11 +978,9 @@ __device__ __forceinline__ void sample_block(const SampleArgs& a, const int b, c
 __global__ void k_sample(SampleArgs a) {
     if (threadIdx.x == 0) trace_mark(a.trace, 0);
     pdl_launch_dependents();
-    pdl_wait();
-    if (threadIdx.x == 0) trace_mark(a.trace, 1);
     extern __shared__ float s_scores_dyn[];  // [num_vq][vocab_pad]
     __shared__ int s_choice[MAX_VQ];
-    sample_block<false>(a, blockIdx.x, gridDim.x, s_scores_dyn, s_choice);
+    sample_block<false, true>(a, blockIdx.x, gridDim.x, s_scores_dyn, s_choice);
     if (threadIdx.x == 0) trace_end(a.trace);
 }
 
