@@ -131,10 +131,10 @@ int gemm_launch_x(int xmode, const CUtensorMap& tmA, const CUtensorMap& tmX, lon
 template <int BN>
 static int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, long long a_rows, long long b_rows, long long K,
                      int split_k, const GemmEpilogue& epi, cudaStream_t stream, const void* pf_ptr, unsigned long long pf_bytes, bool pdl,
-                     float* zero_ptr, unsigned long long zero_f4) {
+                     float* zero_ptr, unsigned long long zero_f4, unsigned long long* trace) {
     GemmShape shp{};
     shp.pf_ptr = pf_ptr; shp.pf_bytes = pf_bytes; shp.a_independent = pdl ? 1 : 0;
-    shp.zero_ptr = zero_ptr; shp.zero_f4 = zero_f4;
+    shp.zero_ptr = zero_ptr; shp.zero_f4 = zero_f4; shp.trace = trace;
     shp.k_blocks = (int)((K + GEMM_BK - 1) / GEMM_BK);
     shp.dbg = g_dbg;
     shp.desc_lbo = g_desc[0]; shp.desc_sbo = g_desc[1]; shp.desc_layout = g_desc[2]; shp.desc_kadv = g_desc[3];
@@ -157,7 +157,7 @@ static int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, long long a
 
 int gemm_launch_maps(const CUtensorMap& tmA, const CUtensorMap& tmB, long long a_rows, long long b_rows, long long K,
                      int block_n, int split_k, const GemmEpilogue& epi, cudaStream_t stream, const void* pf_ptr, unsigned long long pf_bytes, bool pdl,
-                     float* zero_ptr, unsigned long long zero_f4) {
+                     float* zero_ptr, unsigned long long zero_f4, unsigned long long* trace) {
     int st = gemm_init();
     if (st) return st;
     if (g_persistent && !epi.swap && !epi.atomic && split_k <= 1 && a_rows >= 512 && (block_n == 256 || block_n == 128)) {
@@ -175,10 +175,10 @@ int gemm_launch_maps(const CUtensorMap& tmA, const CUtensorMap& tmB, long long a
         return CTP_OK;
     }
     switch (block_n) {
-        case 32: return launch_bn<32>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream, pf_ptr, pf_bytes, pdl, zero_ptr, zero_f4);
-        case 64: return launch_bn<64>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream, pf_ptr, pf_bytes, pdl, zero_ptr, zero_f4);
-        case 128: return launch_bn<128>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream, pf_ptr, pf_bytes, pdl, zero_ptr, zero_f4);
-        case 256: return launch_bn<256>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream, pf_ptr, pf_bytes, pdl, zero_ptr, zero_f4);
+        case 32: return launch_bn<32>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream, pf_ptr, pf_bytes, pdl, zero_ptr, zero_f4, trace);
+        case 64: return launch_bn<64>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream, pf_ptr, pf_bytes, pdl, zero_ptr, zero_f4, trace);
+        case 128: return launch_bn<128>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream, pf_ptr, pf_bytes, pdl, zero_ptr, zero_f4, trace);
+        case 256: return launch_bn<256>(tmA, tmB, a_rows, b_rows, K, split_k, epi, stream, pf_ptr, pf_bytes, pdl, zero_ptr, zero_f4, trace);
         default: ctp_set_error("gemm: unsupported block_n %d", block_n); return CTP_ERR_INVALID;
     }
 }

@@ -34,6 +34,7 @@ struct GemmShape {
     // the CTP_DESC environment variable for bring-up diagnostics only
     uint32_t desc_lbo, desc_sbo, desc_layout, desc_kadv;
     long long* dbg;  // bring-up only: per-CTA clock64 stamps [cta][8], or null
+    unsigned long long* trace;   // bring-up only: in-graph timeline record of this launch (ctp_common.cuh), or null
     int a_independent;        // PDL: the M operand (weights in the decode path) does not depend on the previous kernel
     const void* pf_ptr;       // optional: region the NEXT kernel will stream (its weights); every CTA prefetches a share into L2
     unsigned long long pf_bytes;
@@ -188,6 +189,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int nkb = kb1 - kb0;
     long long* dbg = shp.dbg ? shp.dbg + ((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
     if (dbg && threadIdx.x == 0) dbg[0] = clock64();
+    if (threadIdx.x == 0) trace_mark(shp.trace, 0);
     pdl_launch_dependents();
 
     if (warp == 4 && lane == 0) {
@@ -210,6 +212,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (dbg && threadIdx.x == 0) dbg[1] = clock64();
     const bool early_a = shp.a_independent != 0;
     if (!(early_a && warp == 4 && lane == 0)) pdl_wait();   // the producer thread waits after issuing the weight loads
+    if (threadIdx.x == 0) trace_mark(shp.trace, 1);
 
     if (warp == 4) {
         if (lane == 0) {
@@ -319,6 +322,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (XNORM) w4 = __ldg(reinterpret_cast<const float4*>(shp.norm_w + (kb0 + i) * GEMM_BK + c16 * 4));
                 if (i >= STAGES) mbar_wait(&empty_bar[s], ((i / STAGES) & 1) ^ 1);   // the MMAs that read this B tile have retired
                 mbar_wait(&x_bar[s], (i / STAGES) & 1);
+                if (i == 0 && threadIdx.x == 0) trace_mark(shp.trace, 4);
                 uint8_t* bt = ring + s * S::STAGE_BYTES + S::A_BYTES;
                 const float* xt = reinterpret_cast<const float*>(bt + S::B_BYTES);
 #pragma unroll
@@ -344,6 +348,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full_bar[s]);
             }
+            if (threadIdx.x == 0) trace_mark(shp.trace, 5);
             if (XNORM && shp.ss_out && blockIdx.y == 0) {   // every split adds its k-slice of sum(x^2) once
 #pragma unroll
                 for (int rr = 0; rr < BN / 8; ++rr) {
@@ -359,6 +364,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (nkb > 0) {
             mbar_wait(accum_bar, 0);
+            if (threadIdx.x == 0) trace_mark(shp.trace, 6);
             if (dbg && threadIdx.x == 0) dbg[4] = clock64();
             tc_fence_after();
             const int row_g = m0 + warp * 32 + lane;
@@ -397,10 +403,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     }
     if (dbg && threadIdx.x == 0) dbg[5] = clock64();
+    if (threadIdx.x == 0) trace_mark(shp.trace, 7);
     tc_fence_before();
     __syncthreads();
     if (warp == 5) tmem_dealloc<TMEM_COLS>(tmem_base);
     if (dbg && threadIdx.x == 160) dbg[6] = clock64();
+    if (threadIdx.x == 0) trace_end(shp.trace);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -603,7 +611,8 @@ int gemm_launch(const GemmLaunch& g, cudaStream_t stream);
 // Variant with prebuilt tensor maps (decode path: maps are created once at bind time).
 int gemm_launch_maps(const CUtensorMap& tmA, const CUtensorMap& tmB, long long a_rows, long long b_rows, long long K,
                      int block_n, int split_k, const GemmEpilogue& epi, cudaStream_t stream, const void* pf_ptr = nullptr,
-                     unsigned long long pf_bytes = 0, bool pdl = false, float* zero_ptr = nullptr, unsigned long long zero_f4 = 0);
+                     unsigned long long pf_bytes = 0, bool pdl = false, float* zero_ptr = nullptr, unsigned long long zero_f4 = 0,
+                     unsigned long long* trace = nullptr);
 // Decode QKV / gate|up GEMM with RMSNorm folded in (XNORM kernel): tmX is an fp32 map over the residual stream (make_tmap_f32).
 // `extra` carries norm_w (+ ss_out) for xmode 1, ss_in / ss_dim / eps / up_off for xmode 2 (XSILU: tmX maps the gate|up
 // accumulator), zero_ptr / zero_f4 for either, and the L2 prefetch region.

@@ -77,9 +77,12 @@ struct ctp_gpt {
     bool fuse_norm = true;     // RMSNorm folded into the QKV / gate|up GEMMs (XNORM kernel); CTP_FUSE_NORM=0: stand-alone norm kernels
     CUtensorMap x_map{};       // fp32 map over the first 64 rows of the residual stream
     CUtensorMap gu_map{};      // fp32 map over the decode gate|up accumulator
-    float* dec_gu = nullptr;   // decode only, one re-armable block: ss2[64] (sum(x^2) seen by the gate|up GEMM) | gate|up accumulator [64][2I]
-    float* ss2() const { return dec_gu; }
-    float* gu_acc() const { return dec_gu + 64; }
+    // decode only, re-armable scratch: ss1[64] | ss2[64] | gate|up accumulator [64][2I].  ss1 / ss2 = sum(x^2) per token row as seen by
+    // the QKV / gate|up GEMM (input / post-attention RMSNorm folded in); ss1 is re-armed by o_proj, ss2 and gate|up by the next QKV GEMM
+    float* dec_gu = nullptr;
+    float* ss1() const { return dec_gu; }
+    float* ss2() const { return dec_gu + 64; }
+    float* gu_acc() const { return dec_gu + 128; }
     bool attn_tma = true;      // TMA-staged decode attention (CTP_ATTN=ldg selects the per-thread-load kernel)
     bool use_cluster = false;  // CTP_DECODE_GEMM=cluster: split-K reduced through DSMEM inside a thread-block cluster, 5 kernels per layer.
                                // Parity-green but slower than the RED split-K path on B200 today (profiles/README.md), so opt-in.
@@ -216,8 +219,8 @@ extern "C" ctp_status ctp_gpt_create(ctp_gpt** out, const ctp_gpt_cfg* cfg) {
         if (const char* e = getenv("CTP_DECODE_GEMM")) h->use_cluster = (strcmp(e, "cluster") == 0);
         if (const char* e = getenv("CTP_ATTN")) h->attn_tma = (strcmp(e, "ldg") != 0);
         if (const char* e = getenv("CTP_FUSE_NORM")) h->fuse_norm = atoi(e) != 0;
-        CK(cudaMalloc(&h->dec_gu, sizeof(float) * (64 + (size_t)64 * 2 * cfg->inter)));
-        CK(cudaMemset(h->dec_gu, 0, sizeof(float) * (64 + (size_t)64 * 2 * cfg->inter)));
+        CK(cudaMalloc(&h->dec_gu, sizeof(float) * (128 + (size_t)64 * 2 * cfg->inter)));
+        CK(cudaMemset(h->dec_gu, 0, sizeof(float) * (128 + (size_t)64 * 2 * cfg->inter)));
 
         CK(cudaFuncSetAttribute(k_attn_decode_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
         if (const char* e = getenv("CTP_KV_PREFETCH")) h->kv_prefetch = atoi(e) != 0;
@@ -552,7 +555,7 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
     // (in-kernel token operands, gemm.cuh XNORM / XSILU): FIVE kernels per layer instead of eight.
     const bool fuse = h->fuse_norm && h->attn_tma && B <= 32;
     float* gu = fuse ? h->gu_acc() : h->acc_gu;
-    const unsigned long long rearm_f4 = (unsigned long long)(64 + (size_t)B * 2 * I) / 4;   // ss2 | gate|up rows of the live batch
+    const unsigned long long rearm_f4 = (unsigned long long)(64 + (size_t)B * 2 * I) / 4;   // ss2 | gate|up rows of the live batch (from ss2())
     for (int l = 0; l < (cluster ? 0 : c.n_layers); ++l) {
         const bool f1 = fuse && l > 0;   // layer 0 keeps the norm kernel: it is also the code-embedding front end
         if (!f1) {
@@ -570,11 +573,12 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
             const size_t pfb = sizeof(__half) * (size_t)H * H;
             if (f1) {
                 GemmShape ex{};
-                ex.pf_ptr = pf; ex.pf_bytes = pfb; ex.norm_w = h->w.ln1 + (size_t)l * H; ex.zero_ptr = h->dec_gu; ex.zero_f4 = rearm_f4;
+                ex.pf_ptr = pf; ex.pf_bytes = pfb; ex.norm_w = h->w.ln1 + (size_t)l * H; ex.zero_ptr = h->ss2(); ex.zero_f4 = rearm_f4;
+                ex.ss_out = h->ss1(); ex.trace = h->trace_rec();
                 st = gemm_launch_x(1, h->lmaps[l].wqkv, h->x_map, 3 * H, B, H, split_for(H / 64, 3 * H / GEMM_BM), e, ex, s, pdl);
             } else {
                 st = gemm_launch_maps(h->lmaps[l].wqkv, am.xn, 3 * H, B, H, bn, split_for(H / 64, 3 * H / GEMM_BM), e, s, pf, pfb, pdl,
-                                      fuse ? h->dec_gu : nullptr, fuse ? rearm_f4 : 0);
+                                      fuse ? h->ss2() : nullptr, fuse ? rearm_f4 : 0, h->trace_rec());
             }
             if (st) return st;
         }
@@ -582,14 +586,15 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
         aa.qkv = h->acc_qkv; aa.kcache = h->kplane(l); aa.vcache = h->vplane(l); aa.out = h->attn; aa.part = h->attn_part;
         aa.counters = h->attn_cnt; aa.pad_len = h->pad_len; aa.st = h->st; aa.inv_freq = h->inv_freq;
         aa.H = H; aa.nH = c.n_heads; aa.max_seq = c.max_seq; aa.rearm = 1; aa.eps = c.rms_eps;
-        if (f1) aa.xrow = h->x;   // input_layernorm's row factor (llama.py:718), deferred from the QKV GEMM
+        if (f1) { aa.ss = h->ss1(); aa.ss_parts = 1; aa.ss_stride = 64; }   // input_layernorm's row factor (llama.py:718), deferred from the QKV GEMM
         aa.trace = h->trace_rec();
         if (h->attn_tma) CTP_LAUNCH(k_attn_decode_tma, dim3(c.n_heads, B, nsplit), dim3(AT_THREADS), AT_SMEM, aa);
         else CTP_LAUNCH(k_attn_decode, dim3(c.n_heads, B, nsplit), dim3(128), 0, aa);
         {   // o_proj accumulated straight into the residual stream (llama.py:663-666,737)
             GemmEpilogue e = epi_swap_atomic(h->x, H, B, H);
             if ((st = gemm_launch_maps(h->lmaps[l].wo, am.attn, H, B, H, bn, split_for(H / 64, (H + GEMM_BM - 1) / GEMM_BM), e, s,
-                                       (const __half*)h->w.wgu + (size_t)l * 2 * I * H, sizeof(__half) * (size_t)2 * I * H, pdl))) return st;
+                                       (const __half*)h->w.wgu + (size_t)l * 2 * I * H, sizeof(__half) * (size_t)2 * I * H, pdl,
+                                       fuse ? h->ss1() : nullptr, fuse ? 16 : 0, h->trace_rec()))) return st;   // re-arms ss1 (read by this layer's attention)
         }
         if (!fuse) {
             NormArgs nb{};
@@ -604,7 +609,7 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
             const size_t pfb = sizeof(__half) * (size_t)H * I;
             if (fuse) {
                 GemmShape ex{};
-                ex.pf_ptr = pf; ex.pf_bytes = pfb; ex.norm_w = h->w.ln2 + (size_t)l * H; ex.ss_out = h->ss2();
+                ex.pf_ptr = pf; ex.pf_bytes = pfb; ex.norm_w = h->w.ln2 + (size_t)l * H; ex.ss_out = h->ss2(); ex.trace = h->trace_rec();
                 st = gemm_launch_x(1, h->lmaps[l].wgu, h->x_map, 2 * I, B, H, split_for(H / 64, 2 * I / GEMM_BM), e, ex, s, pdl);
             } else {
                 st = gemm_launch_maps(h->lmaps[l].wgu, am.xn, 2 * I, B, H, bn, split_for(H / 64, 2 * I / GEMM_BM), e, s, pf, pfb, pdl);
@@ -622,6 +627,7 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
             if (fuse) {
                 GemmShape ex{};
                 ex.pf_ptr = nxt; ex.pf_bytes = nxt_bytes; ex.ss_in = h->ss2(); ex.ss_dim = (float)H; ex.eps = c.rms_eps; ex.up_off = I;
+                ex.trace = h->trace_rec();
                 st = gemm_launch_x(2, h->lmaps[l].wdown, h->gu_map, H, B, I, split_for(I / 64, (H + GEMM_BM - 1) / GEMM_BM), e, ex, s, pdl);
             } else {
                 st = gemm_launch_maps(h->lmaps[l].wdown, am.hmid, H, B, I, bn, split_for(I / 64, (H + GEMM_BM - 1) / GEMM_BM), e, s, nxt, nxt_bytes, pdl);
@@ -759,7 +765,7 @@ extern "C" ctp_status ctp_gpt_prefill(ctp_gpt* h, int32_t B, int32_t L0, const f
     // the decode path accumulates into acc_qkv / acc_gu with fp32 atomics and their readers re-arm them: start from zero
     CTP_CUDA_OK(cudaMemsetAsync(h->acc_qkv, 0, sizeof(float) * (size_t)c.max_batch * 3 * H, s));
     CTP_CUDA_OK(cudaMemsetAsync(h->acc_gu, 0, sizeof(float) * (size_t)c.max_batch * 2 * I, s));
-    CTP_CUDA_OK(cudaMemsetAsync(h->dec_gu, 0, sizeof(float) * (64 + (size_t)64 * 2 * I), s));
+    CTP_CUDA_OK(cudaMemsetAsync(h->dec_gu, 0, sizeof(float) * (128 + (size_t)64 * 2 * I), s));
     h->B = B; h->cur_len = L0; h->step = 0; h->max_new = bufs->max_new; h->have_bufs = true;
     return CTP_OK;
 }

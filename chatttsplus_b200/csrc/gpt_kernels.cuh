@@ -180,7 +180,6 @@ struct AttnDecArgs {
     // rsqrt(sum(x^2)/H + eps) (llama.py:85) is applied here; sum(x^2) arrives as ss_parts partial sums per row
     const float* ss;        // [ss_parts][ss_stride] or null (rows already normalised)
     int ss_parts, ss_stride;
-    const float* xrow;      // [B][H] or null: the residual stream the QKV GEMM contracted un-normalised; the row factor is recomputed here
     float eps;
     int rearm;              // 1: qkv is a split-K RED accumulator that its last reader zeroes; 0: plain final values
     unsigned long long* trace;
@@ -439,17 +438,11 @@ __global__ void __launch_bounds__(AT_THREADS) k_attn_decode_tma(AttnDecArgs a) {
 
     // ---- consumer warps (128 threads) ----
     float* qp = a.qkv + (long long)b * 3 * a.H + h * HEAD_DIM;
-    float rf = 1.f;   // deferred RMSNorm row factor (llama.py:85)
-    if (a.xrow) {     // sum(x[b]^2) over the 3 KB row: loads overlap the q/k/v loads below
-        const float* xr = a.xrow + (long long)b * a.H;
-        float ssq = 0.f;
-        for (int c = tid; c < a.H; c += 128) { const float v = xr[c]; ssq += v * v; }
-        ssq = warp_sum(ssq);
-        if (lane == 0) s_m[warp] = ssq;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        rf = rsqrtf((s_m[0] + s_m[1] + s_m[2] + s_m[3]) / (float)a.H + a.eps);
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // s_m is reused by the group merge
-    }
+    // every load of the prologue is issued before the first use: one L2 round trip for q/k/v, the row factor and the length
+    float raw[4] = {0.f, 0.f, 0.f, 0.f};
+    if (tid < 32) { raw[0] = qp[tid]; raw[1] = qp[tid + 32]; raw[2] = qp[a.H + tid]; raw[3] = qp[a.H + tid + 32]; }
+    else if (tid < 96) raw[0] = qp[2 * a.H + tid - 32];
+    float rf = 1.f;   // deferred RMSNorm row factor (llama.py:85): the QKV GEMM contracted x*w, sum(x^2) arrives in ss
     if (a.ss) {
         float part[8];
 #pragma unroll
@@ -464,15 +457,14 @@ __global__ void __launch_bounds__(AT_THREADS) k_attn_decode_tma(AttnDecArgs a) {
         const float ang = pos * a.inv_freq[tid];
         float sn, cs;
         sincosf(ang, &sn, &cs);
-        const float q1 = qp[tid] * rf, q2 = qp[tid + 32] * rf;
-        const float k1 = qp[a.H + tid] * rf, k2 = qp[a.H + tid + 32] * rf;
+        const float q1 = raw[0] * rf, q2 = raw[1] * rf;
+        const float k1 = raw[2] * rf, k2 = raw[3] * rf;
         sq[tid] = (q1 * cs - q2 * sn) * 0.125f;  // 1/sqrt(64) folded into q
         sq[tid + 32] = (q2 * cs + q1 * sn) * 0.125f;
         sk_new[tid] = __float2half_rn(k1 * cs - k2 * sn);
         sk_new[tid + 32] = __float2half_rn(k2 * cs + k1 * sn);
     } else if (tid < 96) {
-        const int d = tid - 32;
-        sv_new[d] = __float2half_rn(qp[2 * a.H + d] * rf);
+        sv_new[tid - 32] = __float2half_rn(raw[0] * rf);
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
     if (tid == 0) trace_mark(a.trace, 4);
@@ -809,6 +801,10 @@ __device__ __forceinline__ void sample_block(const SampleArgs& a, const int b, c
         rep_apply = lane < w && first && my >= 0 && my < V;
         if (rep_apply) alpha = powf(cfg.rep_penalty, (float)mult);
     }
+    // bookkeeping state of the previous step (written by the previous sampler launch)
+    int max_new_st = 0, end_prev = 0;
+    bool fin_prev = false;
+    if (a.st) { max_new_st = a.st->max_new; fin_prev = a.st->finish[b] != 0; end_prev = a.st->end_idx[b]; }
     if (PDL_INSIDE) {
         pdl_wait();
         if (threadIdx.x == 0) trace_mark(a.trace, 1);
@@ -951,22 +947,19 @@ __device__ __forceinline__ void sample_block(const SampleArgs& a, const int b, c
             GenState* st = a.st;
             bool eos = false;
             for (int q = 0; q < a.num_vq; ++q) eos |= (s_choice[q] == cfg.eos);
-            if (step < st->max_new) {   // text mode: the sampled id goes to every VQ column (gpt.py:489-494)
+            if (step < max_new_st) {   // text mode: the sampled id goes to every VQ column (gpt.py:489-494)
                 for (int q = 0; q < a.ids_cols; ++q)
-                    st->ids_buf[((long long)b * st->max_new + step) * a.ids_cols + q] = s_choice[a.num_vq == 1 ? 0 : q];
+                    st->ids_buf[((long long)b * max_new_st + step) * a.ids_cols + q] = s_choice[a.num_vq == 1 ? 0 : q];
             }
-            const bool fin = (st->finish[b] != 0) || eos;   // gpt.py:486-487
+            const bool fin = fin_prev || eos;                // gpt.py:486-487
             st->finish[b] = fin ? 1 : 0;
-            if (!fin) st->end_idx[b] += 1;                   // gpt.py:530-531
-            __threadfence();
-            const int t = atomicAdd(&st->ticket, 1);
-            if (t == n_blocks - 1) {                   // last block: global bookkeeping
+            if (!fin) st->end_idx[b] = end_prev + 1;         // gpt.py:530-531
+            // one ticket per block; the high half counts the rows that have finished, so the last block to arrive knows
+            // whether every sequence is done without re-reading the flags
+            const int t = atomicAdd(&st->ticket, 1 + (fin ? 0x10000 : 0));
+            if ((t & 0xffff) == n_blocks - 1) {              // last block: global bookkeeping
                 st->ticket = 0;
-                int all = 1;
-                __threadfence();
-                const volatile unsigned char* fin_v = st->finish;
-                for (int i = 0; i < n_blocks; ++i) all &= (fin_v[a.b0 + i] != 0);
-                st->all_done = all;
+                st->all_done = ((t >> 16) + (fin ? 1 : 0)) == n_blocks;
                 st->step = step + 1;
                 if (FUSED || a.advance_len) { st->cur_len += 1; }
             }
