@@ -363,6 +363,8 @@ __global__ void __launch_bounds__(128) k_attn_decode(AttnDecArgs a) {
 //   * pre-wait loads use a possibly one-step-old cur_len as a hint and only touch whole tiles below it (slots written by
 //     earlier steps / the prefill, complete long ago); the true length is read after the wait.
 //   * grid (nH, B, nsplit), 160 threads: warps 0-3 consume (16 groups x 8 lanes, online softmax per group), warp 4 produces.
+//   * KV splits are INTERLEAVED by tile (split sp owns tiles sp, sp + nsplit, ... counted from the first unmasked slot), so
+//     which tiles a CTA owns does not depend on the current length and the pre-wait pass works for any nsplit.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int AT_TILE = 64, AT_STAGES = 4, AT_THREADS = 160;
 constexpr int AT_HALF_BYTES = AT_TILE * HEAD_DIM * 2;       // 8 KB: one K (or V) tile
@@ -397,34 +399,35 @@ __global__ void __launch_bounds__(AT_THREADS) k_attn_decode_tma(AttnDecArgs a) {
     }
     __syncthreads();
     int pre = 0;
-    if (warp == 4 && lane == 0 && nsplit == 1) {
+    if (warp == 4 && lane == 0) {
         const int hint = *reinterpret_cast<const volatile int*>(&a.st->cur_len);   // <= the true length (see header)
-        int n_full = (hint - pad) / AT_TILE;
-        pre = n_full < 0 ? 0 : (n_full > AT_STAGES ? AT_STAGES : n_full);
+        const int n_full = (hint - pad) / AT_TILE;                                  // whole tiles below the hint
+        const int mine = n_full > sp ? (n_full - sp + nsplit - 1) / nsplit : 0;     // ... that this split owns
+        pre = mine > AT_STAGES ? AT_STAGES : mine;
         for (int i = 0; i < pre; ++i) {
             uint8_t* st = ring + i * AT_STAGE_BYTES;
+            const long long p0 = pad + (long long)(sp + i * nsplit) * AT_TILE;
             mbar_expect_tx(&full_bar[i], AT_STAGE_BYTES);
-            bulk_load_1d(st, kc + (long long)(pad + i * AT_TILE) * HEAD_DIM, AT_HALF_BYTES, &full_bar[i]);
-            bulk_load_1d(st + AT_HALF_BYTES, vc + (long long)(pad + i * AT_TILE) * HEAD_DIM, AT_HALF_BYTES, &full_bar[i]);
+            bulk_load_1d(st, kc + p0 * HEAD_DIM, AT_HALF_BYTES, &full_bar[i]);
+            bulk_load_1d(st + AT_HALF_BYTES, vc + p0 * HEAD_DIM, AT_HALF_BYTES, &full_bar[i]);
         }
         s_pre = pre;
     }
     pdl_wait();
     if (tid == 0) trace_mark(a.trace, 1);
     const int cur = a.st->cur_len;  // new token's slot
-    // cached slots this split covers: [j0, j1) within [pad, cur); the new token (slot cur) is taken from shared memory by the last split
-    const int n = cur - pad;
-    const int j0 = pad + (int)(((long long)n * sp) / nsplit);
-    const int j1 = pad + (int)(((long long)n * (sp + 1)) / nsplit);
-    int n_tiles = (j1 - j0 + AT_TILE - 1) / AT_TILE;
+    // cached slots [pad, cur) in tiles of 64 counted from pad; this split owns tiles sp, sp + nsplit, ...; the new token (slot cur)
+    // is taken from shared memory by the last split
+    const int nt_all = (cur - pad + AT_TILE - 1) / AT_TILE;
+    int n_tiles = nt_all > sp ? (nt_all - sp + nsplit - 1) / nsplit : 0;
 
     if (warp == 4) {
         if (lane == 0) {
             for (int i = pre; i < n_tiles; ++i) {
                 const int s = i % AT_STAGES;
                 if (i >= AT_STAGES) mbar_wait(&empty_bar[s], ((i / AT_STAGES) & 1) ^ 1);
-                const int p0 = j0 + i * AT_TILE;
-                const int cnt = min(AT_TILE, j1 - p0);
+                const int p0 = pad + (sp + i * nsplit) * AT_TILE;
+                const int cnt = min(AT_TILE, cur - p0);
                 const uint32_t bytes = (uint32_t)cnt * HEAD_DIM * 2;
                 uint8_t* st = ring + s * AT_STAGE_BYTES;
                 mbar_expect_tx(&full_bar[s], 2 * bytes);
@@ -487,7 +490,7 @@ __global__ void __launch_bounds__(AT_THREADS) k_attn_decode_tma(AttnDecArgs a) {
     for (int it = 0; it < n_tiles; ++it) {
         const int s = it % AT_STAGES;
         mbar_wait(&full_bar[s], (it / AT_STAGES) & 1);
-        const int cnt = min(AT_TILE, j1 - (j0 + it * AT_TILE));   // may be <= 0 only in the defensive case above
+        const int cnt = min(AT_TILE, cur - (pad + (sp + it * nsplit) * AT_TILE));   // may be <= 0 only in the defensive case above
         const uint8_t* kt = ring + s * AT_STAGE_BYTES;
         const uint8_t* vt = kt + AT_HALF_BYTES;
         uint4 kr[4], vr[4];

@@ -105,6 +105,12 @@ def test_trunk_long_context_wraps_kv_ring():
     _teacher_forced(cfg, B=26, L0=330, steps=4, seed=35, pads=[0, 5, 64, 129, 200, 329] + [0] * 20)
 
 
+def test_trunk_long_context_two_kv_splits():
+    """Context > 1024 slots splits every (b, head) KV stream over two CTAs (interleaved 64-slot tiles, ring wraps twice per CTA)."""
+    cfg = synth.GPTConfig(num_hidden_layers=2, num_text_tokens=256)
+    _teacher_forced(cfg, B=25, L0=1040, steps=3, seed=36, pads=[0, 700, 1039] + [0] * 22)
+
+
 @pytest.mark.parametrize("env", [{"CTP_ATTN": "ldg"}, {"CTP_DECODE_GEMM": "cluster"}, {"CTP_DECODE_GEMM": "cluster", "CTP_S_DN": "16", "CTP_S_GU": "2"},
                                  {"CTP_PDL": "0"}])
 def test_trunk_opt_in_variants(env, monkeypatch):
