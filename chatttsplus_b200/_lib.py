@@ -45,7 +45,7 @@ class GenBuffers(C.Structure):
 class VocCfg(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
                 ("dvae_idim", "dvae_bn", "dvae_hidden", "dvae_layers", "dvae_odim", "dvae_dilation", "n_mels", "use_vq",
-                 "voc_dim", "voc_inter", "voc_layers", "n_fft", "hop", "max_frames")]
+                 "voc_dim", "voc_inter", "voc_layers", "n_fft", "hop", "max_frames", "encoder")]
 
 
 class ConvNextW(C.Structure):
@@ -58,7 +58,9 @@ class VocWeights(C.Structure):
                 ("out_conv_w", C.c_void_p), ("coef", C.c_void_p), ("vq_proj_w", C.c_void_p), ("vq_proj_b", C.c_void_p),
                 ("embed_w", C.c_void_p), ("embed_b", C.c_void_p), ("norm_w", C.c_void_p), ("norm_b", C.c_void_p),
                 ("voc_blocks", C.POINTER(ConvNextW)), ("final_ln_w", C.c_void_p), ("final_ln_b", C.c_void_p),
-                ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("window", C.c_void_p)]
+                ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("window", C.c_void_p),
+                ("ds0_w", C.c_void_p), ("ds0_b", C.c_void_p), ("ds2_w", C.c_void_p), ("ds2_b", C.c_void_p),
+                ("mel_fb", C.c_void_p), ("vq_in_w", C.c_void_p), ("vq_in_b", C.c_void_p)]
 
 
 # every symbol include/ctp.h declares: (restype, argtypes)
@@ -87,6 +89,7 @@ SYMBOLS = {
     "ctp_voc_bind_weights": (C.c_int, [_VP, C.POINTER(VocWeights)]),
     "ctp_voc_decode": (C.c_int, [_VP, _I32, C.POINTER(_I32), _VP, _VP, C.POINTER(_I64), _VP, _VP]),
     "ctp_voc_decode_mel": (C.c_int, [_VP, _I32, C.POINTER(_I32), _VP, _VP, C.POINTER(_I64), _VP]),
+    "ctp_voc_encode": (C.c_int, [_VP, _I32, _VP, _VP, _VP, C.POINTER(_I32), _VP]),
     "ctp_gemm_f16": (C.c_int, [_I32, _I32, _I32, _VP, _I64, _VP, _I64, _VP, _I64, _VP, _I32, _I32, _I32, _VP]),
 }
 

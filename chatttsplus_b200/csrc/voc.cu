@@ -239,6 +239,95 @@ __global__ void k_overlap_add(const float* __restrict__ frames, float* __restric
     wav[wav_off[u] + n] = acc / env;
 }
 
+// ---- prompt encoder front end: MelSpectrogramFeatures (dvae.py:171-199 = torchaudio MelSpectrogram(power=1, center=True)) --
+// One CTA (256 threads) per frame: 1024 samples around f*hop with reflect padding, times the periodic Hann window, forward
+// real FFT in shared memory (radix-2, conjugated twiddles of the ISTFT kernel), |X[k]| for k <= 512, mel = fb^T |X|,
+// y = log(max(mel, 1e-5)) / coef  (dvae.py:198,266) stored as the fp16 operand row of downsample_conv.0.
+__global__ void __launch_bounds__(256) k_mel_frame(const float* __restrict__ audio, int n_samples, __half* __restrict__ mel16 /* row of frame 0 */,
+                                                    const float* __restrict__ window, const float2* __restrict__ twiddle,
+                                                    const float* __restrict__ fb /*[513][n_mels]*/, const float* __restrict__ coef,
+                                                    int n_mels, int hop) {
+    constexpr int N = 1024, NB = 513;
+    const int f = blockIdx.x;
+    __shared__ float2 a[N];
+    __shared__ float mag[NB];
+    for (int j = threadIdx.x; j < N; j += 256) {
+        long long n = (long long)f * hop - N / 2 + j;
+        if (n < 0) n = -n;                                   // reflect (no edge repeat), torch.stft(center=True, pad_mode="reflect")
+        if (n >= n_samples) n = 2LL * (n_samples - 1) - n;
+        const float v = audio[n] * window[j];
+        const int rev = __brev((unsigned)j) >> 22;
+        a[rev] = make_float2(v, 0.f);
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int s = 1; s <= 10; ++s) {
+        const int half = 1 << (s - 1);
+        for (int j = threadIdx.x; j < N / 2; j += 256) {
+            const int grp = j >> (s - 1), pos = j & (half - 1);
+            const int i0 = (grp << s) + pos, i1 = i0 + half;
+            const float2 w0 = twiddle[pos << (10 - s)];
+            const float2 w = make_float2(w0.x, -w0.y);       // forward transform: exp(-2 pi i k / N)
+            const float2 x1 = a[i1], x0 = a[i0];
+            const float2 t = make_float2(w.x * x1.x - w.y * x1.y, w.x * x1.y + w.y * x1.x);
+            a[i1] = make_float2(x0.x - t.x, x0.y - t.y);
+            a[i0] = make_float2(x0.x + t.x, x0.y + t.y);
+        }
+        __syncthreads();
+    }
+    for (int k = threadIdx.x; k < NB; k += 256) mag[k] = sqrtf(a[k].x * a[k].x + a[k].y * a[k].y);
+    __syncthreads();
+    __half* o = mel16 + (long long)f * MEL_PAD;
+    for (int m = threadIdx.x; m < MEL_PAD; m += 256) {
+        float y = 0.f;
+        if (m < n_mels) {
+            float acc = 0.f;
+            for (int k = 0; k < NB; ++k) acc += fb[k * n_mels + m] * mag[k];
+            y = __logf(fmaxf(acc, 1e-5f)) / coef[m];
+        }
+        o[m] = __float2half_rn(y);
+    }
+}
+
+// ---- GFSQ quantiser (dvae.py:98-126 -> vector_quantize_pytorch GroupedResidualFSQ.forward, levels [5,5,5,5], G groups, R = 2) ----
+// One CTA per code frame, warp g handles group g: z = project_in(x_g) (4 dots of odim/G), residual = bound(z) = tanh(z) * 2.002,
+// then per residual level r: q = rint(tanh(residual / s_r) * 2.002) / 2, digit_j = 2 q_j + 2, index = sum digit_j 5^j,
+// residual -= q s_r with s_r = 4^-r.
+__global__ void k_gfsq_quantize(const float* __restrict__ x /*[T][odim]*/, int odim, int G, const float* __restrict__ w /*[G][4][odim/G]*/,
+                                const float* __restrict__ b /*[G][4]*/, int* __restrict__ ids /*[T][G*2]*/) {
+    const int t = blockIdx.x, g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (g >= G) return;
+    const int gd = odim / G;
+    const float* xr = x + (long long)t * odim + g * gd;
+    float z[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float* wr = w + ((long long)g * 4 + j) * gd;
+        float acc = 0.f;
+        for (int c = lane; c < gd; c += 32) acc += wr[c] * xr[c];
+        z[j] = warp_sum(acc) + b[g * 4 + j];
+    }
+    if (lane == 0) {
+        const float half_l = 4.0f * (1.0f + 1e-3f) / 2.0f;   // (levels - 1) * (1 + eps) / 2
+        float res[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) res[j] = tanhf(z[j]) * half_l;
+        float scale = 1.0f;
+        for (int r = 0; r < 2; ++r) {
+            int idx = 0, basis = 1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float q = rintf(tanhf(res[j] / scale) * half_l) * 0.5f;   // torch.round = round-half-to-even
+                idx += (int)rintf(q * 2.0f + 2.0f) * basis;
+                basis *= 5;
+                res[j] -= q * scale;
+            }
+            ids[(long long)t * (G * 2) + g * 2 + r] = idx;
+            scale *= 0.25f;
+        }
+    }
+}
+
 struct ConvNextDev {
     ctp_convnext_w w;
 };
@@ -249,7 +338,7 @@ struct ctp_voc {
     ctp_voc_cfg cfg{};
     ctp_voc_weights w{};
     std::vector<ctp_convnext_w> dvae_blocks, voc_blocks;
-    bool bound = false, has_dvae = false, has_vocos = false;
+    bool bound = false, has_dvae = false, has_vocos = false, has_encoder = false;
     long long cap_rows = 0;  // capacity in rows (excluding the +-GAP guard rows)
     // activation buffers; every pointer is offset by GAP rows so that rows [-GAP, cap+GAP) are addressable
     __half* x0 = nullptr;     // [rows][idim]
@@ -301,7 +390,8 @@ extern "C" ctp_status ctp_voc_create(ctp_voc** out, const ctp_voc_cfg* c) {
     const long long R = c->max_frames;
     h->cap_rows = R;
     const int cw = std::max(c->dvae_hidden, c->voc_dim);
-    const int iw = std::max(4 * c->dvae_hidden, c->voc_inter);
+    const int iw = std::max(std::max(4 * c->dvae_hidden, c->voc_inter), c->encoder ? c->dvae_idim : 0);
+    CTP_REQUIRE(!c->encoder || (c->dvae_odim <= c->n_fft + 2 && c->dvae_odim % 64 == 0), "encoder odim must be a multiple of 64 and <= n_fft + 2");
     int st = 0;
     if (!st) st = voc_alloc(h, &h->x0, R, c->dvae_idim);
     if (!st) st = voc_alloc(h, &h->c1, R, c->dvae_bn);
@@ -344,12 +434,16 @@ extern "C" ctp_status ctp_voc_bind_weights(ctp_voc* h, const ctp_voc_weights* w)
     CTP_REQUIRE(h && w, "voc_bind: null argument");
     const bool dv = w->conv_in0_w && w->conv_in2_w && w->dvae_blocks && w->conv_out_w && w->out_conv_w && w->coef;
     const bool vc = w->embed_w && w->voc_blocks && w->head_w && w->window && w->norm_w && w->final_ln_w;
-    CTP_REQUIRE(dv || vc, "voc_bind: neither a complete DVAE nor a complete Vocos weight set was given");
+    const bool en = h->cfg.encoder && w->conv_in0_w && w->conv_in2_w && w->dvae_blocks && w->conv_out_w && w->coef && w->ds0_w && w->ds0_b &&
+                    w->ds2_w && w->ds2_b && w->mel_fb && w->vq_in_w && w->vq_in_b && w->window;
+    CTP_REQUIRE(dv || vc || en, "voc_bind: neither a complete DVAE, Vocos nor prompt-encoder weight set was given");
+    CTP_REQUIRE(!h->cfg.encoder || en, "voc_bind: encoder handle needs encoder.*, downsample_conv.*, mel filter bank, window, coef and GFSQ project_in");
     CTP_REQUIRE(!dv || !h->cfg.use_vq || (w->vq_proj_w && w->vq_proj_b), "voc_bind: GFSQ projection missing");
     h->w = *w;
-    if (dv) { h->dvae_blocks.assign(w->dvae_blocks, w->dvae_blocks + h->cfg.dvae_layers); h->w.dvae_blocks = h->dvae_blocks.data(); }
+    if (dv || en) { h->dvae_blocks.assign(w->dvae_blocks, w->dvae_blocks + h->cfg.dvae_layers); h->w.dvae_blocks = h->dvae_blocks.data(); }
+    h->has_encoder = en;
     if (vc) { h->voc_blocks.assign(w->voc_blocks, w->voc_blocks + h->cfg.voc_layers); h->w.voc_blocks = h->voc_blocks.data(); }
-    h->has_dvae = dv; h->has_vocos = vc;
+    h->has_dvae = dv && !h->cfg.encoder; h->has_vocos = vc;
     h->bound = true;
     return CTP_OK;
 }
@@ -424,6 +518,8 @@ static int voc_layout(ctp_voc* h, int n_utt, const std::vector<int>& mel_frames,
     return CTP_OK;
 }
 
+static int voc_run_stack(ctp_voc* h, int rows, cudaStream_t s);
+
 // DVAE decode (dvae.py:272-291): src -> mel32 rows
 static int voc_run_dvae(ctp_voc* h, const GroupLayout& L, const void* src, cudaStream_t s) {
     const ctp_voc_cfg& c = h->cfg;
@@ -435,6 +531,24 @@ static int voc_run_dvae(ctp_voc* h, const GroupLayout& L, const void* src, cudaS
         k_voc_input_hidden<<<rows, 128, 0, s>>>((const float*)src, h->x0, h->row_src, c.dvae_idim);
     }
     VLAUNCH_OK();
+    if ((st = voc_run_stack(h, rows, s))) return st;
+    {   // conv_out: 1x1, no bias (dvae.py:159,167)
+        GemmEpilogue e{};
+        e.out = h->o1; e.ldo = c.dvae_odim; e.out_f16 = 1; e.row_valid = h->valid;
+        if ((st = voc_gemm(h->y16, c.dvae_hidden, 1, rows, h->w.conv_out_w, c.dvae_odim, e, s))) return st;
+    }
+    {   // out_conv: Conv1d(dim -> 100, k3, p1, no bias), then * coef (dvae.py:285,291)
+        GemmEpilogue e{};
+        e.out = h->mel32; e.ldo = c.n_mels; e.gamma = h->w.coef; e.row_valid = h->valid;
+        if ((st = voc_gemm(h->o1, c.dvae_odim, 3, rows, h->w.out_conv_w, c.n_mels, e, s))) return st;
+    }
+    return CTP_OK;
+}
+
+// DVAEDecoder.forward up to (not including) conv_out (dvae.py:161-166): x0 rows -> y16 rows (fp16 copy of the residual stream)
+static int voc_run_stack(ctp_voc* h, int rows, cudaStream_t s) {
+    const ctp_voc_cfg& c = h->cfg;
+    int st;
     {   // conv_in[0]: Conv1d(idim -> bn, k3, p1) + GELU   (dvae.py:145-147)
         GemmEpilogue e{};
         e.out = h->c1; e.ldo = c.dvae_bn; e.out_f16 = 1; e.bias = h->w.conv_in0_b; e.act_gelu = 1; e.row_valid = h->valid;
@@ -452,16 +566,6 @@ static int voc_run_dvae(ctp_voc* h, const GroupLayout& L, const void* src, cudaS
     }
     k_cvt_rows<<<rows, 128, 0, s>>>(h->xres, h->y16, h->valid, c.dvae_hidden, c.dvae_hidden);
     VLAUNCH_OK();
-    {   // conv_out: 1x1, no bias (dvae.py:159,167)
-        GemmEpilogue e{};
-        e.out = h->o1; e.ldo = c.dvae_odim; e.out_f16 = 1; e.row_valid = h->valid;
-        if ((st = voc_gemm(h->y16, c.dvae_hidden, 1, rows, h->w.conv_out_w, c.dvae_odim, e, s))) return st;
-    }
-    {   // out_conv: Conv1d(dim -> 100, k3, p1, no bias), then * coef (dvae.py:285,291)
-        GemmEpilogue e{};
-        e.out = h->mel32; e.ldo = c.n_mels; e.gamma = h->w.coef; e.row_valid = h->valid;
-        if ((st = voc_gemm(h->o1, c.dvae_odim, 3, rows, h->w.out_conv_w, c.n_mels, e, s))) return st;
-    }
     return CTP_OK;
 }
 
@@ -555,6 +659,60 @@ extern "C" ctp_status ctp_voc_decode(ctp_voc* h, int32_t n_utt, const int32_t* l
         if (wav_out) return voc_run_vocos(h, L, j - i, wav_out, s);
         return CTP_OK;
     });
+}
+
+extern "C" ctp_status ctp_voc_encode(ctp_voc* h, int32_t n_samples, const float* audio, int32_t* ids_out, float* feat_out,
+                                     int32_t* n_frames_host, ctp_stream stream) {
+    CTP_REQUIRE(h && h->bound && h->has_encoder, "voc_encode: no prompt-encoder weights bound (create the handle with encoder = 1)");
+    CTP_REQUIRE(audio && ids_out, "voc_encode: null buffer");
+    const ctp_voc_cfg& c = h->cfg;
+    CTP_REQUIRE(n_samples > c.n_fft / 2, "voc_encode: reflect padding needs more than %d samples (got %d)", c.n_fft / 2, n_samples);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int T = n_samples / c.hop + 1;          // torch.stft(center=True)
+    const int T2 = (T - 2) / 2 + 1;               // Conv1d(k4, stride 2, p1), dvae.py:229
+    CTP_REQUIRE(T >= 2, "voc_encode: audio too short");
+    CTP_REQUIRE((long long)T + 2 * GAP <= h->cap_rows, "voc_encode: %d mel frames exceed the workspace (%lld rows)", T, h->cap_rows);
+    const int dim = c.dvae_idim;
+    int st;
+    GroupLayout LA;
+    if ((st = voc_layout(h, 1, std::vector<int>{T}, 0, nullptr, LA, s))) return (ctp_status)st;
+    const int row0 = LA.row0[0];
+    // only the T valid rows are written below: the gap rows of this layout must read as zero padding (a longer previous call may have left data)
+    CTP_CUDA_OK(cudaMemsetAsync(h->mel16, 0, sizeof(__half) * (size_t)LA.rows * MEL_PAD, s));
+    k_mel_frame<<<T, 256, 0, s>>>(audio, n_samples, h->mel16 + (long long)row0 * MEL_PAD, h->w.window, h->twiddle, h->w.mel_fb, h->w.coef,
+                                  c.n_mels, c.hop);
+    VLAUNCH_OK();
+    {   // downsample_conv.0: Conv1d(100 -> dim, k3, p1) + GELU (dvae.py:227-228) -> hm rows (fp16, pitch dim)
+        GemmEpilogue e{};
+        e.out = h->hm; e.ldo = dim; e.out_f16 = 1; e.bias = h->w.ds0_b; e.act_gelu = 1; e.row_valid = h->valid;
+        if ((st = voc_gemm(h->mel16, MEL_PAD, 3, LA.rows, h->w.ds0_w, dim, e, s))) return (ctp_status)st;
+    }
+    GroupLayout LB;
+    if ((st = voc_layout(h, 1, std::vector<int>{T2}, 0, nullptr, LB, s))) return (ctp_status)st;
+    CTP_CUDA_OK(cudaMemsetAsync(h->x0, 0, sizeof(__half) * (size_t)LB.rows * dim, s));
+    {   // downsample_conv.2: Conv1d(dim -> dim, k4, stride 2, p1) + GELU (dvae.py:229-230): output frame t2 reads input frames
+        // 2 t2 - 1 .. 2 t2 + 2, i.e. an im2col window of 4*dim starting one row before row 2 t2 with a row pitch of 2*dim
+        GemmLaunch g{};
+        g.A = h->hm + (long long)(row0 - 1) * dim; g.a_rows = T2; g.lda = 2LL * dim;
+        g.B = h->w.ds2_w; g.b_rows = dim; g.ldb = 4LL * dim; g.K = 4LL * dim;
+        g.block_n = dim >= 256 ? 256 : 128; g.split_k = 1;
+        g.epi.out = h->x0 + (long long)LB.row0[0] * dim; g.epi.ldo = dim; g.epi.out_f16 = 1; g.epi.bias = h->w.ds2_b; g.epi.act_gelu = 1;
+        g.epi.T = T2; g.epi.F = dim;
+        if ((st = gemm_launch(g, s))) return (ctp_status)st;
+    }
+    if ((st = voc_run_stack(h, LB.rows, s))) return (ctp_status)st;
+    float* feat = h->head;   // fp32 scratch [rows][>= odim]
+    {   // encoder.conv_out: 1x1, no bias (dvae.py:159,167), kept in fp32 for the quantiser
+        GemmEpilogue e{};
+        e.out = feat; e.ldo = c.dvae_odim; e.row_valid = h->valid;
+        if ((st = voc_gemm(h->y16, c.dvae_hidden, 1, LB.rows, h->w.conv_out_w, c.dvae_odim, e, s))) return (ctp_status)st;
+    }
+    const float* feat0 = feat + (long long)LB.row0[0] * c.dvae_odim;
+    k_gfsq_quantize<<<T2, 64, 0, s>>>(feat0, c.dvae_odim, 2, h->w.vq_in_w, h->w.vq_in_b, ids_out);
+    VLAUNCH_OK();
+    if (feat_out) CTP_CUDA_OK(cudaMemcpyAsync(feat_out, feat0, sizeof(float) * (size_t)T2 * c.dvae_odim, cudaMemcpyDeviceToDevice, s));
+    if (n_frames_host) *n_frames_host = T2;
+    return CTP_OK;
 }
 
 extern "C" ctp_status ctp_voc_decode_mel(ctp_voc* h, int32_t n_utt, const int32_t* mel_lens_host, const float* mel, float* wav_out,

@@ -261,12 +261,58 @@ class ChatTTSPlusPipeline:
                     self.logger.info("unload lora !")
                     gpt.unload_lora()
 
+    @staticmethod
+    def _load_audio_24k(path: str) -> torch.Tensor:
+        """torchaudio.load + resample to 24 kHz + channel mean (chattts_plus_pipeline.py:495-498).  torchaudio's file IO needs an
+        optional codec package; plain PCM WAV files are read with the standard library when it is absent."""
+        import torchaudio
+        try:
+            wav, sr = torchaudio.load(path)
+        except Exception:
+            import wave
+            with wave.open(path, "rb") as f:
+                sr, ch, sw, n = f.getframerate(), f.getnchannels(), f.getsampwidth(), f.getnframes()
+                raw = f.readframes(n)
+            if sw == 2:
+                a = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
+            elif sw == 4:
+                a = np.frombuffer(raw, dtype="<i4").astype(np.float32) / 2147483648.0
+            elif sw == 1:
+                a = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
+            else:
+                raise ValueError(f"{path}: unsupported PCM sample width {sw}")
+            wav = torch.from_numpy(a.reshape(-1, ch).T.copy())
+        wav = torchaudio.functional.resample(wav, orig_freq=sr, new_freq=24000)
+        return torch.mean(wav, 0)
+
+    @torch.inference_mode()
+    def sample_audio_speaker(self, wav) -> str:
+        """chattts_plus_pipeline.py:279-284: waveform (24 kHz, 1-D) -> b14/LZMA string of the GFSQ prompt codes [num_vq, T]."""
+        from .tokenizer import Tokenizer
+        if isinstance(wav, np.ndarray):
+            wav = torch.from_numpy(wav)
+        if "dvae_encode" not in self.models_dict:
+            raise RuntimeError("zero-shot speaker prompts need the dvae_encode model (configs/infer/chattts_plus.yaml)")
+        ids = self.models_dict["dvae_encode"](wav.to(self.device, torch.float32)[None], "encode").squeeze_(0)
+        return Tokenizer._encode_prompt(ids)
+
     @torch.no_grad()
     def infer(self, text, stream=False, lang=None, skip_refine_text=False, refine_text_only=False, use_decoder=True,
               do_text_normalization=True, do_text_optimization=True, do_homophone_replacement=True,
               params_refine_text=RefineTextParams(), params_infer_code=InferCodeParams(), **kwargs):
         if kwargs.get("speaker_audio_path", None):
-            raise NotImplementedError("zero-shot speaker prompt (DVAE encode) is the next scope row (SURVEY.md §8f f3)")
+            # zero-shot speaker prompt (chattts_plus_pipeline.py:486-500): the audio is encoded to GFSQ codes by the DVAE encoder
+            # and rides in the prompt (tokenizer.encode(prompt_str=...)); no speaker embedding is applied
+            speaker_audio_path = kwargs["speaker_audio_path"]
+            assert os.path.exists(speaker_audio_path), f"speaker_audio_path {speaker_audio_path} not exists!"
+            speaker_audio_text = kwargs.get("speaker_audio_text", "")
+            self.logger.info("Use zero shot >>>")
+            self.logger.info(f"speaker_audio_path is {speaker_audio_path}")
+            self.logger.info(f"speaker_audio_text is {speaker_audio_text}")
+            audio_wav = self._load_audio_24k(speaker_audio_path)
+            params_infer_code.txt_smp = speaker_audio_text
+            params_infer_code.spk_smp = self.sample_audio_speaker(audio_wav)
+            params_infer_code.spk_emb = None
         elif kwargs.get("speaker_emb_path", None):
             p = kwargs["speaker_emb_path"]
             assert os.path.exists(p), f"speaker_emb_path {p} not exists!"

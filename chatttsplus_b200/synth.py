@@ -51,10 +51,16 @@ class DVAEConfig:
     vq_levels: tuple = (5, 5, 5, 5)
     vq_G: int = 2
     vq_R: int = 2
+    # zero-shot prompt encoder (``encoder_config`` of ``dvae_encode``): DVAEDecoder(idim=dim, odim=vq_dim)
+    encoder: bool = False
+    enc_hidden: int = 256
+    enc_layers: int = 12
+    enc_bn: int = 128
+    enc_odim: int = 1024
 
     @staticmethod
-    def codes_model() -> "DVAEConfig":
-        return DVAEConfig(dim=512, idim=512, odim=512, hidden=256, n_layer=12, bn_dim=128, vq=True)
+    def codes_model(encoder: bool = False, enc_layers: int = 12) -> "DVAEConfig":
+        return DVAEConfig(dim=512, idim=512, odim=512, hidden=256, n_layer=12, bn_dim=128, vq=True, encoder=encoder, enc_layers=enc_layers)
 
 
 @dataclass
@@ -137,6 +143,20 @@ def make_dvae_state(cfg: DVAEConfig = DVAEConfig(), seed: int = 4321) -> Dict[st
         _convnext(sd, g, f"decoder.decoder_block.{l}.", cfg.hidden, cfg.hidden * 4, cfg.kernel, 0.05, 0.3)
     sd["decoder.conv_out.weight"] = _n(g, cfg.odim, cfg.hidden, 1, std=cfg.hidden ** -0.5)
     sd["out_conv.weight"] = _n(g, cfg.n_mels, cfg.dim, 3, std=(3 * cfg.dim) ** -0.5)
+    if getattr(cfg, "encoder", False):
+        # zero-shot prompt encoder (dvae.py:224-233): downsample_conv + a DVAEDecoder-shaped encoder (idim dim -> odim vq_dim)
+        sd["downsample_conv.0.weight"] = _n(g, cfg.dim, cfg.n_mels, 3, std=(3 * cfg.n_mels) ** -0.5 / 4)   # mel features are O(10)
+        sd["downsample_conv.0.bias"] = _n(g, cfg.dim, std=0.05)
+        sd["downsample_conv.2.weight"] = _n(g, cfg.dim, cfg.dim, 4, std=(4 * cfg.dim) ** -0.5)
+        sd["downsample_conv.2.bias"] = _n(g, cfg.dim, std=0.05)
+        eh, ebn = cfg.enc_hidden, cfg.enc_bn
+        sd["encoder.conv_in.0.weight"] = _n(g, ebn, cfg.dim, 3, std=(3 * cfg.dim) ** -0.5)
+        sd["encoder.conv_in.0.bias"] = _n(g, ebn, std=0.05)
+        sd["encoder.conv_in.2.weight"] = _n(g, eh, ebn, 3, std=(3 * ebn) ** -0.5)
+        sd["encoder.conv_in.2.bias"] = _n(g, eh, std=0.05)
+        for l in range(cfg.enc_layers):
+            _convnext(sd, g, f"encoder.decoder_block.{l}.", eh, eh * 4, cfg.kernel, 0.05, 0.3)
+        sd["encoder.conv_out.weight"] = _n(g, cfg.vq_dim, eh, 1, std=eh ** -0.5)
     if cfg.vq:
         # GroupedResidualFSQ: one ResidualFSQ per group, each with project_in (dim/G -> len(levels)) and
         # project_out (len(levels) -> dim/G); only project_out is used by get_output_from_indices.

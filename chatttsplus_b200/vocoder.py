@@ -7,7 +7,8 @@ Reference interfaces kept:
     (pip ``vocos`` as assembled by chattts_plus_pipeline.py:93-111 and called at :300-303)
   * ``VocoderEngine.decode_batch`` = ``ChatTTSPlusPipeline._decode_to_wavs`` for the whole batch in one library
     call (the reference loops utterance by utterance at batch 1, chattts_plus_pipeline.py:298-304).
-The encode side (mel-spectrogram -> GFSQ ids, dvae.py:171-199,263-270) is the "next" scope row f3.
+  * ``DVAE.__call__(audio, mode="encode")`` -> GFSQ indices ``[B, 4, T2]`` (dvae.py:263-270): the zero-shot speaker prompt
+    encoder (scope row f3): log-mel front end, downsample_conv, encoder stack and quantiser run in ``ctp_voc_encode``.
 """
 from __future__ import annotations
 
@@ -67,6 +68,16 @@ class DVAE:
             if tuple(self.cfg.vq_levels) != (5, 5, 5, 5) or self.cfg.vq_G != 2 or self.cfg.vq_R != 2:
                 raise _lib.CtpError("the GFSQ embed kernel is built for levels [5,5,5,5], G=2, R=2")
         self.has_encoder = encoder_config is not None
+        if self.has_encoder:
+            e = dict(encoder_config)
+            self.cfg.encoder = True
+            self.cfg.enc_hidden = int(e.get("hidden", 256)); self.cfg.enc_layers = int(e.get("n_layer", 12)); self.cfg.enc_bn = int(e.get("bn_dim", 64))
+            if int(e["idim"]) != self.cfg.dim:
+                raise _lib.CtpError("encoder_config.idim must equal dim (the width of downsample_conv, dvae.py:224-233)")
+            self.cfg.enc_odim = int(e["odim"])
+        self._enc = None          # packed encoder weights
+        self._enc_handle = C.c_void_p(0)
+        self._enc_frames = 0
         if coef is None:
             coef_t = torch.rand(100)
         else:
@@ -104,7 +115,16 @@ class DVAE:
         missing = [k for k in need if k not in sd]
         if missing:
             raise RuntimeError(f"Error(s) in loading state_dict for DVAE: missing {missing[:5]}")
-        # encoder-side tensors (downsample_conv.*, encoder.*, preprocessor_mel.*, project_in) are accepted and unused here
+        if self.has_encoder and "encoder.conv_out.weight" in sd:   # the encode side is optional in a state dict
+            need_e = ["downsample_conv.0.weight", "downsample_conv.0.bias", "downsample_conv.2.weight", "downsample_conv.2.bias",
+                      "encoder.conv_in.0.weight", "encoder.conv_in.0.bias", "encoder.conv_in.2.weight", "encoder.conv_in.2.bias"]
+            need_e += [f"encoder.decoder_block.{l}.{n}" for l in range(self.cfg.enc_layers) for n in
+                       ("dwconv.weight", "dwconv.bias", "norm.weight", "norm.bias", "pwconv1.weight", "pwconv1.bias", "pwconv2.weight", "pwconv2.bias", "gamma")]
+            if self.cfg.vq:
+                need_e += [f"vq_layer.quantizer.rvqs.{g}.project_in.{n}" for g in range(self.cfg.vq_G) for n in ("weight", "bias")]
+            miss_e = [k for k in need_e if k not in sd]
+            if miss_e:
+                raise RuntimeError(f"Error(s) in loading state_dict for DVAE (encoder side): missing {miss_e[:5]}")
         self._state = {k: sd[k].detach().cpu() for k in sd}
         self.coef = self._state["coef"].float().view(1, 100, 1)
         if self.device.type == "cuda":
@@ -139,14 +159,101 @@ class DVAE:
         blocks = (_lib.ConvNextW * c.n_layer)(*[_pack_convnext(sd, f"decoder.decoder_block.{l}.", dev, self._keep) for l in range(c.n_layer)])
         self._w = dict(tensors=w, blocks=blocks)
         self._engine = None
+        self._enc = None
+        if self._enc_handle:
+            _lib.lib().ctp_voc_destroy(self._enc_handle)
+            self._enc_handle = C.c_void_p(0)
+        if self.has_encoder and c.vq and "encoder.conv_out.weight" in sd:
+            self._pack_encoder()
+
+    def _pack_encoder(self):
+        """Prompt-encoder weight set of ``ctp_voc_encode`` (include/ctp.h): encoder.* in the DVAE stack slots, downsample_conv as
+        im2col matrices, the torchaudio mel filter bank (HTK, norm=None) and analysis window, GFSQ project_in."""
+        sd, dev, c = self._state, self.device, self.cfg
+        n_fft, sr = 1024, 24000
+        all_freqs = torch.linspace(0, sr // 2, n_fft // 2 + 1)
+        m_pts = torch.linspace(0.0, 2595.0 * float(np.log10(1.0 + (sr / 2.0) / 700.0)), c.n_mels + 2)
+        f_pts = 700.0 * (10 ** (m_pts / 2595.0) - 1.0)
+        f_diff = f_pts[1:] - f_pts[:-1]
+        slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+        fb = torch.clamp(torch.min(-slopes[:, :-2] / f_diff[:-1], slopes[:, 2:] / f_diff[1:]), min=0.0)   # torchaudio.functional.melscale_fbanks
+        keep: list = []
+        w = dict(
+            conv_in0_w=_dev_f16(_im2col_weight(sd["encoder.conv_in.0.weight"].float()), dev), conv_in0_b=_dev_f32(sd["encoder.conv_in.0.bias"], dev),
+            conv_in2_w=_dev_f16(_im2col_weight(sd["encoder.conv_in.2.weight"].float()), dev), conv_in2_b=_dev_f32(sd["encoder.conv_in.2.bias"], dev),
+            conv_out_w=_dev_f16(sd["encoder.conv_out.weight"].float().squeeze(-1), dev),
+            coef=_dev_f32(sd["coef"].reshape(-1), dev),
+            ds0_w=_dev_f16(_im2col_weight(sd["downsample_conv.0.weight"].float(), MEL_PAD), dev), ds0_b=_dev_f32(sd["downsample_conv.0.bias"], dev),
+            ds2_w=_dev_f16(_im2col_weight(sd["downsample_conv.2.weight"].float()), dev), ds2_b=_dev_f32(sd["downsample_conv.2.bias"], dev),
+            mel_fb=_dev_f32(fb, dev), window=_dev_f32(torch.hann_window(n_fft, periodic=True), dev),
+            vq_in_w=_dev_f32(torch.stack([sd[f"vq_layer.quantizer.rvqs.{g}.project_in.weight"] for g in range(c.vq_G)]), dev),
+            vq_in_b=_dev_f32(torch.stack([sd[f"vq_layer.quantizer.rvqs.{g}.project_in.bias"] for g in range(c.vq_G)]), dev))
+        blocks = (_lib.ConvNextW * c.enc_layers)(*[_pack_convnext(sd, f"encoder.decoder_block.{l}.", dev, keep) for l in range(c.enc_layers)])
+        self._enc = dict(tensors=w, blocks=blocks, keep=keep)
+
+    def _ensure_encoder(self, mel_frames: int):
+        if self._enc_handle and mel_frames + 32 <= self._enc_frames:
+            return
+        lib = _lib.lib()
+        if self._enc_handle:
+            lib.ctp_voc_destroy(self._enc_handle)
+            self._enc_handle = C.c_void_p(0)
+        c = self.cfg
+        self._enc_frames = max(4096, mel_frames + 32)
+        cfg = _lib.VocCfg(dvae_idim=c.dim, dvae_bn=c.enc_bn, dvae_hidden=c.enc_hidden, dvae_layers=c.enc_layers, dvae_odim=c.enc_odim,
+                          dvae_dilation=c.dilation, n_mels=c.n_mels, use_vq=0, voc_dim=512, voc_inter=1536, voc_layers=0, n_fft=1024, hop=256,
+                          max_frames=self._enc_frames, encoder=1)
+        h = C.c_void_p(0)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.ctp_voc_create(C.byref(h), C.byref(cfg)), "ctp_voc_create (prompt encoder)")
+            self._enc_handle = h
+            w = _lib.VocWeights()
+            for k, t in self._enc["tensors"].items():
+                setattr(w, k, t.data_ptr())
+            w.dvae_blocks = C.cast(self._enc["blocks"], C.POINTER(_lib.ConvNextW))
+            _lib.check(lib.ctp_voc_bind_weights(self._enc_handle, C.byref(w)), "ctp_voc_bind_weights (prompt encoder)")
+
+    @torch.inference_mode()
+    def encode(self, audio: torch.Tensor, return_features: bool = False):
+        """audio ``[B, N]`` (24 kHz) -> GFSQ indices ``[B, G*R, T2]`` int64 (dvae.py:263-270); utterances are encoded one by one."""
+        if self._enc is None:
+            raise _lib.CtpError("this DVAE has no prompt encoder on a CUDA device (needs encoder_config, vq_config and encoder.* weights)")
+        if audio.dim() == 1:
+            audio = audio[None]
+        outs, feats = [], []
+        with torch.cuda.device(self.device):
+            for b in range(audio.shape[0]):
+                a = audio[b].to(self.device, torch.float32).contiguous()
+                n = int(a.numel())
+                T = n // 256 + 1
+                T2 = (T - 2) // 2 + 1
+                self._ensure_encoder(T)
+                ids = torch.empty(T2, self.cfg.vq_G * self.cfg.vq_R, device=self.device, dtype=torch.int32)
+                feat = torch.empty(T2, self.cfg.enc_odim, device=self.device, dtype=torch.float32) if return_features else None
+                nf = C.c_int32(0)
+                _lib.check(_lib.lib().ctp_voc_encode(self._enc_handle, n, _lib.ptr(a), _lib.ptr(ids), _lib.ptr(feat), C.byref(nf), _lib.stream_ptr()),
+                           "ctp_voc_encode")
+                assert nf.value == T2
+                outs.append(ids.permute(1, 0).long())
+                if return_features:
+                    feats.append(feat.permute(1, 0))
+        ind = torch.stack(outs)
+        return (ind, torch.stack(feats)) if return_features else ind
+
+    def __del__(self):
+        try:
+            if self._enc_handle:
+                _lib.lib().ctp_voc_destroy(self._enc_handle)
+        except Exception:
+            pass
 
     def __call__(self, inp: torch.Tensor, mode: str = "decode") -> torch.Tensor:
         return self.forward(inp, mode)
 
     @torch.inference_mode()
     def forward(self, inp: torch.Tensor, mode: str = "decode") -> torch.Tensor:
-        if mode == "encode":
-            raise NotImplementedError("DVAE encode (zero-shot speaker prompt) is the next scope row (SURVEY.md §8f f3)")
+        if mode == "encode" and self.has_encoder and self.cfg.vq:   # dvae.py:263
+            return self.encode(inp)
         if self._w is None:
             raise _lib.CtpError("DVAE weights are not on a CUDA device: call .to('cuda') after loading")
         if self._engine is None:

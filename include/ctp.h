@@ -175,6 +175,10 @@ typedef struct ctp_voc_cfg {
     int32_t n_fft;        /* 1024 */
     int32_t hop;          /* 256 */
     int32_t max_frames;   /* workspace: max total mel frames (2 per code frame) per decode call, incl. padding */
+    /* Zero-shot speaker-prompt ENCODER handle (DVAE.forward(mode="encode"), dvae.py:263-270): set encoder = 1 and describe the
+     * `encoder_config` stack with the dvae_* fields above (idim = dim of downsample_conv 512, bn 128, hidden 256, layers 12,
+     * odim = vq dim 1024, configs/infer/chattts_plus.yaml:13); such a handle serves ctp_voc_encode only. */
+    int32_t encoder;
 } ctp_voc_cfg;
 
 /* One ConvNeXt block (dvae.py:16-63 / vocos ConvNeXtBlock). */
@@ -212,7 +216,15 @@ typedef struct ctp_voc_weights {
     const float* final_ln_b;
     const void* head_w;      /* fp16 [n_fft+2][dim] */
     const float* head_b;     /* fp32 [n_fft+2] */
-    const float* window;     /* fp32 [n_fft] */
+    const float* window;     /* fp32 [n_fft]  (encoder handle: the analysis Hann window of MelSpectrogramFeatures, dvae.py:183-190) */
+    /* prompt encoder (cfg.encoder = 1): conv_in0/2, dvae_blocks, conv_out above hold `encoder.*`; coef as above */
+    const void* ds0_w;       /* fp16 [idim][3*mel_pad]  downsample_conv.0 (k3, p1), k = tap*mel_pad + c (dvae.py:227) */
+    const float* ds0_b;      /* fp32 [idim] */
+    const void* ds2_w;       /* fp16 [idim][4*idim]     downsample_conv.2 (k4, stride 2, p1), k = tap*idim + c (dvae.py:229) */
+    const float* ds2_b;      /* fp32 [idim] */
+    const float* mel_fb;     /* fp32 [n_fft/2+1][n_mels] mel filter bank (torchaudio melscale_fbanks, htk, norm=None) */
+    const float* vq_in_w;    /* fp32 [G][4][odim/G]  GFSQ project_in (vector_quantize_pytorch ResidualFSQ) */
+    const float* vq_in_b;    /* fp32 [G][4] */
 } ctp_voc_weights;
 
 CTP_API ctp_status ctp_voc_create(ctp_voc** out, const ctp_voc_cfg* cfg);
@@ -231,6 +243,14 @@ CTP_API ctp_status ctp_voc_decode(ctp_voc* h, int32_t n_utt, const int32_t* lens
  * [sum T_i][n_mels] concatenated, utterance i has mel_lens_host[i] frames -> wav of hop*(T_i-1) samples. */
 CTP_API ctp_status ctp_voc_decode_mel(ctp_voc* h, int32_t n_utt, const int32_t* mel_lens_host, const float* mel,
                                       float* wav_out, const int64_t* wav_offsets_host, ctp_stream stream);
+
+/* DVAE.forward(inp, mode="encode") for ONE utterance (dvae.py:263-270; caller: ChatTTSPlusPipeline.sample_audio_speaker,
+ * chattts_plus_pipeline.py:279-284): audio fp32 [n_samples] at 24 kHz -> log-mel (n_fft 1024, hop 256, 100 mels, centre
+ * reflect padding) / coef -> downsample_conv -> encoder -> GFSQ indices.  ids_out: dev int32 [T2][G*R] with
+ * T2 = ((n_samples / hop + 1) - 2) / 2 + 1 code frames (row t = the reference's ind[0, :, t]); feat_out (optional, may be
+ * NULL): dev fp32 [T2][odim] encoder output before the quantiser; *n_frames_host receives T2. */
+CTP_API ctp_status ctp_voc_encode(ctp_voc* h, int32_t n_samples, const float* audio, int32_t* ids_out, float* feat_out,
+                                  int32_t* n_frames_host, ctp_stream stream);
 
 /* ======================================================================================================
  * Building block exposed for tests and profiling: C = epilogue(A[M,K] * B[N,K]^T), fp16 in, fp32 accumulate,

@@ -446,6 +446,90 @@ def dvae_decode(p: Dict[str, Tensor], inp: Tensor, *, n_layer: int = 12, dilatio
 
 
 # ------------------------------------------------------------------------------------------------
+# DVAE encode = zero-shot speaker prompt: audio -> mel -> encoder -> GFSQ indices
+#   mel / downsample / encoder are PINNED against the reference's own dvae.py (tests/golden/dvae_encode_ref.pt);
+#   the quantiser (pip vector_quantize_pytorch==1.17.8 GroupedResidualFSQ.forward, absent here) is restated: UNPINNED
+# ------------------------------------------------------------------------------------------------
+
+def melscale_fbanks_htk(n_freqs: int = 513, f_min: float = 0.0, f_max: float = 12000.0, n_mels: int = 100,
+                        sample_rate: int = 24000) -> Tensor:
+    """torchaudio.functional.melscale_fbanks(norm=None, mel_scale="htk"), the filter bank of
+    torchaudio.transforms.MelSpectrogram as constructed at dvae.py:183-190 -> [n_freqs, n_mels]."""
+    all_freqs = torch.linspace(0, sample_rate // 2, n_freqs)
+    m_min = 2595.0 * math.log10(1.0 + f_min / 700.0)
+    m_max = 2595.0 * math.log10(1.0 + f_max / 700.0)
+    m_pts = torch.linspace(m_min, m_max, n_mels + 2)
+    f_pts = 700.0 * (10 ** (m_pts / 2595.0) - 1.0)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    down = (-1.0 * slopes[:, :-2]) / f_diff[:-1]
+    up = slopes[:, 2:] / f_diff[1:]
+    return torch.clamp(torch.min(down, up), min=0.0)
+
+
+def mel_features(audio: Tensor, n_fft: int = 1024, hop: int = 256, n_mels: int = 100, sample_rate: int = 24000) -> Tensor:
+    """MelSpectrogramFeatures.forward, dvae.py:196-199: log(clip(mel(|STFT|), 1e-5)); audio [B, N] -> [B, n_mels, N//hop + 1]
+    (center=True, reflect padding, periodic Hann window, power=1)."""
+    win = torch.hann_window(n_fft, periodic=True, dtype=torch.float32)
+    spec = torch.stft(audio.float(), n_fft, hop_length=hop, win_length=n_fft, window=win, center=True, pad_mode="reflect",
+                      normalized=False, onesided=True, return_complex=True).abs()
+    fb = melscale_fbanks_htk(n_fft // 2 + 1, 0.0, sample_rate / 2.0, n_mels, sample_rate)
+    mel = torch.matmul(spec.transpose(-1, -2), fb).transpose(-1, -2)
+    return torch.log(torch.clip(mel, min=1e-5))
+
+
+def dvae_encode_features(p: Dict[str, Tensor], audio: Tensor, *, n_layer: int = 12, dilation: int = 2) -> Tensor:
+    """DVAE.forward encode branch up to the quantiser, dvae.py:263-269: audio [B, N] -> x [B, 1024, T2]."""
+    mel = mel_features(audio)
+    x = mel / p["coef"].view(1, -1, 1)                                   # dvae.py:266
+    x = F.gelu(F.conv1d(x, p["downsample_conv.0.weight"], p["downsample_conv.0.bias"], padding=1))   # dvae.py:227-232
+    x = F.gelu(F.conv1d(x, p["downsample_conv.2.weight"], p["downsample_conv.2.bias"], stride=2, padding=1))
+    y = F.conv1d(x, p["encoder.conv_in.0.weight"], p["encoder.conv_in.0.bias"], padding=1)          # DVAEDecoder.forward, dvae.py:161-168
+    y = F.gelu(y)
+    y = F.conv1d(y, p["encoder.conv_in.2.weight"], p["encoder.conv_in.2.bias"], padding=1)
+    for l in range(n_layer):
+        y = convnext_block(y, p, f"encoder.decoder_block.{l}.", dilation)
+    return F.conv1d(y, p["encoder.conv_out.weight"])
+
+
+def fsq_bound(z: Tensor, levels: Sequence[int], eps: float = 1e-3) -> Tensor:
+    """vector_quantize_pytorch FSQ.bound: tanh squashing to (levels-1)/2 * (1+eps); offset/shift are 0 for odd levels."""
+    lv = torch.tensor(list(levels), dtype=z.dtype)
+    half_l = (lv - 1) * (1 + eps) / 2
+    offset = torch.where(lv % 2 == 0, torch.tensor(0.5, dtype=z.dtype), torch.tensor(0.0, dtype=z.dtype))
+    shift = torch.atanh(offset / half_l)
+    return torch.tanh(z + shift) * half_l - offset
+
+
+def gfsq_quantize(p: Dict[str, Tensor], x: Tensor, levels: Sequence[int] = (5, 5, 5, 5), G: int = 2, R: int = 2) -> Tensor:
+    """GFSQ.forward, dvae.py:98-126 -> GroupedResidualFSQ.forward (UNPINNED restatement of vector_quantize_pytorch 1.17.8):
+    x [B, dim, T] -> ind [B, G*R, T].  Per group: z = project_in(x_g) (Linear dim/G -> 4); residual = bound(z);
+    for r < R: q = round(bound(residual / s_r)) / (levels // 2), ind_r = sum_j (q_j * hw_j + hw_j) * prod(levels[:j]),
+    residual -= q * s_r, with s_r = (levels - 1) ** -r."""
+    B, D, T = x.shape
+    xt = x.transpose(1, 2).float()                     # dvae.py:99-100
+    gd = D // G
+    lv = torch.tensor(list(levels), dtype=torch.float32)
+    half_width = torch.div(lv, 2, rounding_mode="floor")
+    basis = torch.cumprod(torch.tensor([1] + list(levels[:-1]), dtype=torch.float32), 0)
+    out = torch.zeros(B, T, G, R, dtype=torch.long)
+    for g in range(G):
+        z = F.linear(xt[..., g * gd:(g + 1) * gd], p[f"vq_layer.quantizer.rvqs.{g}.project_in.weight"],
+                     p[f"vq_layer.quantizer.rvqs.{g}.project_in.bias"])
+        residual = fsq_bound(z, levels)
+        for r in range(R):
+            scale = (lv - 1) ** (-r)
+            q = torch.round(fsq_bound(residual / scale, levels)) / half_width
+            out[:, :, g, r] = ((q * half_width + half_width) * basis).sum(-1).round().long()
+            residual = residual - q * scale
+    return out.view(B, T, G * R).transpose(1, 2)       # dvae.py:109-126: [B, T, (g r)] -> [B, G*R, T]
+
+
+def dvae_encode(p: Dict[str, Tensor], audio: Tensor, **kw) -> Tensor:
+    return gfsq_quantize(p, dvae_encode_features(p, audio, **kw))
+
+
+# ------------------------------------------------------------------------------------------------
 # Vocos decode   (A24; third-party `vocos` package restated — UNPINNED)
 # ------------------------------------------------------------------------------------------------
 

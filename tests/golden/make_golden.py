@@ -13,6 +13,8 @@ exist on the GPU box, so the outputs of the reference itself are captured here o
                                                                   -> pins oracle.gpt_embed / generate (A1,A3-A5,A13-A18)
   dvae_ref.pt         reference chattts_plus/models/dvae.py DVAE decode branch
                                                                   -> pins oracle.dvae_decode (A20-A22)
+  dvae_encode_ref.pt  reference dvae.py MelSpectrogramFeatures + downsample_conv + encoder (encode branch up to the quantiser)
+                                                                  -> pins oracle.mel_features / dvae_encode_features (f3)
 
 Import shims (this script only; nothing of the reference is copied): stub parent packages so that
 ``models/__init__.py`` (which imports the absent pybase16384) is bypassed; stub modules ``pybase16384`` and
@@ -214,6 +216,29 @@ def gen_dvae(dvae_mod):
     print("dvae_ref.pt", tuple(mel.shape))
 
 
+def gen_dvae_encode(dvae_mod):
+    """Zero-shot prompt encoder: the reference's own MelSpectrogramFeatures, downsample_conv and encoder
+    modules chained as DVAE.forward(mode="encode") does (dvae.py:263-269).  The quantiser (vector_quantize_pytorch) is absent
+    here, so the golden stops at the encoder output."""
+    cfg = synth.DVAEConfig.codes_model(encoder=True, enc_layers=3)
+    cfg.n_layer = 2
+    sd = synth.make_dvae_state(cfg, seed=17)
+    m = dvae_mod.DVAE(decoder_config=dict(idim=cfg.idim, odim=cfg.odim, hidden=cfg.hidden, n_layer=cfg.n_layer, bn_dim=cfg.bn_dim),
+                      encoder_config=dict(idim=cfg.dim, odim=cfg.vq_dim, hidden=cfg.enc_hidden, n_layer=cfg.enc_layers, bn_dim=cfg.enc_bn),
+                      vq_config=None, dim=cfg.dim).eval()
+    missing = m.load_state_dict({k: v for k, v in sd.items() if not k.startswith("vq_layer.")}, strict=False)
+    assert all(k.startswith("preprocessor_mel.") for k in missing.missing_keys), missing
+    g = torch.Generator().manual_seed(43)
+    audio = 0.1 * torch.randn(1, 256 * 37 + 91, generator=g)
+    with torch.no_grad():
+        mel = m.preprocessor_mel(audio.clone())
+        x = m.downsample_conv(torch.div(mel, m.coef.view(1, 100, 1).expand(mel.shape)))
+        x = m.encoder(x)
+    torch.save({"weight_seed": 17, "n_layer": cfg.n_layer, "enc_layers": cfg.enc_layers, "audio": audio, "mel": mel.clone(), "x": x.clone()},
+               os.path.join(HERE, "dvae_encode_ref.pt"))
+    print("dvae_encode_ref.pt", tuple(mel.shape), tuple(x.shape))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     llama, processors, gpt_mod, dvae_mod = _load_reference()
@@ -221,3 +246,4 @@ if __name__ == "__main__":
     gen_processors(processors)
     gen_gpt(gpt_mod, processors)
     gen_dvae(dvae_mod)
+    gen_dvae_encode(dvae_mod)

@@ -143,11 +143,43 @@ def test_refine_text_flow_through_infer(tmp_path):
     assert len(wavs) == 1 and wavs[0].shape == (256 * 9,)
 
 
-def test_unbuilt_scope_rows_fail_loudly(tmp_path):
+def test_zero_shot_speaker_prompt_flow(tmp_path):
+    """speaker_audio_path (chattts_plus_pipeline.py:486-500): WAV file -> 24 kHz mono -> DVAE encode -> b14/LZMA prompt string ->
+    audio-prompt rows appended to every input (tokenizer.py:100-137); generation runs without a speaker embedding."""
+    import wave
+    import numpy as np
     from chattts_plus.commons.utils import InferCodeParams
-    pipe, *_ = _pipeline(layers=1)
-    with pytest.raises(NotImplementedError):
-        pipe.infer("x", speaker_audio_path=__file__, params_infer_code=InferCodeParams(show_tqdm=False))
+    from chatttsplus_b200.tokenizer import Tokenizer
+    from chatttsplus_b200.vocoder import DVAE
+    pipe, cfg, *_ = _pipeline(layers=1)
+    ecfg = synth.DVAEConfig.codes_model(encoder=True, enc_layers=2)
+    ecfg.n_layer = 2
+    esd = synth.make_dvae_state(ecfg, seed=23)
+    enc = DVAE(decoder_config=dict(idim=512, odim=512, hidden=256, n_layer=2, bn_dim=128),
+               encoder_config=dict(idim=512, odim=1024, hidden=256, n_layer=2, bn_dim=128),
+               vq_config=dict(dim=1024, levels=[5, 5, 5, 5], G=2, R=2), dim=512)
+    enc.load_state_dict(esd)
+    enc.to("cuda")
+    pipe.models_dict["dvae_encode"] = enc
+    path = str(tmp_path / "spk.wav")
+    rng = np.random.default_rng(0)
+    pcm = (rng.standard_normal(16000) * 3000).astype("<i2")       # 1 s at 16 kHz -> resampled to 24 kHz
+    with wave.open(path, "wb") as f:
+        f.setnchannels(1); f.setsampwidth(2); f.setframerate(16000); f.writeframes(pcm.tobytes())
+    wav24 = pipe._load_audio_24k(path)
+    assert wav24.shape == (24000,)
+    spk_smp = pipe.sample_audio_speaker(wav24)
+    prompt = Tokenizer._decode_prompt(spk_smp)
+    T2 = ((24000 // 256 + 1) - 2) // 2 + 1
+    assert prompt.shape == (4, T2) and int(prompt.min()) >= 0 and int(prompt.max()) < 625
+    assert torch.equal(prompt, O.gfsq_quantize(esd, O.dvae_encode_features(esd, wav24[None], n_layer=2))[0]) or \
+        float((prompt == O.gfsq_quantize(esd, O.dvae_encode_features(esd, wav24[None], n_layer=2))[0]).float().mean()) >= 0.97
+    params = InferCodeParams(show_tqdm=False, max_new_token=6, min_new_token=6, temperature=0.3)
+    wavs = None
+    for wavs in pipe.infer(["hello"], skip_refine_text=True, speaker_audio_path=path, speaker_audio_text="ab", params_infer_code=params):
+        pass
+    assert params.spk_emb is None and params.spk_smp == spk_smp and params.txt_smp == "ab"
+    assert len(wavs) == 1 and wavs[0].numel() == 256 * (2 * 6 - 1) and bool(torch.isfinite(wavs[0]).all())
 
 
 def test_stream_mode_yields_growing_audio(tmp_path):

@@ -118,3 +118,45 @@ def test_refine_text_pass_matches_reference_gpt(golden_dir):
                    rep_penalty=None, sampler="torch", infer_text=True)
     for a, b in zip(r.ids, c["ids"]):
         assert a.shape == b.shape and torch.equal(a, b)
+
+
+def test_dvae_encode_front_end_matches_reference_golden(golden_dir):
+    """Zero-shot prompt encoder (f3): mel features and the encoder output equal what the reference's own MelSpectrogramFeatures /
+    downsample_conv / encoder modules produced (tests/golden/make_golden.py::gen_dvae_encode)."""
+    ref = _load(golden_dir, "dvae_encode_ref.pt")
+    cfg = synth.DVAEConfig.codes_model(encoder=True, enc_layers=ref["enc_layers"])
+    cfg.n_layer = ref["n_layer"]
+    sd = synth.make_dvae_state(cfg, seed=ref["weight_seed"])
+    mel = O.mel_features(ref["audio"])
+    assert mel.shape == ref["mel"].shape and float((mel - ref["mel"]).abs().max()) < 1e-4
+    x = O.dvae_encode_features(sd, ref["audio"], n_layer=ref["enc_layers"])
+    assert x.shape == ref["x"].shape and float((x - ref["x"]).abs().max()) < 1e-4
+
+
+def test_gfsq_quantize_is_consistent_with_embed():
+    """The quantiser restatement (unpinned: vector_quantize_pytorch is absent) and the pinned-by-formula embed (A23) agree:
+    embed(quantize(x)) == project_out(sum_r q_r * 4^-r) and every index is a valid code."""
+    cfg = synth.DVAEConfig.codes_model(encoder=True, enc_layers=1)
+    sd = synth.make_dvae_state(cfg, seed=3)
+    g = torch.Generator().manual_seed(5)
+    x = 3.0 * torch.randn(2, 1024, 11, generator=g)
+    ids = O.gfsq_quantize(sd, x)
+    assert ids.shape == (2, 4, 11) and int(ids.min()) >= 0 and int(ids.max()) < 625
+    feat = O.gfsq_embed(sd, ids)
+    # recompute the quantised vector directly
+    xt = x.transpose(1, 2)
+    outs = []
+    for gi in range(2):
+        z = torch.nn.functional.linear(xt[..., gi * 512:(gi + 1) * 512], sd[f"vq_layer.quantizer.rvqs.{gi}.project_in.weight"],
+                                       sd[f"vq_layer.quantizer.rvqs.{gi}.project_in.bias"])
+        res = O.fsq_bound(z, (5, 5, 5, 5))
+        q_sum = torch.zeros_like(z)
+        for r in range(2):
+            sc = 4.0 ** (-r)
+            q = torch.round(O.fsq_bound(res / sc, (5, 5, 5, 5))) / 2
+            q_sum = q_sum + q * sc
+            res = res - q * sc
+        outs.append(torch.nn.functional.linear(q_sum, sd[f"vq_layer.quantizer.rvqs.{gi}.project_out.weight"],
+                                               sd[f"vq_layer.quantizer.rvqs.{gi}.project_out.bias"]))
+    direct = torch.cat(outs, -1).transpose(1, 2)
+    assert float((feat - direct).abs().max()) < 1e-4
