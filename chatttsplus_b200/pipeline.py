@@ -214,21 +214,7 @@ class ChatTTSPlusPipeline:
             text_list = []
             for t in text_in:
                 text_list.extend([s.strip() for s in t.split("\n") if s.strip()])
-            retext, short = [], ""
-            for it in _text.split_text(text_list):
-                if len(it) < 30:
-                    short += f"{it} [uv_break] "
-                    if len(short) > 30:
-                        retext.append(short)
-                        short = ""
-                else:
-                    retext.append(short + it)
-                    short = ""
-            if len(short) > 30 or len(retext) < 1:
-                retext.append(short)
-            elif short:
-                retext[-1] += f" [uv_break] {short}"
-            text_in = retext
+            text_in = _text.merge_short_texts(_text.split_text(text_list))
         text_in = [self.normalizer(t, do_text_normalization, do_homophone_replacement, lang) for t in text_in]
         slice_size = kwargs.get("slice_size", 4)
         gpt = self.models_dict["gpt"]

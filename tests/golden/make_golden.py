@@ -13,6 +13,7 @@ exist on the GPU box, so the outputs of the reference itself are captured here o
                                                                   -> pins oracle.gpt_embed / generate (A1,A3-A5,A13-A18)
   dvae_ref.pt         reference chattts_plus/models/dvae.py DVAE decode branch
                                                                   -> pins oracle.dvae_decode (A20-A22)
+  text_ref.json       reference commons/text_utils.py + commons/norm.py on fixed samples  -> pins chatttsplus_b200/text.py (f4)
   dvae_encode_ref.pt  reference dvae.py MelSpectrogramFeatures + downsample_conv + encoder (encode branch up to the quantiser)
                                                                   -> pins oracle.mel_features / dvae_encode_features (f3)
 
@@ -239,6 +240,70 @@ def gen_dvae_encode(dvae_mod):
     print("dvae_encode_ref.pt", tuple(mel.shape), tuple(x.shape))
 
 
+TEXT_SAMPLES = [
+    "Hello world, this is a test.", "I have 3 apples, 12 pears and 105 plums!", "The price is 1,234.56 dollars (50% off) [uv_break] ok",
+    "2+3=5 and 7*8 = 56; 9-4", "1/2 of 3.5/7", "Call 911 now: it's urgent [laugh] really?", "x = 1000000 and y=20001 [lbreak]",
+    "今天天气不错，我们去公园玩吧！", "他说: hello (world) 你好【测试】《书名》", "混合 text with 中文 and English words, 还有 numbers 42.",
+    "emoji 😀 and symbols #$%^&*~ should go", "[break] leading tag and trailing tag [uv_break]", "", "   ",
+    "A very long English sentence, " * 12 + "the end.", "这是一个很长的中文句子，" * 30 + "结束。",
+    "Decimal 3.14159 stays, but sentence ends. Next one? Yes! Fine; good: ok) done} more… and more",
+    "17 77 707 7 70", "999999999999999999999 is too long, 1234567890123456 is not", "tags [laugh][laugh] twice [uv_break][lbreak] end",
+]
+
+
+def gen_text():
+    """Host text front-end (f4): the reference's own commons/text_utils.py and commons/norm.py functions on fixed samples.
+    ``zh_normalization`` (absent) is stubbed at import time only; functions that need it (split_text on Chinese) are not recorded."""
+    import json
+    import tempfile
+    zh = types.ModuleType("zh_normalization")
+    zh.TextNormalizer = object
+    sys.modules["zh_normalization"] = zh
+
+    def load(modname, rel):
+        spec = importlib.util.spec_from_file_location(modname, os.path.join(R, rel))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[modname] = mod
+        spec.loader.exec_module(mod)
+        return mod
+    tu = load("chattts_plus.commons.text_utils", "commons/text_utils.py")
+    norm = load("chattts_plus.commons.norm", "commons/norm.py")
+    out = {"num_to_english": {}, "num2text": {}, "remove_brackets": {}, "get_lang": {}, "split_by_punct": {}, "normalizer": []}
+    nums = list(range(0, 130)) + [199, 200, 201, 210, 211, 999, 1000, 1001, 1010, 1011, 1100, 2024, 9999, 10000, 10001, 10011, 12345, 100000,
+                                 100200, 1000000, 1000001, 1002003, 20001, 1234567, 999999999, 1000000000, 123456789012, 1000000000000, 1234567890123456]
+    for n in nums:
+        try:
+            out["num_to_english"][str(n)] = tu.num_to_english(n)
+        except Exception as e:  # the reference raises IndexError for ...10
+            out["num_to_english"][str(n)] = "!" + type(e).__name__
+    for t in TEXT_SAMPLES:
+        try:
+            out["num2text"][t] = tu.num2text(t)
+        except Exception as e:
+            out["num2text"][t] = "!" + type(e).__name__
+        out["remove_brackets"][t] = tu.remove_brackets(t)
+        out["get_lang"][t] = tu.get_lang(t)
+        out["split_by_punct"][t] = tu.split_text_by_punctuation(t)
+    hm = {"好": "郝", "天": "添", "书": "叔", "a": "b"}
+    with tempfile.TemporaryDirectory() as d:
+        mp = os.path.join(d, "homophones_map.json")
+        with open(mp, "w", encoding="utf-8") as f:
+            json.dump(hm, f, ensure_ascii=False)
+        nz = norm.Normalizer(mp)
+        nz.register("en", lambda s: s.replace("test", "TEST"))
+        for t in TEXT_SAMPLES:
+            for tn in (True, False):
+                for hr in (True, False):
+                    for lang in (None, "zh", "en"):
+                        out["normalizer"].append({"text": t, "tn": tn, "hr": hr, "lang": lang, "out": nz(t, tn, hr, lang)})
+    out["homophones"] = hm
+    out["tables"] = {"simplify": {chr(k): v for k, v in nz.character_simplifier.items()},
+                     "half2full": {chr(k): v for k, v in nz.halfwidth_2_fullwidth.items()}}
+    with open(os.path.join(HERE, "text_ref.json"), "w", encoding="utf-8") as f:
+        json.dump(out, f, ensure_ascii=False, indent=0)
+    print("text_ref.json", len(out["num_to_english"]), len(out["normalizer"]))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     llama, processors, gpt_mod, dvae_mod = _load_reference()
@@ -247,3 +312,4 @@ if __name__ == "__main__":
     gen_gpt(gpt_mod, processors)
     gen_dvae(dvae_mod)
     gen_dvae_encode(dvae_mod)
+    gen_text()
