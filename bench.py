@@ -214,7 +214,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(B * 256 * (2 * GEN - 1) * 4)},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": traffic, "kernel": "decode step (CUDA-graph replay)", "peak_source": peak_src,
+                     "traffic": traffic, "kernel": "decode step (one CUDA-graph replay: 5 kernels per layer x 20 + embed-norm, final norm, heads, sampler)", "peak_source": peak_src,
                      "algorithmic_bytes_per_step_mean": int(alg_bytes / dec_steps)},
         "clocks": clocks,
     }

@@ -547,6 +547,7 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
     const int bn = B <= 32 ? 32 : 64;
     const ActMaps& am = bn == 32 ? h->act32 : h->act64;
     int st;
+    h->trace_n = 0;
     const bool cluster = h->use_cluster && B <= 32;
     if (cluster) {
         if ((st = run_decode_trunk_cluster(h, B, nsplit, ids_ext, s))) return st;
