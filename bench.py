@@ -375,8 +375,9 @@ def run_reference(args):
            "unit": "frames/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": round(1e3 * dt / args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"configs[1]: batch={args.batch} synthetic {L0}-token prompts, {args.gen} generated codes, hidden->mel->wav "
-                                  "(bounded sample per step, see cpu_baseline.sample)"},
+           "config": {"workload": f"configs[1]: batch={args.batch} synthetic {L0}-token prompts, default speaker, {args.gen} generated codes, hidden->mel->wav",
+                      "per_gpu_batch": args.batch, "prompt_len": L0, "gen_frames": args.gen,
+                      "note": "CPU arm: each step is a bounded sample of this workload (see cpu_baseline.sample)"},
            "cpu_baseline": cb, "e2e": {"value": round(v, 2), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
