@@ -716,8 +716,13 @@ extern "C" ctp_status ctp_gpt_prefill(ctp_gpt* h, int32_t B, int32_t L0, const f
         k_rope_prefill<<<dim3(L0, B), c.n_heads * 32, 0, s>>>(h->acc_qkv, h->kplane(l), h->vplane(l), h->pad_len, h->inv_freq, H,
                                                                c.n_heads, L0, c.max_seq);
         LAUNCH_OK();
-        k_attn_prefill<<<dim3(c.n_heads, B, (L0 + 7) / 8), 256, 0, s>>>(h->acc_qkv, h->kplane(l), h->vplane(l), h->attn, h->pad_len,
-                                                                         H, c.n_heads, L0, c.max_seq);
+        static const bool scalar_attn = getenv("CTP_PREFILL_ATTN") && strcmp(getenv("CTP_PREFILL_ATTN"), "scalar") == 0;
+        if (scalar_attn)
+            k_attn_prefill<<<dim3(c.n_heads, B, (L0 + 7) / 8), 256, 0, s>>>(h->acc_qkv, h->kplane(l), h->vplane(l), h->attn, h->pad_len,
+                                                                             H, c.n_heads, L0, c.max_seq);
+        else
+            k_attn_prefill_mma<<<dim3((L0 + PF_TILE - 1) / PF_TILE, c.n_heads, B), 128, 0, s>>>(h->acc_qkv, h->kplane(l), h->vplane(l), h->attn,
+                                                                                                h->pad_len, H, c.n_heads, L0, c.max_seq);
         LAUNCH_OK();
         {
             GemmLaunch g{};

@@ -704,6 +704,145 @@ __global__ void __launch_bounds__(256) k_attn_prefill(const float* __restrict__ 
     orow[lane + 32] = __float2half_rn(o1 / l);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Prefill attention on the tensor cores (default): flash-style causal attention with left-padding mask, one CTA per
+// (64-query tile, head, sequence), 4 warps x 16 query rows.  S = Q K^T and O += P V run as mma.sync.m16n8k16 (fp16 in, fp32
+// accumulate: a 64x64x64 tile pair per step is far too small for tcgen05, whose minimum M is 64 per CTA-wide instruction and
+// whose operands must round-trip through shared memory descriptors); K is staged row-major and V transposed in shared memory
+// so that every B fragment is one conflict-free 32-bit load; the score fragments are reused in place as the A operand of P V.
+// Same semantics as k_attn_prefill: query slot i sees key slots [pad, i]; padded query rows (i < pad) see only themselves
+// (their output is never consumed).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+constexpr int PF_TILE = 64, PF_PITCH = 72;   // 64-slot tiles; shared-memory row pitch in halfs (144 B: conflict-free fragment loads)
+
+__global__ void __launch_bounds__(128) k_attn_prefill_mma(const float* __restrict__ qkv, const __half* __restrict__ kcache,
+                                                           const __half* __restrict__ vcache, __half* __restrict__ out,
+                                                           const int* __restrict__ pad_len, int H, int nH, int L0, int max_seq) {
+    const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    __shared__ __align__(16) __half sK[PF_TILE * PF_PITCH];    // [key][d]
+    __shared__ __align__(16) __half sVt[HEAD_DIM * PF_PITCH];  // [d][key]
+    const int pad = pad_len[b];
+    const long long head_off = (((long long)b * nH + h) * max_seq) * HEAD_DIM;
+    const __half* kc = kcache + head_off;
+    const __half* vc = vcache + head_off;
+    // this thread's two query rows
+    const int i0 = qt * PF_TILE + warp * 16 + g, i1 = i0 + 8;
+    // Q fragments (A operand, 16 x 64 per warp = 4 k-steps), 1/sqrt(64) folded in; rows beyond L0 read as zero
+    uint32_t qa[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        const int d0 = ks * 16 + 2 * t;
+        const float* r0 = qkv + ((long long)b * L0 + i0) * 3 * H + h * HEAD_DIM;
+        const float* r1 = qkv + ((long long)b * L0 + i1) * 3 * H + h * HEAD_DIM;
+        const bool ok0 = i0 < L0, ok1 = i1 < L0;
+        qa[ks][0] = ok0 ? pack_h2(r0[d0] * 0.125f, r0[d0 + 1] * 0.125f) : 0u;
+        qa[ks][1] = ok1 ? pack_h2(r1[d0] * 0.125f, r1[d0 + 1] * 0.125f) : 0u;
+        qa[ks][2] = ok0 ? pack_h2(r0[d0 + 8] * 0.125f, r0[d0 + 9] * 0.125f) : 0u;
+        qa[ks][3] = ok1 ? pack_h2(r1[d0 + 8] * 0.125f, r1[d0 + 9] * 0.125f) : 0u;
+    }
+    const int lo0 = i0 >= pad ? pad : i0, lo1 = i1 >= pad ? pad : i1;   // first visible key slot of each row
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    float o[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
+
+    const int q_hi = min(qt * PF_TILE + PF_TILE - 1, L0 - 1);           // last query slot of the tile
+    const int q_lo = qt * PF_TILE;
+    const int k_first = (min(q_lo, pad) / PF_TILE);                      // rows >= pad start at pad; padded rows at themselves (>= q_lo)
+    for (int kt = k_first; kt * PF_TILE <= q_hi; ++kt) {
+        const int j0 = kt * PF_TILE;
+        __syncthreads();   // previous tile fully consumed
+        // stage K [key][d] and V^T [d][key]: 64 keys x 8 chunks of 8 halfs; keys beyond the prompt read as zero (masked below)
+        for (int c = tid; c < PF_TILE * 8; c += 128) {
+            const int key = c >> 3, ch = c & 7;
+            uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+            if (j0 + key < L0) {
+                kv = __ldg(reinterpret_cast<const uint4*>(kc + (long long)(j0 + key) * HEAD_DIM) + ch);
+                vv = __ldg(reinterpret_cast<const uint4*>(vc + (long long)(j0 + key) * HEAD_DIM) + ch);
+            }
+            *reinterpret_cast<uint4*>(sK + key * PF_PITCH + ch * 8) = kv;
+            const __half* vh = reinterpret_cast<const __half*>(&vv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sVt[(ch * 8 + e) * PF_PITCH + key] = vh[e];
+        }
+        __syncthreads();
+        // S = Q K^T for 16 rows x 64 keys
+        float sc[8][4];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const __half* kp = sK + (n * 8 + g) * PF_PITCH + ks * 16 + 2 * t;
+                mma_16816(sc[n], qa[ks], *reinterpret_cast<const uint32_t*>(kp), *reinterpret_cast<const uint32_t*>(kp + 8));
+            }
+        }
+        // mask + online softmax (rows i0 and i1; this thread holds keys j0 + 8n + 2t, +1)
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int j = j0 + n * 8 + 2 * t + e;
+                if (j > i0 || j < lo0) sc[n][e] = -INFINITY;
+                if (j > i1 || j < lo1) sc[n][2 + e] = -INFINITY;
+                mx0 = fmaxf(mx0, sc[n][e]);
+                mx1 = fmaxf(mx1, sc[n][2 + e]);
+            }
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+        // rows with no visible key in this tile (and none before) keep m = -inf: use 0 as the reference to avoid inf - inf
+        const float ref0 = mn0 == -INFINITY ? 0.f : mn0, ref1 = mn1 == -INFINITY ? 0.f : mn1;
+        const float corr0 = __expf(m0 - ref0), corr1 = __expf(m1 - ref1);   // exp(-inf) = 0 on the first visible tile
+        float ps0 = 0.f, ps1 = 0.f;
+        uint32_t pa[4][4];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            const float p00 = __expf(sc[n][0] - ref0), p01 = __expf(sc[n][1] - ref0);
+            const float p10 = __expf(sc[n][2] - ref1), p11 = __expf(sc[n][3] - ref1);
+            ps0 += p00 + p01; ps1 += p10 + p11;
+            // score fragment of key n-tile n -> A fragment of key k-step n/2 (low half: n even, high half: n odd)
+            pa[n >> 1][(n & 1) * 2 + 0] = pack_h2(p00, p01);
+            pa[n >> 1][(n & 1) * 2 + 1] = pack_h2(p10, p11);
+        }
+        ps0 += __shfl_xor_sync(0xffffffffu, ps0, 1); ps0 += __shfl_xor_sync(0xffffffffu, ps0, 2);
+        ps1 += __shfl_xor_sync(0xffffffffu, ps1, 1); ps1 += __shfl_xor_sync(0xffffffffu, ps1, 2);
+        l0 = l0 * corr0 + ps0; l1 = l1 * corr1 + ps1;
+        m0 = mn0; m1 = mn1;
+        // O = O * corr + P V
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            o[n][0] *= corr0; o[n][1] *= corr0; o[n][2] *= corr1; o[n][3] *= corr1;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const __half* vp = sVt + (n * 8 + g) * PF_PITCH + ks * 16 + 2 * t;
+                mma_16816(o[n], pa[ks], *reinterpret_cast<const uint32_t*>(vp), *reinterpret_cast<const uint32_t*>(vp + 8));
+            }
+        }
+    }
+    // normalise and store (fp16 operand rows of the o_proj GEMM)
+    const float inv0 = l0 > 0.f ? 1.f / l0 : 0.f, inv1 = l1 > 0.f ? 1.f / l1 : 0.f;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+        const int d = n * 8 + 2 * t;
+        if (i0 < L0) *reinterpret_cast<uint32_t*>(out + ((long long)b * L0 + i0) * H + h * HEAD_DIM + d) = pack_h2(o[n][0] * inv0, o[n][1] * inv0);
+        if (i1 < L0) *reinterpret_cast<uint32_t*>(out + ((long long)b * L0 + i1) * H + h * HEAD_DIM + d) = pack_h2(o[n][2] * inv1, o[n][3] * inv1);
+    }
+}
+
 // x_last[b] = x[b][L0-1]  (only the last prompt position feeds the heads, gpt.py:442)
 __global__ void k_gather_last(const float* __restrict__ x, float* __restrict__ out, int L0, int H) {
     const int b = blockIdx.x;
