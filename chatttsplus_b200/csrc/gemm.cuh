@@ -332,7 +332,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     float v0, v1, v2, v3;
                     if (XNORM) {
                         ssacc[rr] += a4.x * a4.x + a4.y * a4.y + a4.z * a4.z + a4.w * a4.w;
-                        v0 = a4.x * w4.x; v1 = a4.y * w4.y; v2 = a4.z * w4.z; v3 = a4.w * w4.w;
+                        // un-normalised operand: saturate instead of overflowing fp16 should a checkpoint carry a massive activation
+                        v0 = fminf(fmaxf(a4.x * w4.x, -65504.f), 65504.f); v1 = fminf(fmaxf(a4.y * w4.y, -65504.f), 65504.f);
+                        v2 = fminf(fmaxf(a4.z * w4.z, -65504.f), 65504.f); v3 = fminf(fmaxf(a4.w * w4.w, -65504.f), 65504.f);
                     } else {
                         const float4 u4 = *reinterpret_cast<const float4*>(xt + BN * GEMM_BK + r * GEMM_BK + c16 * 4);
                         const float q = rf[rr];
