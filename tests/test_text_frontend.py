@@ -62,3 +62,28 @@ def test_split_and_merge_flow():
     assert T.merge_short_texts(["a", "b"]) == ["a [uv_break] b [uv_break] "]
     assert T.merge_short_texts(["x" * 40, "tail"]) == ["x" * 40 + " [uv_break] tail [uv_break] "]
     assert T.merge_short_texts(["x" * 20, "y" * 20, "z" * 40]) == ["x" * 20 + " [uv_break] ", "y" * 20 + " [uv_break] ", "z" * 40]
+
+
+def test_prompt_audio_loader_reads_pcm_wav_without_codec_backend(tmp_path):
+    """speaker_audio_path loading (chattts_plus_pipeline.py:495-498): torchaudio.load needs an optional codec package; PCM WAV files
+    are read with the standard library, resampled to 24 kHz and averaged over channels."""
+    import wave
+    import numpy as np
+    import torch
+    from chatttsplus_b200.pipeline import ChatTTSPlusPipeline
+    t = np.arange(8000) / 8000.0
+    left = (np.sin(2 * np.pi * 220 * t) * 12000).astype("<i2")
+    right = (np.sin(2 * np.pi * 330 * t) * 8000).astype("<i2")
+    p = str(tmp_path / "stereo8k.wav")
+    with wave.open(p, "wb") as f:
+        f.setnchannels(2); f.setsampwidth(2); f.setframerate(8000)
+        f.writeframes(np.stack([left, right], 1).reshape(-1).tobytes())
+    wav = ChatTTSPlusPipeline._load_audio_24k(p)
+    assert wav.shape == (24000,) and wav.dtype == torch.float32
+    assert 0.1 < float(wav.abs().max()) < 0.45                     # mean of the two channels, int16 full scale = 1.0
+    p8 = str(tmp_path / "mono8bit.wav")
+    with wave.open(p8, "wb") as f:
+        f.setnchannels(1); f.setsampwidth(1); f.setframerate(24000)
+        f.writeframes((np.sin(2 * np.pi * 100 * np.arange(2400) / 24000.0) * 100 + 128).astype(np.uint8).tobytes())
+    w8 = ChatTTSPlusPipeline._load_audio_24k(p8)
+    assert w8.shape == (2400,) and abs(float(w8.mean())) < 0.05
