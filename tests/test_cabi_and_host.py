@@ -61,6 +61,11 @@ def test_reference_signatures_are_kept():
     assert (p.prompt, p.temperature, p.repetition_penalty, p.max_new_token, p.top_P, p.top_K) == ("[speed_5]", 0.3, 1.05, 2048, 0.7, 20)
     assert os.path.isabs(constants.CHECKPOINT_DIR)
     assert all(hasattr(models, n) for n in ("GPT", "DVAE", "Tokenizer"))
+    # the text front end and the zero-shot prompt hooks keep the reference's module paths and method names too
+    from chattts_plus.commons import norm, text_utils
+    assert callable(text_utils.split_text) and callable(text_utils.num2text) and callable(norm.Normalizer(None))
+    assert list(inspect.signature(ChatTTSPlusPipeline.sample_audio_speaker).parameters) == ["self", "wav"]
+    assert "mode" in inspect.signature(models.DVAE.__call__).parameters
 
 
 def test_config_shim_matches_reference_keys():
