@@ -2,8 +2,7 @@
 // C-ABI entry points are declared in include/ctp.h (each cites the reference interface it replaces).
 #include "gemm.cuh"
 #include "gpt_kernels.cuh"
-#include "decode_gemm.cuh"
-#include "step_kernel.cuh"
+#include "layer_kernel.cuh"
 
 #include <map>
 #include <math.h>
@@ -67,51 +66,27 @@ struct ctp_gpt {
     std::map<GraphKey, long long> graph_nodes;
     cudaStream_t cap_stream = nullptr;
 
-    // fused persistent step kernel (v1): packed weights, step buffers, grid-barrier state
-    __half* wqkv_p = nullptr; __half* wo_p = nullptr; __half* wgu_p = nullptr; __half* wdn_p = nullptr; __half* whead_p = nullptr;
-    float* qbuf = nullptr; __half* attn_p = nullptr; __half* h_p = nullptr;
-    unsigned long long* bar = nullptr;   // [0] arrivals counter, [1] epoch (arrivals completed by previous launches)
-    int sm_count = 0, step_smem = 0, ring_slots = 0;
-    bool use_pdl = true;     // programmatic dependent launch between the kernels of the decode step graph (CTP_PDL=0 disables)
-    // ---- cluster decode path (decode_gemm.cuh): split-K reduced through distributed shared memory, no L2 atomics ----------
+    int sm_count = 0;
+    bool use_pdl = true;       // programmatic dependent launch between the kernels of the decode step graph (CTP_PDL=0 disables)
     bool fuse_norm = true;     // RMSNorm folded into the QKV / gate|up GEMMs (XNORM kernel); CTP_FUSE_NORM=0: stand-alone norm kernels
+    bool use_chain = true;     // layer-chain kernel (layer_kernel.cuh): o_proj -> gate|up -> down -> next q|k|v in ONE launch per layer;
+                               // CTP_DECODE=ops selects one launch per GEMM (five kernels per layer)
     CUtensorMap x_map{};       // fp32 map over the first 64 rows of the residual stream
     CUtensorMap gu_map{};      // fp32 map over the decode gate|up accumulator
     // decode only, re-armable scratch: ss1[64] | ss2[64] | gate|up accumulator [64][2I].  ss1 / ss2 = sum(x^2) per token row as seen by
-    // the QKV / gate|up GEMM (input / post-attention RMSNorm folded in); ss1 is re-armed by o_proj, ss2 and gate|up by the next QKV GEMM
+    // the QKV / gate|up GEMM (input / post-attention RMSNorm folded in)
     float* dec_gu = nullptr;
     float* ss1() const { return dec_gu; }
     float* ss2() const { return dec_gu + 64; }
     float* gu_acc() const { return dec_gu + 128; }
-    bool attn_tma = true;      // TMA-staged decode attention (CTP_ATTN=ldg selects the per-thread-load kernel)
-    bool use_cluster = false;  // CTP_DECODE_GEMM=cluster: split-K reduced through DSMEM inside a thread-block cluster, 5 kernels per layer.
-                               // Parity-green but slower than the RED split-K path on B200 today (profiles/README.md), so opt-in.
-    bool kv_prefetch = true;   // the gate|up GEMM warms L2 with the next layer's K/V streams (CTP_KV_PREFETCH=0 disables)
-    unsigned long long kvpf_cap = 96 * 1024;   // per-stream prefetch cap in bytes (CTP_KV_PREFETCH_CAP, KiB)
-    int s_qkv = 8, s_o = 8, s_gu = 4, s_dn = 8;   // cluster sizes = split-K factors (CTP_S_QKV / CTP_S_O / CTP_S_GU / CTP_S_DN)
+    unsigned int* chain_flags = nullptr;   // layer-chain kernel: [0..2] phase counters, [3] epoch (zeroed by every prefill)
+    int chain_grid = 0;                    // CTAs of the layer-chain kernel (0: shape / device not eligible)
+    LkPhase chain_ph[4]{};
     int attn_cta_target = 296;   // split the KV range until B*heads*nsplit reaches this many CTAs (CTP_ATTN_CTAS)
-    float* dec_buf = nullptr;    // one block: qkv [64][3H] | gate|up [64][2I] | ssA [8][64] | ssB [8][64]   (plain-stored, never accumulated)
-    float* qkv_dec() const { return dec_buf; }
-    float* gu_dec() const { return dec_buf + (size_t)64 * 3 * cfg.hidden; }
-    float* ss_a() const { return gu_dec() + (size_t)64 * 2 * cfg.inter; }   // sum(x^2) partials of the rows input_layernorm sees (written by down_proj)
-    float* ss_b() const { return ss_a() + 8 * 64; }                          // ... post_attention_layernorm sees (written by o_proj)
     // bring-up: in-graph timeline (CTP_TRACE=1): one 8-stamp record per kernel of the step graph, in launch order
     unsigned long long* trace = nullptr;
     int trace_n = 0;
     unsigned long long* trace_rec() { return trace ? trace + 8 * (size_t)(trace_n++ % 256) : nullptr; }
-    bool fused_ok = false;
-    bool use_fused = false;  // measured (profiles/README.md): the per-op graph path is faster today; CTP_DECODE_IMPL=fused selects the fused kernel
-    // lanes: the batch is split into K contiguous row slices, each running its own fused-step kernel on its own stream over
-    // sm_count/K SMs.  The fused step is a latency chain (DRAM 8 %, issue-active 16 % at K=1, profiles/README.md): independent
-    // lanes overlap each other's grid barriers and dependent sequences.
-    static constexpr int MAX_LANES = 8;
-    int n_lanes = 1;
-    struct Lane {
-        float* x = nullptr; float* q = nullptr; __half* attn_p = nullptr; __half* h_p = nullptr;
-        unsigned long long* bar = nullptr; GenState* st = nullptr; GenState* st_pin = nullptr;
-        cudaStream_t stream = nullptr; cudaEvent_t done = nullptr;
-    } lanes[MAX_LANES];
-    cudaEvent_t fork_ev = nullptr;
 
     // host mirror of the generation state
     int B = 0, cur_len = 0, step = 0, max_new = 0;
@@ -202,91 +177,44 @@ extern "C" ctp_status ctp_gpt_create(ctp_gpt** out, const ctp_gpt_cfg* cfg) {
         for (int i = 0; i < 32; ++i) f[i] = 1.0f / powf(cfg->rope_theta, (float)(2 * i) / (float)HEAD_DIM);
         CK(cudaMemcpy(h->inv_freq, f, sizeof(f), cudaMemcpyHostToDevice));
     }
-    {   // fused step kernel resources
+    {   // decode-path resources and bring-up switches (read once, here)
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, dev));
         h->sm_count = prop.multiProcessorCount;
         const int I = cfg->inter;
-        const int areg = (H / 64) * A_KB_BYTES + DBUF_BYTES;
-        const int fixed = areg + 512 + 1024;
-        int S = ((int)prop.sharedMemPerBlockOptin - fixed) / SLOT_BYTES;
-        if (S > MAX_RING) S = MAX_RING;
-        h->ring_slots = S;
-        h->step_smem = S * SLOT_BYTES + fixed;
-        h->fused_ok = (S >= 7) && (I % 192 == 0) && (H % 64 == 0) && cfg->num_vq <= 4 && cfg->num_audio <= 640 && mb <= 32;
-        if (const char* e = getenv("CTP_DECODE_IMPL")) h->use_fused = (strcmp(e, "fused") == 0);
         if (const char* e = getenv("CTP_PDL")) h->use_pdl = atoi(e) != 0;
-        if (const char* e = getenv("CTP_DECODE_GEMM")) h->use_cluster = (strcmp(e, "cluster") == 0);
-        if (const char* e = getenv("CTP_ATTN")) h->attn_tma = (strcmp(e, "ldg") != 0);
         if (const char* e = getenv("CTP_FUSE_NORM")) h->fuse_norm = atoi(e) != 0;
-        CK(cudaMalloc(&h->dec_gu, sizeof(float) * (128 + (size_t)64 * 2 * cfg->inter)));
-        CK(cudaMemset(h->dec_gu, 0, sizeof(float) * (128 + (size_t)64 * 2 * cfg->inter)));
-
-        CK(cudaFuncSetAttribute(k_attn_decode_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-        if (const char* e = getenv("CTP_KV_PREFETCH")) h->kv_prefetch = atoi(e) != 0;
-        if (const char* e = getenv("CTP_KV_PREFETCH_CAP")) h->kvpf_cap = (unsigned long long)atoi(e) * 1024ULL;
+        if (const char* e = getenv("CTP_DECODE")) h->use_chain = (strcmp(e, "ops") != 0);
         if (const char* e = getenv("CTP_ATTN_CTAS")) h->attn_cta_target = atoi(e);
-        if (const char* e = getenv("CTP_S_QKV")) h->s_qkv = atoi(e);
-        if (const char* e = getenv("CTP_S_O")) h->s_o = atoi(e);
-        if (const char* e = getenv("CTP_S_GU")) h->s_gu = atoi(e);
-        if (const char* e = getenv("CTP_S_DN")) h->s_dn = atoi(e);
-        for (int* sp : {&h->s_qkv, &h->s_o, &h->s_gu, &h->s_dn}) {   // cluster sizes: powers of two up to 16
-            int v = 1;
-            while (v * 2 <= *sp && v < 16) v *= 2;
-            *sp = v;
-        }
-        if (H % 128 != 0 || (2 * cfg->inter) % 128 != 0) h->use_cluster = false;
-        {
-            const size_t n = (size_t)64 * 3 * H + (size_t)64 * 2 * cfg->inter + 2 * 8 * 64;
-            CK(cudaMalloc(&h->dec_buf, sizeof(float) * n));
-            CK(cudaMemset(h->dec_buf, 0, sizeof(float) * n));
-            CK(cudaFuncSetAttribute(k_dec_gemm<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM));
-            CK(cudaFuncSetAttribute(k_dec_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM));
-            CK(cudaFuncSetAttribute(k_dec_gemm<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM));
-            CK(cudaFuncSetAttribute(k_dec_gemm<0>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-            CK(cudaFuncSetAttribute(k_dec_gemm<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-            CK(cudaFuncSetAttribute(k_dec_gemm<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        }
+        CK(cudaMalloc(&h->dec_gu, sizeof(float) * (128 + (size_t)64 * 2 * I)));
+        CK(cudaMemset(h->dec_gu, 0, sizeof(float) * (128 + (size_t)64 * 2 * I)));
+        CK(cudaMalloc(&h->chain_flags, sizeof(unsigned int) * 4));
+        CK(cudaMemset(h->chain_flags, 0, sizeof(unsigned int) * 4));
+        CK(cudaFuncSetAttribute(k_attn_decode_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+        CK(cudaFuncSetAttribute(k_layer_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, LK_SMEM));
         if (const char* e = getenv("CTP_TRACE")) if (atoi(e)) {
             CK(cudaMalloc(&h->trace, sizeof(unsigned long long) * 8 * 256));
             CK(cudaMemset(h->trace, 0, sizeof(unsigned long long) * 8 * 256));
         }
-        if (h->fused_ok) {
-            CK(cudaFuncSetAttribute(k_decode_step, cudaFuncAttributeMaxDynamicSharedMemorySize, h->step_smem));
-            const size_t L = cfg->n_layers;
-            const size_t F16 = ((size_t)cfg->num_vq * cfg->num_audio + 15) / 16 * 16;
-            CK(cudaMalloc(&h->wqkv_p, sizeof(__half) * L * 3 * H * H));
-            CK(cudaMalloc(&h->wo_p, sizeof(__half) * L * H * H));
-            CK(cudaMalloc(&h->wgu_p, sizeof(__half) * L * 2 * I * H));
-            CK(cudaMalloc(&h->wdn_p, sizeof(__half) * L * H * I));
-            CK(cudaMalloc(&h->whead_p, sizeof(__half) * F16 * H));
-            CK(cudaMalloc(&h->qbuf, sizeof(float) * 32 * H));
-            CK(cudaMalloc(&h->attn_p, sizeof(__half) * 32 * H + 65536));
-            CK(cudaMalloc(&h->h_p, sizeof(__half) * 32 * I + 65536));
-            CK(cudaMemset(h->attn_p, 0, sizeof(__half) * 32 * H + 65536));
-            CK(cudaMemset(h->h_p, 0, sizeof(__half) * 32 * I + 65536));
-            CK(cudaMalloc(&h->bar, sizeof(unsigned long long) * 2));
-            CK(cudaMemset(h->bar, 0, sizeof(unsigned long long) * 2));
-            h->n_lanes = 1;
-            if (const char* e = getenv("CTP_LANES")) h->n_lanes = atoi(e);
-            if (h->n_lanes < 1) h->n_lanes = 1;
-            if (h->n_lanes > ctp_gpt::MAX_LANES) h->n_lanes = ctp_gpt::MAX_LANES;
-            CK(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
-            for (int k = 0; k < h->n_lanes; ++k) {
-                ctp_gpt::Lane& ln = h->lanes[k];
-                CK(cudaMalloc(&ln.x, sizeof(float) * 32 * H));
-                CK(cudaMalloc(&ln.q, sizeof(float) * 32 * H));
-                CK(cudaMalloc(&ln.attn_p, sizeof(__half) * 32 * H));
-                CK(cudaMalloc(&ln.h_p, sizeof(__half) * 32 * I));
-                CK(cudaMemset(ln.attn_p, 0, sizeof(__half) * 32 * H));
-                CK(cudaMemset(ln.h_p, 0, sizeof(__half) * 32 * I));
-                CK(cudaMalloc(&ln.bar, sizeof(unsigned long long) * 2));
-                CK(cudaMemset(ln.bar, 0, sizeof(unsigned long long) * 2));
-                CK(cudaMalloc(&ln.st, sizeof(GenState)));
-                CK(cudaMallocHost(&ln.st_pin, sizeof(GenState)));
-                CK(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
-                CK(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+        // layer-chain plan: one (128-row weight tile, k-slice) unit per CTA and GEMM; every CTA must be resident (one per SM)
+        h->chain_grid = 0;
+        if (H % 128 == 0 && (2 * I) % 128 == 0 && I % 64 == 0 && (int)prop.sharedMemPerBlockOptin >= LK_SMEM) {
+            const int G = h->sm_count;
+            const int mt[4] = {H / 128, 2 * I / 128, H / 128, 3 * H / 128};
+            const int kb[4] = {H / 64, H / 64, I / 64, H / 64};
+            const int cap[4] = {LK_MAX_KB, LK_MAX_KB, LK_MAX_KB / 2, LK_MAX_KB};   // phase 2 lands a gate and an up tile per k-block
+            int slots = 0;
+            bool ok = true;
+            for (int p = 0; p < 4; ++p) {
+                int sp = mt[p] <= G ? G / mt[p] : 0;
+                if (sp > kb[p]) sp = kb[p];
+                if (sp < 1) { ok = false; break; }
+                const int kmax = (kb[p] + sp - 1) / sp;
+                if (kmax > cap[p]) { ok = false; break; }
+                h->chain_ph[p].m_tiles = mt[p]; h->chain_ph[p].k_blocks = kb[p]; h->chain_ph[p].splits = sp; h->chain_ph[p].w_slot0 = slots;
+                slots += kmax;
             }
+            if (ok && slots <= LK_W_SLOTS) h->chain_grid = G;
         }
     }
 #undef CK
@@ -300,19 +228,9 @@ extern "C" void ctp_gpt_destroy(ctp_gpt* h) {
     if (!h) return;
     for (auto& kvp : h->graphs) cudaGraphExecDestroy(kvp.second);
     cudaFree(h->x); cudaFree(h->xn); cudaFree(h->acc_qkv); cudaFree(h->attn); cudaFree(h->acc_gu); cudaFree(h->hmid);
-    cudaFree(h->dec_buf); cudaFree(h->trace); cudaFree(h->dec_gu);
+    cudaFree(h->trace); cudaFree(h->dec_gu); cudaFree(h->chain_flags);
     cudaFree(h->x_last); cudaFree(h->hidden); cudaFree(h->logits); cudaFree(h->kv); cudaFree(h->attn_part);
     cudaFree(h->attn_cnt); cudaFree(h->pad_len); cudaFree(h->inv_freq); cudaFree(h->st);
-    cudaFree(h->wqkv_p); cudaFree(h->wo_p); cudaFree(h->wgu_p); cudaFree(h->wdn_p); cudaFree(h->whead_p);
-    cudaFree(h->qbuf); cudaFree(h->attn_p); cudaFree(h->h_p); cudaFree(h->bar);
-    for (int k = 0; k < ctp_gpt::MAX_LANES; ++k) {
-        ctp_gpt::Lane& ln = h->lanes[k];
-        cudaFree(ln.x); cudaFree(ln.q); cudaFree(ln.attn_p); cudaFree(ln.h_p); cudaFree(ln.bar); cudaFree(ln.st);
-        if (ln.st_pin) cudaFreeHost(ln.st_pin);
-        if (ln.stream) cudaStreamDestroy(ln.stream);
-        if (ln.done) cudaEventDestroy(ln.done);
-    }
-    if (h->fork_ev) cudaEventDestroy(h->fork_ev);
     if (h->st_pin) cudaFreeHost(h->st_pin);
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     delete h;
@@ -342,28 +260,6 @@ extern "C" ctp_status ctp_gpt_bind_weights(ctp_gpt* h, const ctp_gpt_weights* w)
     if (w->head_text && w->emb_text) {
         if ((st = make_tmap_kmajor(&h->head_text_map, w->head_text, (long long)c.num_text, H, H, GEMM_BM))) return (ctp_status)st;
         h->have_head_text = true;
-    }
-    if (h->fused_ok) {   // per-item pre-swizzled blobs for the fused step kernel (one bulk copy fills a ring slot)
-        const int nH = c.n_heads, nkbH = (int)(H / 64), nkbI = (int)(I / 64);
-        for (int l = 0; l < c.n_layers; ++l) {
-            const __half* wqkv = (const __half*)w->wqkv + (size_t)l * 3 * H * H;
-            const __half* wo = (const __half*)w->wo + (size_t)l * H * H;
-            const __half* wgu = (const __half*)w->wgu + (size_t)l * 2 * I * H;
-            const __half* wd = (const __half*)w->wdown + (size_t)l * H * I;
-            int n_items = 3 * nH * 4;
-            k_pack_weights<<<n_items * nkbH, 128>>>(wqkv, h->wqkv_p + (size_t)l * 3 * H * H, PACK_QKV, (int)(3 * H), (int)H, nH, (int)I, n_items, 16, nkbH, 1);
-            n_items = (int)(H / 16);
-            k_pack_weights<<<n_items * nkbH, 128>>>(wo, h->wo_p + (size_t)l * H * H, PACK_PLAIN16, (int)H, (int)H, nH, (int)I, n_items, 16, nkbH, 1);
-            n_items = (int)(I / 24);
-            k_pack_weights<<<n_items * nkbH, 384>>>(wgu, h->wgu_p + (size_t)l * 2 * I * H, PACK_GU, (int)(2 * I), (int)H, nH, (int)I, n_items, 48, nkbH, 1);
-            n_items = (int)(H / 16) * DN_KSPLIT;
-            k_pack_weights<<<n_items * (nkbI / DN_KSPLIT), 128>>>(wd, h->wdn_p + (size_t)l * H * I, PACK_DN, (int)H, (int)I, nH, (int)I, n_items, 16, nkbI / DN_KSPLIT, DN_KSPLIT);
-        }
-        const int F = c.num_vq * c.num_audio;
-        const int n_items = (F + 15) / 16;
-        k_pack_weights<<<n_items * nkbH, 128>>>((const __half*)w->head_code, h->whead_p, PACK_PLAIN16, F, (int)H, nH, (int)I, n_items, 16, nkbH, 1);
-        CTP_CUDA_OK(cudaGetLastError());
-        CTP_CUDA_OK(cudaDeviceSynchronize());
     }
     h->w = *w;
     h->bound = true;
@@ -415,127 +311,66 @@ static int launch_heads(ctp_gpt* h, int B, cudaStream_t s, bool pdl = false) {
     return gemm_launch_maps(h->text_mode ? h->head_text_map : h->head_map, am.xn, F, B, c.hidden, bn, split_for(c.hidden / 64, m_tiles), e, s, nullptr, 0, pdl);
 }
 
-// bring-up hook (not in include/ctp.h): device buffer [n_cta][128][2] of clock64 stamps around every grid barrier
-static long long* g_step_dbg = nullptr;
-extern "C" __attribute__((visibility("default"))) void ctp_debug_step_stamps(long long* buf) { g_step_dbg = buf; }
-
-// Fused path: ONE cooperative launch per decode step (step_kernel.cuh).
-static int run_decode_fused_lane(ctp_gpt* h, int b0, int Bk, int grid, float* x, float* q, __half* attn_p, __half* h_p,
-                                 unsigned long long* bar, GenState* st, const int* ids_ext, int do_sample, cudaStream_t s);
-
-static int run_decode_fused(ctp_gpt* h, int B, const int* ids_ext, int do_sample, cudaStream_t s) {
-    return run_decode_fused_lane(h, 0, B, h->sm_count, h->x, h->qbuf, h->attn_p, h->h_p, h->bar, h->st, ids_ext, do_sample, s);
-}
-
-static int run_decode_fused_lane(ctp_gpt* h, int b0, int B, int grid, float* x, float* q, __half* attn_p, __half* h_p,
-                                 unsigned long long* bar, GenState* st, const int* ids_ext, int do_sample, cudaStream_t s) {
-    const ctp_gpt_cfg& c = h->cfg;
-    StepParams p{};
-    p.b0 = b0;
-    p.L = c.n_layers; p.H = c.hidden; p.nH = c.n_heads; p.I = c.inter; p.num_vq = c.num_vq; p.num_audio = c.num_audio; p.B = B;
-    p.max_seq = c.max_seq; p.eps = c.rms_eps; p.ring_slots = h->ring_slots; p.do_sample = do_sample;
-    p.wqkv_p = h->wqkv_p; p.wo_p = h->wo_p; p.wgu_p = h->wgu_p; p.wdn_p = h->wdn_p; p.whead_p = h->whead_p;
-    p.ln1 = h->w.ln1; p.ln2 = h->w.ln2; p.norm_f = h->w.norm_f; p.emb_code = (const __half*)h->w.emb_code;
-    p.x = x; p.q = q; p.attn_p = attn_p; p.h_p = h_p; p.kv = h->kv; p.kv_plane = (long long)h->kv_plane_elems();
-    p.logits = h->logits; p.hidden = h->hidden; p.st = st; p.pad_len = h->pad_len; p.inv_freq = h->inv_freq; p.ids_ext = ids_ext;
-    p.bar = bar; p.bar_epoch = bar + 1; p.dbg = g_step_dbg;
-    void* args[] = {&p};
-    cudaError_t e;
-    if (grid == h->sm_count) {
-        e = cudaLaunchCooperativeKernel((void*)k_decode_step, dim3(grid), dim3(STEP_THREADS), args, (size_t)h->step_smem, s);
-    } else {
-        // lanes: cooperative launches do not overlap each other; a plain launch is safe because the lanes together never exceed
-        // one CTA per SM (the kernel's shared-memory footprint allows exactly one), so every CTA of every lane is resident
-        k_decode_step<<<grid, STEP_THREADS, (size_t)h->step_smem, s>>>(p);
-        e = cudaGetLastError();
-    }
-    ctp_count_launch();
-    if (e != cudaSuccess) { ctp_set_error("fused decode step launch failed: %s", cudaGetErrorString(e)); return CTP_ERR_CUDA; }
-    return CTP_OK;
-}
-
 // One decode trunk step for B sequences (ids_ext == nullptr -> codes of the previous sample step).
 #define CTP_LAUNCH(kern, grid, block, smem, ...) do { cudaError_t _le = launch_k(kern, grid, block, (size_t)(smem), s, pdl, __VA_ARGS__); ctp_count_launch(); if (_le == cudaSuccess) _le = cudaGetLastError(); if (_le != cudaSuccess) { ctp_set_error("%s:%d launch %s: %s", __FILE__, __LINE__, #kern, cudaGetErrorString(_le)); return CTP_ERR_CUDA; } } while (0)
 
-// ---- cluster decode path -------------------------------------------------------------------------------------------------
-// Per layer FIVE kernels (the reference runs ~40, llama.py:689-749): QKV GEMM (input_layernorm folded) -> attention (RoPE, KV
-// append, softmax.V) -> o_proj GEMM (+ residual) -> gate|up GEMM (post_attention_layernorm folded) -> down GEMM (SiLU gate
-// folded, + residual).  Every GEMM reduces its split-K inside a thread-block cluster and plain-stores final values.
-#define CTP_DEC_GEMM(MODE, tmA_, tmB_, args_, m_tiles_, S_) do { cudaError_t _le = launch_dec_gemm<MODE>(tmA_, tmB_, args_, m_tiles_, S_, s, pdl); ctp_count_launch(); if (_le == cudaSuccess) _le = cudaGetLastError(); if (_le != cudaSuccess) { ctp_set_error("%s:%d decode gemm launch: %s", __FILE__, __LINE__, cudaGetErrorString(_le)); return CTP_ERR_CUDA; } } while (0)
-
-static void set_kv_prefetch(ctp_gpt* h, DecGemmArgs& g, int layer, int B) {
+static int launch_attn(ctp_gpt* h, int l, int B, int nsplit, bool row_factor, cudaStream_t s, bool pdl, bool prefetch_chain) {
     const ctp_gpt_cfg& c = h->cfg;
-    g.kvpf_base = h->kplane(layer); g.kvpf_plane = sizeof(__half) * h->kv_plane_elems();
-    g.kvpf_stream = sizeof(__half) * (size_t)c.max_seq * HEAD_DIM; g.kvpf_streams = B * c.n_heads;
-    g.kvpf_len = &h->st->cur_len; g.kvpf_slot_bytes = HEAD_DIM * (int)sizeof(__half); g.kvpf_cap = h->kvpf_cap;
+    const size_t H = c.hidden, I = c.inter;
+    AttnDecArgs aa{};
+    aa.qkv = h->acc_qkv; aa.kcache = h->kplane(l); aa.vcache = h->vplane(l); aa.out = h->attn; aa.part = h->attn_part;
+    aa.counters = h->attn_cnt; aa.pad_len = h->pad_len; aa.st = h->st; aa.inv_freq = h->inv_freq;
+    aa.H = c.hidden; aa.nH = c.n_heads; aa.max_seq = c.max_seq; aa.eps = c.rms_eps;
+    if (row_factor) aa.ss = h->ss1();   // input_layernorm's row factor (llama.py:718), deferred from the QKV GEMM
+    if (prefetch_chain) {   // warm L2 with everything the layer-chain kernel behind this launch streams
+        aa.pf_ptr[0] = (const __half*)h->w.wo + (size_t)l * H * H;         aa.pf_bytes[0] = sizeof(__half) * H * H;
+        aa.pf_ptr[1] = (const __half*)h->w.wgu + (size_t)l * 2 * I * H;    aa.pf_bytes[1] = sizeof(__half) * 2 * I * H;
+        aa.pf_ptr[2] = (const __half*)h->w.wdown + (size_t)l * H * I;      aa.pf_bytes[2] = sizeof(__half) * H * I;
+        if (l + 1 < c.n_layers) { aa.pf_ptr[3] = (const __half*)h->w.wqkv + (size_t)(l + 1) * 3 * H * H; aa.pf_bytes[3] = sizeof(__half) * 3 * H * H; }
+        else { aa.pf_ptr[3] = h->text_mode ? h->w.head_text : h->w.head_code; aa.pf_bytes[3] = sizeof(__half) * H * (size_t)(h->text_mode ? c.num_text : c.num_vq * c.num_audio); }
+    }
+    aa.trace = h->trace_rec();
+    CTP_LAUNCH(k_attn_decode_tma, dim3(c.n_heads, B, nsplit), dim3(AT_THREADS), AT_SMEM, aa);
+    return CTP_OK;
 }
 
-static int run_decode_trunk_cluster(ctp_gpt* h, int B, int nsplit, const int* ids_ext, cudaStream_t s) {
+// Layer-chain path (default, batch <= 32): per layer TWO launches — attention, then k_layer_chain (o_proj -> gate|up -> down ->
+// next layer's q|k|v; layer_kernel.cuh) — instead of five; 45 kernels per step at 20 layers.
+static int run_decode_trunk_chain(ctp_gpt* h, int B, int nsplit, const int* ids_ext, cudaStream_t s) {
     const ctp_gpt_cfg& c = h->cfg;
     const bool pdl = h->use_pdl;
     const int H = c.hidden, I = c.inter, L = c.n_layers;
-    const int mtH = H / DG_BM;
-    const ActMaps& am = h->act32;
-    const __half* wqkv = (const __half*)h->w.wqkv; const __half* wo = (const __half*)h->w.wo;
-    const __half* wgu = (const __half*)h->w.wgu; const __half* wdn = (const __half*)h->w.wdown;
-    h->trace_n = 0;
+    int st;
+    {   // layer 0: code-embedding front end + input_layernorm, then q|k|v as a stand-alone GEMM
+        NormArgs na{};
+        na.x = h->x; na.w = h->w.ln1; na.xn = h->xn; na.H = H; na.eps = c.rms_eps;
+        na.st = h->st; na.ids_ext = ids_ext; na.emb_code = (const __half*)h->w.emb_code; na.num_vq = c.num_vq; na.num_audio = c.num_audio;
+        na.emb_text = h->text_mode ? (const __half*)h->w.emb_text : nullptr;
+        na.trace = h->trace_rec();
+        CTP_LAUNCH(k_rmsnorm, dim3(B), dim3(256), 0, na);
+        GemmEpilogue e = epi_swap_atomic(h->acc_qkv, 3 * H, B, 3 * H);
+        if ((st = gemm_launch_maps(h->lmaps[0].wqkv, h->act32.xn, 3 * H, B, H, 32, split_for(H / 64, 3 * H / GEMM_BM), e, s, nullptr, 0, pdl,
+                                   nullptr, 0, h->trace_rec()))) return st;
+    }
     for (int l = 0; l < L; ++l) {
-        // layer 0 keeps the stand-alone RMSNorm kernel: it is also the code-embedding front end that writes the residual stream
-        const bool folded = l > 0;
-        if (!folded) {
-            NormArgs na{};
-            na.x = h->x; na.w = h->w.ln1; na.xn = h->xn; na.H = H; na.eps = c.rms_eps;
-            na.st = h->st; na.ids_ext = ids_ext; na.emb_code = (const __half*)h->w.emb_code; na.num_vq = c.num_vq; na.num_audio = c.num_audio;
-            na.emb_text = h->text_mode ? (const __half*)h->w.emb_text : nullptr;
-            na.trace = h->trace_rec();
-            CTP_LAUNCH(k_rmsnorm, dim3(B), dim3(256), 0, na);
-        }
-        {   // q,k,v projections as one GEMM (llama.py:619-621); input_layernorm (llama.py:718) folded: contracts x*w, attention applies the row factor
-            DecGemmArgs g{};
-            g.k_blocks = H / 64; g.T = B; g.out = h->qkv_dec(); g.ldo = 3 * H;
-            if (folded) { g.bsrc = h->x; g.ldbs = H; g.bw = h->w.ln1 + (size_t)l * H; }
-            g.pf_ptr = wo + (size_t)l * H * H; g.pf_bytes = sizeof(__half) * (size_t)H * H;
-            g.trace = h->trace_rec();
-            if (folded) CTP_DEC_GEMM(1, h->lmaps[l].wqkv, h->lmaps[l].wqkv, g, 3 * H / DG_BM, h->s_qkv);
-            else CTP_DEC_GEMM(0, h->lmaps[l].wqkv, am.xn, g, 3 * H / DG_BM, h->s_qkv);
-        }
-        AttnDecArgs aa{};
-        aa.qkv = h->qkv_dec(); aa.kcache = h->kplane(l); aa.vcache = h->vplane(l); aa.out = h->attn; aa.part = h->attn_part;
-        aa.counters = h->attn_cnt; aa.pad_len = h->pad_len; aa.st = h->st; aa.inv_freq = h->inv_freq;
-        aa.H = H; aa.nH = c.n_heads; aa.max_seq = c.max_seq; aa.rearm = 0; aa.eps = c.rms_eps;
-        if (folded) { aa.ss = h->ss_a(); aa.ss_parts = mtH; aa.ss_stride = 64; }
-        aa.trace = h->trace_rec();
-        if (h->attn_tma) CTP_LAUNCH(k_attn_decode_tma, dim3(c.n_heads, B, nsplit), dim3(AT_THREADS), AT_SMEM, aa);
-        else CTP_LAUNCH(k_attn_decode, dim3(c.n_heads, B, nsplit), dim3(128), 0, aa);
-        {   // o_proj + residual (llama.py:663-666,737): x = x + attn.Wo^T, plain-stored; leaves sum(x^2) partials for post_attention_layernorm
-            DecGemmArgs g{};
-            g.k_blocks = H / 64; g.T = B; g.out = h->x; g.ldo = H; g.residual = h->x; g.ldr = H;
-            g.ss_out = h->ss_b(); g.ss_out_stride = 64;
-            g.pf_ptr = wgu + (size_t)l * 2 * I * H; g.pf_bytes = sizeof(__half) * (size_t)2 * I * H;
-            g.trace = h->trace_rec();
-            CTP_DEC_GEMM(0, h->lmaps[l].wo, am.attn, g, mtH, h->s_o);
-        }
-        {   // gate_proj | up_proj (llama.py:214); post_attention_layernorm (llama.py:741) folded (row factor applied by the down GEMM's prologue)
-            DecGemmArgs g{};
-            g.k_blocks = H / 64; g.T = B; g.out = h->gu_dec(); g.ldo = 2 * I;
-            g.bsrc = h->x; g.ldbs = H; g.bw = h->w.ln2 + (size_t)l * H;
-            g.pf_ptr = wdn + (size_t)l * H * I; g.pf_bytes = sizeof(__half) * (size_t)H * I;
-            if (h->kv_prefetch && l + 1 < L) set_kv_prefetch(h, g, l + 1, B);
-            g.trace = h->trace_rec();
-            CTP_DEC_GEMM(1, h->lmaps[l].wgu, h->lmaps[l].wgu, g, 2 * I / DG_BM, h->s_gu);
-        }
-        {   // down_proj + residual (llama.py:214,745); silu(gate)*up folded into the token operand; leaves sum(x^2) partials for the next input_layernorm
-            DecGemmArgs g{};
-            g.k_blocks = I / 64; g.T = B; g.out = h->x; g.ldo = H; g.residual = h->x; g.ldr = H;
-            g.bsrc = h->gu_dec(); g.ldbs = 2 * I; g.bI = I;
-            g.ss_in = h->ss_b(); g.ss_parts = mtH; g.ss_stride = 64; g.ss_dim = (float)H; g.eps = c.rms_eps;
-            g.ss_out = h->ss_a(); g.ss_out_stride = 64;
-            if (l + 1 < L) { g.pf_ptr = wqkv + (size_t)(l + 1) * 3 * H * H; g.pf_bytes = sizeof(__half) * (size_t)3 * H * H; }
-            else { g.pf_ptr = h->w.head_code; g.pf_bytes = sizeof(__half) * (size_t)c.num_vq * c.num_audio * H; }
-            if (h->kv_prefetch && l + 1 == L) set_kv_prefetch(h, g, 0, B);   // the next step's first attention reads layer 0's streams
-            g.trace = h->trace_rec();
-            CTP_DEC_GEMM(2, h->lmaps[l].wdown, h->lmaps[l].wdown, g, mtH, h->s_dn);
-        }
+        if ((st = launch_attn(h, l, B, nsplit, l > 0, s, pdl, true))) return st;
+        LayerArgs a{};
+        for (int p = 0; p < 4; ++p) a.ph[p] = h->chain_ph[p];
+        a.ph[0].out = h->x; a.ph[0].ldo = H;                  // o_proj accumulated straight into the residual stream (llama.py:663-666,737)
+        a.ph[1].out = h->gu_acc(); a.ph[1].ldo = 2 * I;       // gate_proj | up_proj (llama.py:214), post_attention_layernorm (llama.py:741) folded
+        a.ph[2].out = h->x; a.ph[2].ldo = H;                  // down_proj + residual (llama.py:214,745), silu(gate)*up folded
+        a.ph[3].out = h->acc_qkv; a.ph[3].ldo = 3 * H;        // next layer's q,k,v (llama.py:619-621), its input_layernorm (llama.py:718) folded
+        a.n_phases = (l + 1 < L) ? 4 : 3;
+        a.T = B; a.I = I; a.ss_dim = (float)H; a.eps = c.rms_eps;
+        a.ln_post = h->w.ln2 + (size_t)l * H;
+        a.ln_next = h->w.ln1 + (size_t)(l + 1 < L ? l + 1 : l) * H;
+        a.ss1 = h->ss1(); a.ss2 = h->ss2();
+        a.rearm_ptr = h->ss2(); a.rearm_f4 = (unsigned long long)(64 + (size_t)B * 2 * I) / 4;
+        a.flags = h->chain_flags;
+        a.trace = h->trace_rec();
+        const LayerMaps& m = h->lmaps[l];
+        const CUtensorMap& next_qkv = h->lmaps[l + 1 < L ? l + 1 : l].wqkv;
+        CTP_LAUNCH(k_layer_chain, dim3(h->chain_grid), dim3(LK_THREADS), LK_SMEM, m.wo, m.wgu, m.wdown, next_qkv, h->act32.attn, h->x_map, h->gu_map, a);
     }
     return CTP_OK;
 }
@@ -548,16 +383,16 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
     const ActMaps& am = bn == 32 ? h->act32 : h->act64;
     int st;
     h->trace_n = 0;
-    const bool cluster = h->use_cluster && B <= 32;
-    if (cluster) {
-        if ((st = run_decode_trunk_cluster(h, B, nsplit, ids_ext, s))) return st;
+    // Batch <= 32: RMSNorm is folded into the QKV / gate|up GEMMs and silu(gate)*up into down_proj (in-kernel token operands).
+    const bool fuse = h->fuse_norm && B <= 32;
+    const bool chain = fuse && h->use_chain && h->chain_grid > 0;
+    if (chain) {
+        if ((st = run_decode_trunk_chain(h, B, nsplit, ids_ext, s))) return st;
     }
-    // Batch <= 32 with the TMA-staged attention: RMSNorm is folded into the QKV / gate|up GEMMs and silu(gate)*up into down_proj
-    // (in-kernel token operands, gemm.cuh XNORM / XSILU): FIVE kernels per layer instead of eight.
-    const bool fuse = h->fuse_norm && h->attn_tma && B <= 32;
     float* gu = fuse ? h->gu_acc() : h->acc_gu;
     const unsigned long long rearm_f4 = (unsigned long long)(64 + (size_t)B * 2 * I) / 4;   // ss2 | gate|up rows of the live batch (from ss2())
-    for (int l = 0; l < (cluster ? 0 : c.n_layers); ++l) {
+    // CTP_DECODE=ops (and batches of 33..64 rows, which use the 64-token N tile with stand-alone norm / SiLU kernels): one launch per op
+    for (int l = 0; l < (chain ? 0 : c.n_layers); ++l) {
         const bool f1 = fuse && l > 0;   // layer 0 keeps the norm kernel: it is also the code-embedding front end
         if (!f1) {
             NormArgs na{};
@@ -583,14 +418,7 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
             }
             if (st) return st;
         }
-        AttnDecArgs aa{};
-        aa.qkv = h->acc_qkv; aa.kcache = h->kplane(l); aa.vcache = h->vplane(l); aa.out = h->attn; aa.part = h->attn_part;
-        aa.counters = h->attn_cnt; aa.pad_len = h->pad_len; aa.st = h->st; aa.inv_freq = h->inv_freq;
-        aa.H = H; aa.nH = c.n_heads; aa.max_seq = c.max_seq; aa.rearm = 1; aa.eps = c.rms_eps;
-        if (f1) { aa.ss = h->ss1(); aa.ss_parts = 1; aa.ss_stride = 64; }   // input_layernorm's row factor (llama.py:718), deferred from the QKV GEMM
-        aa.trace = h->trace_rec();
-        if (h->attn_tma) CTP_LAUNCH(k_attn_decode_tma, dim3(c.n_heads, B, nsplit), dim3(AT_THREADS), AT_SMEM, aa);
-        else CTP_LAUNCH(k_attn_decode, dim3(c.n_heads, B, nsplit), dim3(128), 0, aa);
+        if ((st = launch_attn(h, l, B, nsplit, f1, s, pdl, false))) return st;
         {   // o_proj accumulated straight into the residual stream (llama.py:663-666,737)
             GemmEpilogue e = epi_swap_atomic(h->x, H, B, H);
             if ((st = gemm_launch_maps(h->lmaps[l].wo, am.attn, H, B, H, bn, split_for(H / 64, (H + GEMM_BM - 1) / GEMM_BM), e, s,
@@ -772,6 +600,7 @@ extern "C" ctp_status ctp_gpt_prefill(ctp_gpt* h, int32_t B, int32_t L0, const f
     CTP_CUDA_OK(cudaMemsetAsync(h->acc_qkv, 0, sizeof(float) * (size_t)c.max_batch * 3 * H, s));
     CTP_CUDA_OK(cudaMemsetAsync(h->acc_gu, 0, sizeof(float) * (size_t)c.max_batch * 2 * I, s));
     CTP_CUDA_OK(cudaMemsetAsync(h->dec_gu, 0, sizeof(float) * (128 + (size_t)64 * 2 * I), s));
+    CTP_CUDA_OK(cudaMemsetAsync(h->chain_flags, 0, sizeof(unsigned int) * 4, s));   // phase counters + epoch of the layer-chain kernel
     h->B = B; h->cur_len = L0; h->step = 0; h->max_new = bufs->max_new; h->have_bufs = true;
     return CTP_OK;
 }
@@ -780,9 +609,7 @@ extern "C" ctp_status ctp_gpt_decode_step(ctp_gpt* h, const int32_t* ids, ctp_st
     CTP_REQUIRE(h && h->bound && h->have_bufs, "decode_step: call prefill first");
     CTP_REQUIRE(h->cur_len + 1 <= h->cfg.max_seq, "decode_step: KV cache full (%d slots)", h->cfg.max_seq);
     CTP_REQUIRE(ids != nullptr || h->step >= 1, "decode_step: no sampled codes yet and no ids given");
-    int st;
-    if (h->fused_ok && h->use_fused && h->B <= 32 && !h->text_mode) st = run_decode_fused(h, h->B, ids, 0, (cudaStream_t)stream);
-    else st = run_decode_trunk(h, h->B, nsplit_for(h, h->B, h->cur_len + 1), ids, (cudaStream_t)stream);
+    int st = run_decode_trunk(h, h->B, nsplit_for(h, h->B, h->cur_len + 1), ids, (cudaStream_t)stream);
     if (st) return (ctp_status)st;
     h->cur_len += 1;
     return CTP_OK;
@@ -861,64 +688,8 @@ extern "C" ctp_status ctp_gpt_generate(ctp_gpt* h, const ctp_sample_cfg* cfg, in
     CTP_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     bool pending = false;
     h->st_pin->all_done = 0;
-    const bool fused = h->fused_ok && h->use_fused && h->B <= 32 && !h->text_mode;
-    int K = fused ? h->n_lanes : 1;
-    while (K > 1 && (h->B < K || h->sm_count / K < 8)) K /= 2;
-    if (fused && K > 1) {
-        // ---- K independent row slices, each with its own generation state, stream and share of the SMs
-        cudaEventDestroy(ev);
-        int b0s[ctp_gpt::MAX_LANES], bks[ctp_gpt::MAX_LANES];
-        for (int k = 0; k < K; ++k) { b0s[k] = (int)((long long)h->B * k / K); bks[k] = (int)((long long)h->B * (k + 1) / K) - b0s[k]; }
-        CTP_CUDA_OK(cudaMemcpyAsync(h->st_pin, h->st, sizeof(GenState), cudaMemcpyDeviceToHost, s));
-        CTP_CUDA_OK(cudaStreamSynchronize(s));
-        for (int k = 0; k < K; ++k) {
-            *h->lanes[k].st_pin = *h->st_pin;
-            h->lanes[k].st_pin->ticket = 0;
-            h->lanes[k].st_pin->all_done = 0;
-            CTP_CUDA_OK(cudaMemcpyAsync(h->lanes[k].st, h->lanes[k].st_pin, sizeof(GenState), cudaMemcpyHostToDevice, s));
-        }
-        CTP_CUDA_OK(cudaEventRecord(h->fork_ev, s));
-        for (int k = 0; k < K; ++k) CTP_CUDA_OK(cudaStreamWaitEvent(h->lanes[k].stream, h->fork_ev, 0));
-        const int grid = h->sm_count / K;
-        int launched = 0;
-        bool stop = false;
-        for (int it = 0; it < iters && !stop; ++it) {
-            for (int k = 0; k < K; ++k) {
-                ctp_gpt::Lane& ln = h->lanes[k];
-                if ((st = run_decode_fused_lane(h, b0s[k], bks[k], grid, ln.x, ln.q, ln.attn_p, ln.h_p, ln.bar, ln.st, nullptr, 1, ln.stream))) return (ctp_status)st;
-            }
-            ++launched;
-            if ((it + 1) % check_every == 0 && it + 1 < iters) {
-                // poll: every lane reports whether all of ITS rows have finished (small sync every check_every steps)
-                bool all = true;
-                for (int k = 0; k < K; ++k) {
-                    cudaMemcpyAsync(&h->lanes[k].st_pin->all_done, reinterpret_cast<char*>(h->lanes[k].st) + offsetof(GenState, all_done),
-                                    sizeof(int), cudaMemcpyDeviceToHost, h->lanes[k].stream);
-                }
-                for (int k = 0; k < K; ++k) { cudaStreamSynchronize(h->lanes[k].stream); all = all && h->lanes[k].st_pin->all_done; }
-                if (all) stop = true;
-            }
-        }
-        for (int k = 0; k < K; ++k) {
-            CTP_CUDA_OK(cudaEventRecord(h->lanes[k].done, h->lanes[k].stream));
-            CTP_CUDA_OK(cudaStreamWaitEvent(s, h->lanes[k].done, 0));
-        }
-        // fold the lane counters back into the handle's state (all lanes advanced by `launched` steps)
-        h->cur_len += launched; h->step += launched;
-        {
-            int vals[2] = {h->cur_len, h->step};
-            CTP_CUDA_OK(cudaMemcpyAsync(reinterpret_cast<char*>(h->st) + offsetof(GenState, cur_len), &vals[0], sizeof(int), cudaMemcpyHostToDevice, s));
-            CTP_CUDA_OK(cudaMemcpyAsync(reinterpret_cast<char*>(h->st) + offsetof(GenState, step), &vals[1], sizeof(int), cudaMemcpyHostToDevice, s));
-            CTP_CUDA_OK(cudaStreamSynchronize(s));
-        }
-        CTP_CUDA_OK(cudaGetLastError());
-        if (steps_done) *steps_done = launched;
-        return CTP_OK;
-    }
     for (int it = 0; it < iters; ++it) {
-        if (fused) {
-            if ((st = run_decode_fused(h, h->B, nullptr, 1, s))) { cudaEventDestroy(ev); return (ctp_status)st; }
-        } else {
+        {
             cudaGraphExec_t g;
             if ((st = get_graph(h, h->B, nsplit_for(h, h->B, h->cur_len + 1), &g))) { cudaEventDestroy(ev); return (ctp_status)st; }
             ctp_count_launch((int)h->graph_nodes[GraphKey{h->B, nsplit_for(h, h->B, h->cur_len + 1), h->text_mode}]);

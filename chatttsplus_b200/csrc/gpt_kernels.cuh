@@ -163,7 +163,7 @@ __global__ void k_silu_mul(float* __restrict__ gu, __half* __restrict__ out, int
 // Decode attention: RoPE (llama.py:106-119,151-182) on the new q/k, KV append (replaces the torch.cat of
 // DynamicCache.update, llama.py:630-633, with an O(1) in-place write), softmax(q K^T / 8) V over the cached slots
 // of this sequence (SDPA q_len = 1, llama.py:653-661).  Left padding: slots [0, pad_len[b]) are masked.
-// grid (nH, B, nsplit), 128 threads; split partials are merged by the last CTA to arrive for each (b, h).
+// split partials are merged by the last CTA to arrive for each (b, h).
 // ---------------------------------------------------------------------------------------------------------
 struct AttnDecArgs {
     float* qkv;             // [B][3H] fp32 accumulators of the QKV GEMM (re-armed to zero by their last reader)
@@ -176,186 +176,18 @@ struct AttnDecArgs {
     const GenState* st;
     const float* inv_freq;  // [32]
     int H, nH, max_seq;
-    // RMSNorm folded into the QKV GEMM (decode_gemm.cuh BMODE 1): the GEMM contracted x*w, the row factor
-    // rsqrt(sum(x^2)/H + eps) (llama.py:85) is applied here; sum(x^2) arrives as ss_parts partial sums per row
-    const float* ss;        // [ss_parts][ss_stride] or null (rows already normalised)
-    int ss_parts, ss_stride;
+    // RMSNorm folded into the QKV GEMM (XNORM operand): the GEMM contracted x*w, the row factor rsqrt(sum(x^2)/H + eps)
+    // (llama.py:85) is applied here; sum(x^2) per row arrives in ss
+    const float* ss;        // [B] or null (rows already normalised)
     float eps;
-    int rearm;              // 1: qkv is a split-K RED accumulator that its last reader zeroes; 0: plain final values
+    // optional: regions the kernel BEHIND this one streams (the layer-chain kernel's weights); every CTA prefetches a share into L2
+    const void* pf_ptr[4];
+    unsigned long long pf_bytes[4];
     unsigned long long* trace;
 };
 
-__global__ void __launch_bounds__(128) k_attn_decode(AttnDecArgs a) {
-    if (threadIdx.x == 0) trace_mark(a.trace, 0);
-    pdl_launch_dependents();
-    pdl_wait();
-    if (threadIdx.x == 0) trace_mark(a.trace, 1);
-    const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z, nsplit = gridDim.z;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int cur = a.st->cur_len;  // new token's slot
-    const int pad = a.pad_len[b];
-    __shared__ float sq[HEAD_DIM];
-    __shared__ __align__(16) __half sk_new[HEAD_DIM];
-    __shared__ __align__(16) __half sv_new[HEAD_DIM];
-    __shared__ float s_m[16], s_l[16];
-    __shared__ float s_o[16][HEAD_DIM + 1];
-    __shared__ int s_last;
-
-    float* qp = a.qkv + (long long)b * 3 * a.H + h * HEAD_DIM;
-    float rf = 1.f;   // deferred RMSNorm row factor (llama.py:85)
-    if (a.ss) {
-        float part[8];   // independent loads: one L2 round trip
-#pragma unroll
-        for (int p = 0; p < 8; ++p) part[p] = p < a.ss_parts ? __ldcg(a.ss + p * a.ss_stride + b) : 0.f;
-        float ssum = 0.f;
-#pragma unroll
-        for (int p = 0; p < 8; ++p) ssum += part[p];
-        rf = rsqrtf(ssum / (float)a.H + a.eps);
-    }
-    if (tid < 32) {
-        const float pos = (float)(cur - pad);
-        const float ang = pos * a.inv_freq[tid];
-        float sn, cs;
-        sincosf(ang, &sn, &cs);
-        const float q1 = qp[tid] * rf, q2 = qp[tid + 32] * rf;
-        const float k1 = qp[a.H + tid] * rf, k2 = qp[a.H + tid + 32] * rf;
-        sq[tid] = (q1 * cs - q2 * sn) * 0.125f;  // 1/sqrt(64) folded into q
-        sq[tid + 32] = (q2 * cs + q1 * sn) * 0.125f;
-        sk_new[tid] = __float2half_rn(k1 * cs - k2 * sn);
-        sk_new[tid + 32] = __float2half_rn(k2 * cs + k1 * sn);
-    } else if (tid < 96) {
-        const int d = tid - 32;
-        sv_new[d] = __float2half_rn(qp[2 * a.H + d] * rf);
-    }
-    __syncthreads();
-    if (tid == 0) trace_mark(a.trace, 4);
-    const long long head_off = (((long long)b * a.nH + h) * a.max_seq) * HEAD_DIM;
-    __half* kc = a.kcache + head_off;
-    __half* vc = a.vcache + head_off;
-    if (sp == nsplit - 1 && tid < 16) {  // append (16 threads x 16 B = 64 halfs for K and for V)
-        reinterpret_cast<uint2*>(kc + (long long)cur * HEAD_DIM)[tid] = reinterpret_cast<const uint2*>(sk_new)[tid];
-        reinterpret_cast<uint2*>(vc + (long long)cur * HEAD_DIM)[tid] = reinterpret_cast<const uint2*>(sv_new)[tid];
-    }
-    // slots this split covers: [j0, j1) within [pad, cur]  (cur = the new token, taken from shared memory)
-    const int n = cur + 1 - pad;
-    const int j0 = pad + (int)(((long long)n * sp) / nsplit);
-    const int j1 = pad + (int)(((long long)n * (sp + 1)) / nsplit);
-
-    // 16 groups of 8 lanes; lane `sub` owns dims [8*sub, 8*sub+8)
-    const int grp = tid >> 3, sub = tid & 7;
-    float q[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) q[i] = sq[sub * 8 + i];
-    float m = -INFINITY, l = 0.f, o[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = 0.f;
-
-    constexpr int UNROLL = 4;
-    // loop bounds are uniform over the CTA; validity is a per-group predicate (shuffles stay convergent)
-    for (int jb = j0; jb < j1; jb += 16 * UNROLL) {
-        uint4 kr[UNROLL], vr[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const int j = jb + grp + u * 16;
-            kr[u] = make_uint4(0, 0, 0, 0);
-            vr[u] = make_uint4(0, 0, 0, 0);
-            if (j < j1) {
-                if (j == cur) {
-                    kr[u] = reinterpret_cast<const uint4*>(sk_new)[sub];
-                    vr[u] = reinterpret_cast<const uint4*>(sv_new)[sub];
-                } else {
-                    kr[u] = __ldg(reinterpret_cast<const uint4*>(kc + (long long)j * HEAD_DIM) + sub);
-                    vr[u] = __ldg(reinterpret_cast<const uint4*>(vc + (long long)j * HEAD_DIM) + sub);
-                }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const int j = jb + grp + u * 16;
-            const bool valid = j < j1;
-            const __half2* k2 = reinterpret_cast<const __half2*>(&kr[u]);
-            float s = 0.f;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 f = __half22float2(k2[i]);
-                s += q[2 * i] * f.x + q[2 * i + 1] * f.y;
-            }
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            s += __shfl_xor_sync(0xffffffffu, s, 4);
-            if (valid) {
-                const float mn = fmaxf(m, s);
-                const float corr = __expf(m - mn);
-                const float p = __expf(s - mn);
-                l = l * corr + p;
-                const __half2* v2 = reinterpret_cast<const __half2*>(&vr[u]);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float2 f = __half22float2(v2[i]);
-                    o[2 * i] = o[2 * i] * corr + p * f.x;
-                    o[2 * i + 1] = o[2 * i + 1] * corr + p * f.y;
-                }
-                m = mn;
-            }
-        }
-    }
-    // merge the 16 groups
-    if (tid == 0) trace_mark(a.trace, 5);
-    if (sub == 0) { s_m[grp] = m; s_l[grp] = l; }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s_o[grp][sub * 8 + i] = o[i];
-    __syncthreads();
-    float M = -INFINITY, Lsum = 0.f, O = 0.f;
-    if (tid < HEAD_DIM) {
-#pragma unroll
-        for (int g = 0; g < 16; ++g) M = fmaxf(M, s_m[g]);
-#pragma unroll
-        for (int g = 0; g < 16; ++g) {
-            const float w = (s_m[g] == -INFINITY) ? 0.f : __expf(s_m[g] - M);
-            Lsum += s_l[g] * w;
-            O += s_o[g][tid] * w;
-        }
-    }
-    if (nsplit == 1) {
-        if (tid < HEAD_DIM) {
-            a.out[(long long)b * a.H + h * HEAD_DIM + tid] = __float2half_rn(O / Lsum);
-            if (a.rearm) { qp[tid] = 0.f; qp[a.H + tid] = 0.f; qp[2 * a.H + tid] = 0.f; }   // all reads of q,k,v happened before the first sync
-        }
-        if (tid == 0) trace_end(a.trace);
-        return;
-    }
-    float* pp = a.part + (((long long)b * a.nH + h) * nsplit + sp) * 66;
-    if (tid < HEAD_DIM) pp[tid] = O;
-    if (tid == 0) { pp[64] = M; pp[65] = Lsum; }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        const int t = atomicAdd(&a.counters[b * a.nH + h], 1);
-        s_last = (t == nsplit - 1);
-        if (s_last) a.counters[b * a.nH + h] = 0;
-    }
-    __syncthreads();
-    if (tid == 0) trace_end(a.trace);
-    if (!s_last) return;
-    __threadfence();
-    if (tid < HEAD_DIM) {
-        const float* p0 = a.part + (((long long)b * a.nH + h) * nsplit) * 66;
-        float MM = -INFINITY;
-        for (int s = 0; s < nsplit; ++s) MM = fmaxf(MM, p0[s * 66 + 64]);
-        float LL = 0.f, OO = 0.f;
-        for (int s = 0; s < nsplit; ++s) {
-            const float ms = p0[s * 66 + 64];
-            const float w = (ms == -INFINITY) ? 0.f : __expf(ms - MM);
-            LL += p0[s * 66 + 65] * w;
-            OO += p0[s * 66 + tid] * w;
-        }
-        a.out[(long long)b * a.H + h * HEAD_DIM + tid] = __float2half_rn(OO / LL);
-        if (a.rearm) { qp[tid] = 0.f; qp[a.H + tid] = 0.f; qp[2 * a.H + tid] = 0.f; }   // every split has arrived (ticket): safe to re-arm
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------------
-// Decode attention, TMA-staged (default): same math as k_attn_decode, but the cached K/V stream of this (b, head) is pulled
+// Decode attention, TMA-staged: the cached K/V stream of this (b, head) is pulled
 // into a 4-stage shared-memory ring by 1-D bulk copies (cp.async.bulk, 8 KB K + 8 KB V per 64-slot tile, one elected
 // producer thread, mbarrier full/empty handshake) instead of per-thread 16-byte loads: few large requests keep HBM busy,
 // and — because cached slots do not depend on this step's QKV GEMM — the first ring pass is issued BEFORE
@@ -412,6 +244,25 @@ __global__ void __launch_bounds__(AT_THREADS) k_attn_decode_tma(AttnDecArgs a) {
             bulk_load_1d(st + AT_HALF_BYTES, vc + p0 * HEAD_DIM, AT_HALF_BYTES, &full_bar[i]);
         }
         s_pre = pre;
+        // warm L2 with the next kernel's weight stream (after our own loads are in flight)
+        const unsigned long long n_cta = (unsigned long long)gridDim.x * gridDim.y * gridDim.z;
+        const unsigned long long cta = ((unsigned long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (a.pf_ptr[r] == nullptr) continue;
+            const unsigned long long per = ((a.pf_bytes[r] + n_cta - 1) / n_cta + 127) & ~127ULL;
+            const unsigned long long off = cta * per;
+            if (off >= a.pf_bytes[r]) continue;
+            unsigned long long n = a.pf_bytes[r] - off < per ? a.pf_bytes[r] - off : per;
+            n &= ~15ULL;
+            const char* src = reinterpret_cast<const char*>(a.pf_ptr[r]) + off;
+            while (n > 0) {
+                const unsigned int chunk = n > 32768ULL ? 32768u : (unsigned int)n;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(chunk) : "memory");
+                src += chunk;
+                n -= chunk;
+            }
+        }
     }
     pdl_wait();
     if (tid == 0) trace_mark(a.trace, 1);
@@ -446,15 +297,7 @@ __global__ void __launch_bounds__(AT_THREADS) k_attn_decode_tma(AttnDecArgs a) {
     if (tid < 32) { raw[0] = qp[tid]; raw[1] = qp[tid + 32]; raw[2] = qp[a.H + tid]; raw[3] = qp[a.H + tid + 32]; }
     else if (tid < 96) raw[0] = qp[2 * a.H + tid - 32];
     float rf = 1.f;   // deferred RMSNorm row factor (llama.py:85): the QKV GEMM contracted x*w, sum(x^2) arrives in ss
-    if (a.ss) {
-        float part[8];
-#pragma unroll
-        for (int p = 0; p < 8; ++p) part[p] = p < a.ss_parts ? __ldcg(a.ss + p * a.ss_stride + b) : 0.f;
-        float ssum = 0.f;
-#pragma unroll
-        for (int p = 0; p < 8; ++p) ssum += part[p];
-        rf = rsqrtf(ssum / (float)a.H + a.eps);
-    }
+    if (a.ss) rf = rsqrtf(__ldcg(a.ss + b) / (float)a.H + a.eps);
     if (tid < 32) {
         const float pos = (float)(cur - pad);
         const float ang = pos * a.inv_freq[tid];
@@ -577,7 +420,7 @@ __global__ void __launch_bounds__(AT_THREADS) k_attn_decode_tma(AttnDecArgs a) {
     if (nsplit == 1) {
         if (tid < HEAD_DIM) {
             a.out[(long long)b * a.H + h * HEAD_DIM + tid] = __float2half_rn(O / Lsum);
-            if (a.rearm) { qp[tid] = 0.f; qp[a.H + tid] = 0.f; qp[2 * a.H + tid] = 0.f; }   // all reads of q,k,v happened before the first barrier
+            { qp[tid] = 0.f; qp[a.H + tid] = 0.f; qp[2 * a.H + tid] = 0.f; }   // all reads of q,k,v happened before the first barrier
         }
         if (tid == 0) trace_end(a.trace);
         return;
@@ -608,7 +451,7 @@ __global__ void __launch_bounds__(AT_THREADS) k_attn_decode_tma(AttnDecArgs a) {
             OO += p0[s * 66 + tid] * w;
         }
         a.out[(long long)b * a.H + h * HEAD_DIM + tid] = __float2half_rn(OO / LL);
-        if (a.rearm) { qp[tid] = 0.f; qp[a.H + tid] = 0.f; qp[2 * a.H + tid] = 0.f; }   // every split has arrived (ticket): safe to re-arm
+        { qp[tid] = 0.f; qp[a.H + tid] = 0.f; qp[2 * a.H + tid] = 0.f; }   // every split has arrived (ticket): safe to re-arm
     }
 }
 

@@ -38,12 +38,21 @@ lib.ctp_debug_trace.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int]
 n = lib.ctp_debug_trace(gpt._handle, buf, 256)
 recs = [tuple(buf[8 * i + j] for j in range(8)) for i in range(n)]
 t0 = recs[0][0]
-names_fused = ["qkv", "attn", "o", "gu", "down"]
-print(f"{n} kernels; columns: idx  enter  wait_ret  exit(cta0)  exit(last)  | dur(last-enter)  gap(enter - prev last exit)  [us, relative to kernel 0 enter]")
+print(f"{n} kernels of the last replayed step, launch order; times in us.  enter / wait_ret / exit0 / exit_last are relative to kernel 0's enter "
+      f"(CTA 0 enters, its griddepcontrol.wait returns, CTA 0 leaves, the last CTA leaves); body = exit_last - wait_ret; handoff = wait_ret - previous "
+      f"exit_last; s4..s7 = kernel-specific phase stamps relative to wait_ret (layer-chain kernel: s4/s5/s6 = phase counters 0/1/2 observed complete)")
 prev_end = None
-for i, (a, b, c, d, e4, e5, e6, e7) in enumerate(recs):
-    gap = (a - prev_end) / 1e3 if prev_end else 0.0
-    wgap = (b - prev_end) / 1e3 if prev_end else 0.0
-    print(f"{i:3d} {(a - t0) / 1e3:9.2f} {(b - t0) / 1e3:9.2f} {(c - t0) / 1e3:9.2f} {(d - t0) / 1e3:9.2f} | dur {(d - a) / 1e3:7.2f}  body {(d - b) / 1e3:7.2f}  enter-prev_end {gap:7.2f}  wait_ret-prev_end {wgap:7.2f}" + (f"  | gemm cta0 after wait: Bstored {(e4 - b) / 1e3:5.2f} arrived {(e5 - b) / 1e3:5.2f} accum {(e6 - b) / 1e3:5.2f} epi_done {(e7 - b) / 1e3:5.2f}" if e6 and e7 else (f"  | s4 {(e4 - b) / 1e3:5.2f} s5 {(e5 - b) / 1e3:5.2f} s6 {(e6 - b) / 1e3:5.2f} s7 {(e7 - b) / 1e3:5.2f}" if e4 else "")))
+tot_body = tot_hand = 0.0
+for i, r in enumerate(recs):
+    a, b, c, d = r[:4]
+    if not (a and b and d):
+        print(f"{i:3d} (no record)")
+        continue
+    hand = (b - prev_end) / 1e3 if prev_end else 0.0
+    extra = "  ".join(f"s{j} {(r[j] - b) / 1e3:6.2f}" for j in range(4, 8) if r[j] >= a)
+    print(f"{i:3d} enter {(a - t0) / 1e3:8.2f} wait_ret {(b - t0) / 1e3:8.2f} exit0 {(c - t0) / 1e3:8.2f} exit_last {(d - t0) / 1e3:8.2f} | "
+          f"body {(d - b) / 1e3:6.2f} handoff {hand:6.2f} | {extra}")
+    tot_body += (d - b) / 1e3
+    tot_hand += hand
     prev_end = d
-print("step span (first enter -> last exit):", (recs[-1][3] - t0) / 1e3, "us")
+print(f"sum of bodies {tot_body:.1f} us, sum of hand-offs {tot_hand:.1f} us, span (first enter -> last exit) {(recs[-1][3] - t0) / 1e3:.1f} us")
