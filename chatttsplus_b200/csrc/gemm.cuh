@@ -376,7 +376,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // consecutive features of one token and issues vector reductions: 4x fewer RED operations through the LSU
             // (scalar: ~6.9k cycles per 128x32 tile, measured with tests/prof_gemm_stamps.py).
             const bool fast = epi.swap && epi.atomic && !epi.out_f16 && !epi.bias && !epi.gamma && !epi.residual && !epi.row_valid &&
-                              !epi.act_gelu && ((epi.ldo & 3) == 0) && (m0 + GEMM_BM <= epi.F);
+                              !epi.act_gelu && ((epi.ldo & 3) == 0) && ((epi.F & 3) == 0);   // (partial last m-tile: per-lane feature guard below)
 #pragma unroll 1
             for (int c = 0; c < BN; c += 32) {
                 float acc[32];
@@ -391,7 +391,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     for (int r = 0; r < 8; ++r) {
                         const int tl = 4 * r + (lane >> 3);
                         const int t = n0 + c + tl;
-                        if (t < epi.T) {
+                        if (t < epi.T && m0 + warp * 32 + f4 < epi.F) {
                             const float4 v = *reinterpret_cast<const float4*>(tile + tl * 36 + f4);
                             float* o = reinterpret_cast<float*>(epi.out) + (long long)t * epi.ldo + (m0 + warp * 32 + f4);
                             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");

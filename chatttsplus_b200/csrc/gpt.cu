@@ -69,8 +69,9 @@ struct ctp_gpt {
     int sm_count = 0;
     bool use_pdl = true;       // programmatic dependent launch between the kernels of the decode step graph (CTP_PDL=0 disables)
     bool fuse_norm = true;     // RMSNorm folded into the QKV / gate|up GEMMs (XNORM kernel); CTP_FUSE_NORM=0: stand-alone norm kernels
-    bool use_chain = true;     // layer-chain kernel (layer_kernel.cuh): o_proj -> gate|up -> down -> next q|k|v in ONE launch per layer;
-                               // CTP_DECODE=ops selects one launch per GEMM (five kernels per layer)
+    bool use_chain = false;    // CTP_DECODE=chain: layer-chain kernel (layer_kernel.cuh): o_proj -> gate|up -> down -> next q|k|v in ONE launch per
+                               // layer (two launches per layer with attention).  Parity-green; measured 633 vs 600 us/step for one launch per GEMM
+                               // (profiles/README.md: an in-kernel grid-wide exchange costs what a PDL kernel boundary costs), so opt-in
     CUtensorMap x_map{};       // fp32 map over the first 64 rows of the residual stream
     CUtensorMap gu_map{};      // fp32 map over the decode gate|up accumulator
     // decode only, re-armable scratch: ss1[64] | ss2[64] | gate|up accumulator [64][2I].  ss1 / ss2 = sum(x^2) per token row as seen by
@@ -82,6 +83,9 @@ struct ctp_gpt {
     unsigned int* chain_flags = nullptr;   // layer-chain kernel: [0..2] phase counters, [3] epoch (zeroed by every prefill)
     int chain_grid = 0;                    // CTAs of the layer-chain kernel (0: shape / device not eligible)
     LkPhase chain_ph[4]{};
+    bool attn_prefetch = false;            // CTP_ATTN_PREFETCH=1: the attention kernel (not the previous layer-chain launch) warms L2 with the chain's weights
+    bool kv_prefetch = false;              // CTP_KV_PREFETCH=1: layer-chain kernel warms L2 with the next attention's K/V streams (measured: competes with the chain's own weight tiles, 631 -> 700 us/step)
+    unsigned long long kvpf_cap = 96 * 1024;   // per-stream cap in bytes (CTP_KV_PREFETCH_CAP, KiB): 768 streams x 96 KB = 72 MB of the 126 MB L2
     int attn_cta_target = 296;   // split the KV range until B*heads*nsplit reaches this many CTAs (CTP_ATTN_CTAS)
     // bring-up: in-graph timeline (CTP_TRACE=1): one 8-stamp record per kernel of the step graph, in launch order
     unsigned long long* trace = nullptr;
@@ -184,8 +188,11 @@ extern "C" ctp_status ctp_gpt_create(ctp_gpt** out, const ctp_gpt_cfg* cfg) {
         const int I = cfg->inter;
         if (const char* e = getenv("CTP_PDL")) h->use_pdl = atoi(e) != 0;
         if (const char* e = getenv("CTP_FUSE_NORM")) h->fuse_norm = atoi(e) != 0;
-        if (const char* e = getenv("CTP_DECODE")) h->use_chain = (strcmp(e, "ops") != 0);
+        if (const char* e = getenv("CTP_DECODE")) h->use_chain = (strcmp(e, "chain") == 0);
         if (const char* e = getenv("CTP_ATTN_CTAS")) h->attn_cta_target = atoi(e);
+        if (const char* e = getenv("CTP_KV_PREFETCH")) h->kv_prefetch = atoi(e) != 0;
+        if (const char* e = getenv("CTP_ATTN_PREFETCH")) h->attn_prefetch = atoi(e) != 0;
+        if (const char* e = getenv("CTP_KV_PREFETCH_CAP")) h->kvpf_cap = (unsigned long long)atoi(e) * 1024ULL;
         CK(cudaMalloc(&h->dec_gu, sizeof(float) * (128 + (size_t)64 * 2 * I)));
         CK(cudaMemset(h->dec_gu, 0, sizeof(float) * (128 + (size_t)64 * 2 * I)));
         CK(cudaMalloc(&h->chain_flags, sizeof(unsigned int) * 4));
@@ -193,8 +200,8 @@ extern "C" ctp_status ctp_gpt_create(ctp_gpt** out, const ctp_gpt_cfg* cfg) {
         CK(cudaFuncSetAttribute(k_attn_decode_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
         CK(cudaFuncSetAttribute(k_layer_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, LK_SMEM));
         if (const char* e = getenv("CTP_TRACE")) if (atoi(e)) {
-            CK(cudaMalloc(&h->trace, sizeof(unsigned long long) * 8 * 256));
-            CK(cudaMemset(h->trace, 0, sizeof(unsigned long long) * 8 * 256));
+            CK(cudaMalloc(&h->trace, sizeof(unsigned long long) * (8 * 256 + 128)));
+            CK(cudaMemset(h->trace, 0, sizeof(unsigned long long) * (8 * 256 + 128)));
         }
         // layer-chain plan: one (128-row weight tile, k-slice) unit per CTA and GEMM; every CTA must be resident (one per SM)
         h->chain_grid = 0;
@@ -301,14 +308,15 @@ static int split_for(int k_blocks, int m_tiles, int target_ctas = 0) {
 #define LAUNCH_OK() do { ctp_count_launch(); cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { ctp_set_error("%s:%d launch: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); return CTP_ERR_CUDA; } } while (0)
 
 // heads: logits[b][q*A + a] = hidden_n[b] . head_code[q*A + a]   (gpt.py:424-439; weight_norm folded at bind)
-static int launch_heads(ctp_gpt* h, int B, cudaStream_t s, bool pdl = false) {
+static int launch_heads(ctp_gpt* h, int B, cudaStream_t s, bool pdl = false, bool traced = false) {
     const ctp_gpt_cfg& c = h->cfg;
     const int F = h->text_mode ? c.num_text : c.num_vq * c.num_audio;   // head_text (gpt.py:425-426) or the 4 code heads
     const int bn = B <= 32 ? 32 : 64;
     const ActMaps& am = bn == 32 ? h->act32 : h->act64;
     const int m_tiles = (F + GEMM_BM - 1) / GEMM_BM;
     GemmEpilogue e = epi_swap_atomic(h->logits, F, B, F);
-    return gemm_launch_maps(h->text_mode ? h->head_text_map : h->head_map, am.xn, F, B, c.hidden, bn, split_for(c.hidden / 64, m_tiles), e, s, nullptr, 0, pdl);
+    return gemm_launch_maps(h->text_mode ? h->head_text_map : h->head_map, am.xn, F, B, c.hidden, bn, split_for(c.hidden / 64, m_tiles), e, s, nullptr, 0, pdl,
+                            nullptr, 0, traced ? h->trace_rec() : nullptr);
 }
 
 // One decode trunk step for B sequences (ids_ext == nullptr -> codes of the previous sample step).
@@ -334,7 +342,7 @@ static int launch_attn(ctp_gpt* h, int l, int B, int nsplit, bool row_factor, cu
     return CTP_OK;
 }
 
-// Layer-chain path (default, batch <= 32): per layer TWO launches — attention, then k_layer_chain (o_proj -> gate|up -> down ->
+// Layer-chain path (CTP_DECODE=chain, batch <= 32): per layer TWO launches — attention, then k_layer_chain (o_proj -> gate|up -> down ->
 // next layer's q|k|v; layer_kernel.cuh) — instead of five; 45 kernels per step at 20 layers.
 static int run_decode_trunk_chain(ctp_gpt* h, int B, int nsplit, const int* ids_ext, cudaStream_t s) {
     const ctp_gpt_cfg& c = h->cfg;
@@ -353,7 +361,7 @@ static int run_decode_trunk_chain(ctp_gpt* h, int B, int nsplit, const int* ids_
                                    nullptr, 0, h->trace_rec()))) return st;
     }
     for (int l = 0; l < L; ++l) {
-        if ((st = launch_attn(h, l, B, nsplit, l > 0, s, pdl, true))) return st;
+        if ((st = launch_attn(h, l, B, nsplit, l > 0, s, pdl, h->attn_prefetch))) return st;
         LayerArgs a{};
         for (int p = 0; p < 4; ++p) a.ph[p] = h->chain_ph[p];
         a.ph[0].out = h->x; a.ph[0].ldo = H;                  // o_proj accumulated straight into the residual stream (llama.py:663-666,737)
@@ -367,10 +375,35 @@ static int run_decode_trunk_chain(ctp_gpt* h, int B, int nsplit, const int* ids_
         a.ss1 = h->ss1(); a.ss2 = h->ss2();
         a.rearm_ptr = h->ss2(); a.rearm_f4 = (unsigned long long)(64 + (size_t)B * 2 * I) / 4;
         a.flags = h->chain_flags;
+        if (!h->attn_prefetch) {   // warm L2 with the weight stream of the next layer-chain launch (and the heads / first q|k|v of the next step)
+            const size_t Hs = H, Is = I;
+            const __half* wqkv = (const __half*)h->w.wqkv; const __half* wo = (const __half*)h->w.wo;
+            const __half* wgu = (const __half*)h->w.wgu; const __half* wdn = (const __half*)h->w.wdown;
+            const int ln = (l + 1) % L;
+            a.pf_ptr[0] = wo + (size_t)ln * Hs * Hs;          a.pf_bytes[0] = sizeof(__half) * Hs * Hs;
+            a.pf_ptr[1] = wgu + (size_t)ln * 2 * Is * Hs;     a.pf_bytes[1] = sizeof(__half) * 2 * Is * Hs;
+            a.pf_ptr[2] = wdn + (size_t)ln * Hs * Is;         a.pf_bytes[2] = sizeof(__half) * Hs * Is;
+            if (l + 2 < L) { a.pf_ptr[3] = wqkv + (size_t)(l + 2) * 3 * Hs * Hs; a.pf_bytes[3] = sizeof(__half) * 3 * Hs * Hs; }
+            if (l + 2 == L) {   // the launch before the last: the heads GEMM follows the last layer-chain launch
+                a.pf_ptr[3] = h->text_mode ? h->w.head_text : h->w.head_code;
+                a.pf_bytes[3] = sizeof(__half) * Hs * (size_t)(h->text_mode ? c.num_text : c.num_vq * c.num_audio);
+            }
+            if (l + 1 == L) {   // the last launch: the next step starts with q|k|v of layer 0 and needs layer 1's in its first chain launch
+                a.pf_ptr[3] = wqkv; a.pf_bytes[3] = sizeof(__half) * 3 * Hs * Hs;
+                if (L > 1) { a.pf_ptr[4] = wqkv + 3 * Hs * Hs; a.pf_bytes[4] = sizeof(__half) * 3 * Hs * Hs; }
+            }
+        }
+        if (h->kv_prefetch) {   // warm L2 with the K/V streams of the next attention launch (layer l+1, or layer 0 of the next step)
+            const int ln = (l + 1) % L;
+            a.kv_k = (const char*)h->kplane(ln); a.kv_v = (const char*)h->vplane(ln);
+            a.kv_stream_bytes = sizeof(__half) * (size_t)c.max_seq * HEAD_DIM; a.kv_cap = h->kvpf_cap;
+            a.kv_streams = B * c.n_heads; a.nH = c.n_heads; a.pad_len = h->pad_len; a.cur_len = &h->st->cur_len;
+        }
         a.trace = h->trace_rec();
+        a.dbg = (h->trace && l == L / 2) ? h->trace + 8 * 256 : nullptr;   // fine-grained stamps of one mid-stack launch
         const LayerMaps& m = h->lmaps[l];
         const CUtensorMap& next_qkv = h->lmaps[l + 1 < L ? l + 1 : l].wqkv;
-        CTP_LAUNCH(k_layer_chain, dim3(h->chain_grid), dim3(LK_THREADS), LK_SMEM, m.wo, m.wgu, m.wdown, next_qkv, h->act32.attn, h->x_map, h->gu_map, a);
+        CTP_LAUNCH(k_layer_chain, dim3(h->chain_grid), dim3(LK_THREADS), LK_SMEM, m.wo, m.wgu, m.wdown, next_qkv, h->act32.attn, a);
     }
     return CTP_OK;
 }
@@ -391,7 +424,7 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
     }
     float* gu = fuse ? h->gu_acc() : h->acc_gu;
     const unsigned long long rearm_f4 = (unsigned long long)(64 + (size_t)B * 2 * I) / 4;   // ss2 | gate|up rows of the live batch (from ss2())
-    // CTP_DECODE=ops (and batches of 33..64 rows, which use the 64-token N tile with stand-alone norm / SiLU kernels): one launch per op
+    // default (batches of 33..64 rows use the 64-token N tile with stand-alone norm / SiLU kernels): one launch per op
     for (int l = 0; l < (chain ? 0 : c.n_layers); ++l) {
         const bool f1 = fuse && l > 0;   // layer 0 keeps the norm kernel: it is also the code-embedding front end
         if (!f1) {
@@ -470,7 +503,7 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
     nf.zero_buf = h->logits; nf.zero_n = h->text_mode ? c.num_text : c.num_vq * c.num_audio; nf.st = h->st; nf.write_hid = 1;
     nf.trace = h->trace_rec();
     CTP_LAUNCH(k_rmsnorm, dim3(B), dim3(256), 0, nf);
-    if ((st = launch_heads(h, B, s, pdl))) return st;
+    if ((st = launch_heads(h, B, s, pdl, true))) return st;
     if (!advance_in_sampler) CTP_LAUNCH(k_advance_len, dim3(1), dim3(1), 0, h->st);
     return CTP_OK;
 }
@@ -722,6 +755,14 @@ extern "C" __attribute__((visibility("default"))) int ctp_debug_trace(ctp_gpt* h
     cudaDeviceSynchronize();
     cudaMemcpy(out, h->trace, sizeof(unsigned long long) * 8 * (size_t)n, cudaMemcpyDeviceToHost);
     return n;
+}
+
+// bring-up hook (not in include/ctp.h): the 2 x 64 fine-grained stamps of the mid-stack layer-chain launch (CTA 0, last CTA)
+extern "C" __attribute__((visibility("default"))) int ctp_debug_chain_stamps(ctp_gpt* h, unsigned long long* out) {
+    if (!h || !h->trace) return 0;
+    cudaDeviceSynchronize();
+    cudaMemcpy(out, h->trace + 8 * 256, sizeof(unsigned long long) * 128, cudaMemcpyDeviceToHost);
+    return 128;
 }
 
 extern "C" const float* ctp_gpt_logits(ctp_gpt* h) { return h ? h->logits : nullptr; }

@@ -111,11 +111,13 @@ def test_trunk_long_context_two_kv_splits():
     _teacher_forced(cfg, B=25, L0=1040, steps=3, seed=36, pads=[0, 700, 1039] + [0] * 22)
 
 
-@pytest.mark.parametrize("env", [{"CTP_DECODE": "ops"}, {"CTP_PDL": "0"}, {"CTP_DECODE": "ops", "CTP_PDL": "0"}, {"CTP_FUSE_NORM": "0"}])
+@pytest.mark.parametrize("env", [{"CTP_DECODE": "chain"}, {"CTP_DECODE": "chain", "CTP_PDL": "0"}, {"CTP_DECODE": "chain", "CTP_KV_PREFETCH": "1"},
+                                 {"CTP_DECODE": "chain", "CTP_ATTN_PREFETCH": "1"}, {"CTP_PDL": "0"}, {"CTP_FUSE_NORM": "0"}])
 def test_trunk_opt_in_variants(env, monkeypatch):
-    """The default decode layer is two launches (attention + the layer-chain kernel).  The remaining switches stay parity-green:
-    one launch per GEMM (five kernels per layer, CTP_DECODE=ops), launches without programmatic dependent launch, stand-alone
-    norm / SiLU kernels (eight per layer, the path batches of 33..64 rows take).  (Read at handle creation.)"""
+    """The default decode layer is five launches (q|k|v, attention, o_proj, gate|up, down).  The switches stay parity-green: the
+    layer-chain kernel (attention + ONE persistent launch for the four GEMMs, phases separated by release/acquire counters), with
+    and without its L2 warm-up variants; launches without programmatic dependent launch; stand-alone norm / SiLU kernels (eight per
+    layer, the path batches of 33..64 rows take).  (Read at handle creation.)"""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     cfg = synth.GPTConfig(num_hidden_layers=3, num_text_tokens=256)
@@ -138,6 +140,13 @@ def test_trunk_full_depth_config2_shape():
     """20 layers, B=32, L0=128 (BASELINE.json configs[1] shape), 4 teacher-forced steps."""
     cfg = synth.GPTConfig()
     # 20 layers: split-K fp32 atomics make the last bits order-dependent; bound = SURVEY.md §8c (max-abs 2e-2, rel-RMS 5e-3)
+    _teacher_forced(cfg, B=32, L0=128, steps=4, seed=40, tol_rms=2e-3, tol_abs=2e-2)
+
+
+def test_trunk_full_depth_layer_chain(monkeypatch):
+    """Same shape through the layer-chain kernel (CTP_DECODE=chain): all 148 CTAs hold a unit in the gate|up / down phases."""
+    monkeypatch.setenv("CTP_DECODE", "chain")
+    cfg = synth.GPTConfig()
     _teacher_forced(cfg, B=32, L0=128, steps=4, seed=40, tol_rms=2e-3, tol_abs=2e-2)
 
 
