@@ -75,6 +75,7 @@ SYMBOLS = {
     "ctp_gpt_bind_weights": (C.c_int, [_VP, C.POINTER(GptWeights)]),
     "ctp_gpt_embed_prompt": (C.c_int, [_VP, _I32, _I32, _VP, _VP, _VP, _VP]),
     "ctp_gpt_prefill": (C.c_int, [_VP, _I32, _I32, _VP, C.POINTER(_I32), C.POINTER(GenBuffers), _I32, _VP]),
+    "ctp_gpt_rewind": (C.c_int, [_VP, _VP]),
     "ctp_gpt_decode_step": (C.c_int, [_VP, _VP, _VP]),
     "ctp_gpt_sample_step": (C.c_int, [_VP, C.POINTER(SampleCfg), _VP, _VP]),
     "ctp_gpt_generate": (C.c_int, [_VP, C.POINTER(SampleCfg), _I32, _VP, _I32, C.POINTER(_I32), _VP]),
@@ -90,6 +91,7 @@ SYMBOLS = {
     "ctp_voc_decode": (C.c_int, [_VP, _I32, C.POINTER(_I32), _VP, _VP, C.POINTER(_I64), _VP, _VP]),
     "ctp_voc_decode_mel": (C.c_int, [_VP, _I32, C.POINTER(_I32), _VP, _VP, C.POINTER(_I64), _VP]),
     "ctp_voc_encode": (C.c_int, [_VP, _I32, _VP, _VP, _VP, C.POINTER(_I32), _VP]),
+    "ctp_voc_quantize": (C.c_int, [_VP, _I32, _VP, _VP, _VP]),
     "ctp_gemm_f16": (C.c_int, [_I32, _I32, _I32, _VP, _I64, _VP, _I64, _VP, _I64, _VP, _I32, _I32, _I32, _VP]),
 }
 

@@ -93,7 +93,7 @@ struct ctp_gpt {
     unsigned long long* trace_rec() { return trace ? trace + 8 * (size_t)(trace_n++ % 256) : nullptr; }
 
     // host mirror of the generation state
-    int B = 0, cur_len = 0, step = 0, max_new = 0;
+    int B = 0, cur_len = 0, step = 0, max_new = 0, prompt_len = 0;
     bool have_bufs = false;
 
     size_t kv_plane_elems() const { return (size_t)cfg.max_batch * cfg.n_heads * cfg.max_seq * HEAD_DIM; }
@@ -634,7 +634,23 @@ extern "C" ctp_status ctp_gpt_prefill(ctp_gpt* h, int32_t B, int32_t L0, const f
     CTP_CUDA_OK(cudaMemsetAsync(h->acc_gu, 0, sizeof(float) * (size_t)c.max_batch * 2 * I, s));
     CTP_CUDA_OK(cudaMemsetAsync(h->dec_gu, 0, sizeof(float) * (128 + (size_t)64 * 2 * I), s));
     CTP_CUDA_OK(cudaMemsetAsync(h->chain_flags, 0, sizeof(unsigned int) * 4, s));   // phase counters + epoch of the layer-chain kernel
-    h->B = B; h->cur_len = L0; h->step = 0; h->max_new = bufs->max_new; h->have_bufs = true;
+    h->B = B; h->cur_len = L0; h->prompt_len = L0; h->step = 0; h->max_new = bufs->max_new; h->have_bufs = true;
+    return CTP_OK;
+}
+
+// device-side part of ctp_gpt_rewind: step 0, nothing finished (one thread)
+__global__ void k_rewind_state(GenState* st, int B) {
+    st->step = 0; st->all_done = 0; st->ticket = 0;
+    for (int b = 0; b < B; ++b) { st->end_idx[b] = 0; st->finish[b] = 0; }
+}
+
+extern "C" ctp_status ctp_gpt_rewind(ctp_gpt* h, ctp_stream stream) {
+    CTP_REQUIRE(h && h->bound && h->have_bufs, "rewind: call prefill first");
+    CTP_REQUIRE(h->step <= 1 && h->cur_len == h->prompt_len, "rewind: a decode step has run since the prefill (step %d, cache length %d, prompt %d)",
+                h->step, h->cur_len, h->prompt_len);
+    k_rewind_state<<<1, 1, 0, (cudaStream_t)stream>>>(h->st, h->B);
+    LAUNCH_OK();
+    h->step = 0;
     return CTP_OK;
 }
 

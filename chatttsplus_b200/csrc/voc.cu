@@ -715,6 +715,14 @@ extern "C" ctp_status ctp_voc_encode(ctp_voc* h, int32_t n_samples, const float*
     return CTP_OK;
 }
 
+extern "C" ctp_status ctp_voc_quantize(ctp_voc* h, int32_t n_frames, const float* feat, int32_t* ids_out, ctp_stream stream) {
+    CTP_REQUIRE(h && h->bound && h->has_encoder, "voc_quantize: no prompt-encoder weights bound (create the handle with encoder = 1)");
+    CTP_REQUIRE(n_frames >= 1 && feat && ids_out, "voc_quantize: bad argument");
+    k_gfsq_quantize<<<n_frames, 64, 0, (cudaStream_t)stream>>>(feat, h->cfg.dvae_odim, 2, h->w.vq_in_w, h->w.vq_in_b, ids_out);
+    VLAUNCH_OK();
+    return CTP_OK;
+}
+
 extern "C" ctp_status ctp_voc_decode_mel(ctp_voc* h, int32_t n_utt, const int32_t* mel_lens_host, const float* mel, float* wav_out,
                                          const int64_t* wav_offsets_host, ctp_stream stream) {
     CTP_REQUIRE(h && h->bound && h->has_vocos, "voc_decode_mel: Vocos weights not bound");

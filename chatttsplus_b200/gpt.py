@@ -65,6 +65,23 @@ def _fold_weight_norm(g: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
     return g.float() * v.float() / v.float().norm(dim=1, keepdim=True)
 
 
+class _TrunkView:
+    """Stand-in for ``GPT.gpt`` (reference: the LlamaModel instance)."""
+
+    def __init__(self, owner: "GPT"):
+        self._owner = owner
+        self.config = owner.cfg
+
+    def cpu(self):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    def eval(self):
+        return self
+
+
 class GPT:
     class Context:
         def __init__(self):
@@ -102,7 +119,7 @@ class GPT:
         self.device = torch.device("cpu")
         self._state: Optional[Dict[str, torch.Tensor]] = None   # fp32 CPU state dict (reference key names)
         self._packed: Optional[Dict[str, torch.Tensor]] = None  # device tensors bound to the library
-        self._base_attn: Optional[Tuple[torch.Tensor, torch.Tensor]] = None  # un-merged wqkv / wo while LoRA is loaded
+        self._base_w: Optional[Dict[str, torch.Tensor]] = None  # un-merged wqkv / wo / wgu / wdown while a LoRA adapter is merged
         self._handle = C.c_void_p(0)
         self._max_batch = int(kwargs.get("max_batch", 32))
         self._max_seq = 0
@@ -184,7 +201,7 @@ class GPT:
             p["head_text"] = _fold_weight_norm(sd["head_text.parametrizations.weight.original0"],
                                                sd["head_text.parametrizations.weight.original1"]).to(dev, f16).contiguous()
         self._packed = p
-        self._base_attn = None
+        self._base_w = None
         self._bind()
 
     def _ensure_handle(self, batch: int, seq: int):
@@ -222,53 +239,118 @@ class GPT:
             pass
 
     # ---- LoRA (A12) --------------------------------------------------------------------------------------
-    def merge_lora(self, lora_sd: Dict[str, torch.Tensor], alpha: float, r: int):
-        """W' = W + (alpha/r) * B @ A on q/k/v/o of every layer that has an adapter (peft merge_and_unload)."""
+    _LORA_TARGETS = ("q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj")
+
+    @staticmethod
+    def _pattern_value(pattern: Optional[dict], module_name: str, default):
+        """peft ``rank_pattern`` / ``alpha_pattern`` lookup: the first key that equals the module name or matches its tail."""
+        import re
+        for key, val in (pattern or {}).items():
+            if module_name == key or re.match(rf"(.*\.)?{key}$", module_name):
+                return val
+        return default
+
+    def merge_lora(self, lora_sd: Dict[str, torch.Tensor], alpha: float, r: int, use_rslora: bool = False,
+                   rank_pattern: Optional[dict] = None, alpha_pattern: Optional[dict] = None, fan_in_fan_out: bool = False):
+        """peft ``merge_and_unload`` for LoRA adapters: W' = W + scale * B @ A on every adapted Linear of the trunk — q/k/v/o
+        (configs/train/train_voice_clone_lora.yaml:72-80) and gate/up/down — with scale = alpha / r (alpha / sqrt(r) for rsLoRA),
+        per-module r / alpha from ``rank_pattern`` / ``alpha_pattern``.  Every ``lora_*`` tensor of the adapter must be consumed:
+        an adapter on a module this trunk does not have (or any DoRA / embedding adapter tensor) raises instead of being dropped."""
         if self._packed is None:
             raise _lib.CtpError("merge_lora: model not on device")
         c = self.cfg
-        H = c.hidden_size
-        if self._base_attn is None:
-            self._base_attn = (self._packed["wqkv"].clone(), self._packed["wo"].clone())
-        wqkv = self._base_attn[0].float()
-        wo = self._base_attn[1].float()
-        s = float(alpha) / float(r)
+        H, I = c.hidden_size, c.intermediate_size
+        if self._base_w is None:
+            self._base_w = {k: self._packed[k].clone() for k in ("wqkv", "wo", "wgu", "wdown")}
+        w = {k: v.float() for k, v in self._base_w.items()}
+        consumed = set()
         for l in range(c.num_hidden_layers):
-            for j, nm in enumerate(("q_proj", "k_proj", "v_proj", "o_proj")):
+            for nm in self._LORA_TARGETS:
+                sub = "self_attn" if nm in ("q_proj", "k_proj", "v_proj", "o_proj") else "mlp"
                 a = b = None
                 for pre in ("base_model.model.", "base_model.model.model.", ""):
-                    ka = f"{pre}layers.{l}.self_attn.{nm}.lora_A.weight"
-                    if ka in lora_sd:
-                        a, b = lora_sd[ka], lora_sd[ka.replace("lora_A", "lora_B")]
+                    for mid in ("lora_A.weight", "lora_A.default.weight"):
+                        ka = f"{pre}layers.{l}.{sub}.{nm}.{mid}"
+                        if ka in lora_sd:
+                            kb = ka.replace("lora_A", "lora_B")
+                            if kb not in lora_sd:
+                                raise _lib.CtpError(f"LoRA adapter has {ka} but not {kb}")
+                            a, b = lora_sd[ka], lora_sd[kb]
+                            consumed.update((ka, kb))
+                            break
+                    if a is not None:
                         break
                 if a is None:
                     continue
-                delta = s * (b.to(self.device, torch.float32) @ a.to(self.device, torch.float32))
-                if j < 3:
-                    wqkv[l, j * H:(j + 1) * H] += delta
+                name = f"layers.{l}.{sub}.{nm}"
+                r_m = int(a.shape[0])
+                r_cfg = int(self._pattern_value(rank_pattern, name, r))
+                if r_cfg != r_m:
+                    raise _lib.CtpError(f"LoRA rank mismatch for {name}: adapter tensors have r={r_m}, config says {r_cfg}")
+                alpha_m = float(self._pattern_value(alpha_pattern, name, alpha))
+                scale = alpha_m / (r_m ** 0.5) if use_rslora else alpha_m / r_m
+                delta = scale * (b.to(self.device, torch.float32) @ a.to(self.device, torch.float32))
+                if fan_in_fan_out:
+                    delta = delta.t()
+                if nm in ("q_proj", "k_proj", "v_proj"):
+                    j = ("q_proj", "k_proj", "v_proj").index(nm)
+                    w["wqkv"][l, j * H:(j + 1) * H] += delta
+                elif nm == "o_proj":
+                    w["wo"][l] += delta
+                elif nm == "gate_proj":
+                    w["wgu"][l, :I] += delta
+                elif nm == "up_proj":
+                    w["wgu"][l, I:] += delta
                 else:
-                    wo[l] += delta
-        self._packed["wqkv"] = wqkv.to(torch.float16).contiguous()
-        self._packed["wo"] = wo.to(torch.float16).contiguous()
+                    w["wdown"][l] += delta
+        unused = sorted(k for k in lora_sd if "lora_" in k and k not in consumed)
+        if unused:
+            raise _lib.CtpError(f"LoRA adapter tensors not consumed by the merge (unsupported target or variant): {unused[:4]}"
+                                f"{' ...' if len(unused) > 4 else ''}")
+        if not consumed:
+            raise _lib.CtpError("LoRA adapter holds no lora_A / lora_B tensors for this trunk")
+        for k in w:
+            self._packed[k] = w[k].to(torch.float16).contiguous()
         self._bind()
 
     def load_lora(self, lora_path: str):
-        """peft adapter directory: adapter_config.json (r, lora_alpha) + adapter_model.safetensors|.bin."""
+        """peft adapter directory: adapter_config.json + adapter_model.safetensors|.bin (webui.py:48-62)."""
         with open(os.path.join(lora_path, "adapter_config.json"), "r", encoding="utf-8") as f:
             ac = json.load(f)
+        if str(ac.get("peft_type", "LORA")).upper() != "LORA":
+            raise _lib.CtpError(f"adapter type {ac.get('peft_type')!r} is not supported (LoRA only)")
+        for key in ("use_dora", "modules_to_save", "layers_to_transform", "layer_replication", "megatron_config"):
+            if ac.get(key):   # peft's merge honours these; the native merge does not implement them
+                raise _lib.CtpError(f"adapter_config.json: {key}={ac[key]!r} is not supported by the native merge")
+        if ac.get("bias", "none") != "none":
+            raise _lib.CtpError(f"adapter_config.json: bias={ac['bias']!r} is not supported (the trunk has no biases)")
         st_path = os.path.join(lora_path, "adapter_model.safetensors")
         if os.path.exists(st_path):
             from safetensors.torch import load_file
             sd = load_file(st_path)
         else:
             sd = torch.load(os.path.join(lora_path, "adapter_model.bin"), weights_only=True, map_location="cpu")
-        self.merge_lora(sd, float(ac.get("lora_alpha", 16)), int(ac.get("r", 8)))
+        self.merge_lora(sd, float(ac.get("lora_alpha", 16)), int(ac.get("r", 8)), use_rslora=bool(ac.get("use_rslora", False)),
+                        rank_pattern=ac.get("rank_pattern") or None, alpha_pattern=ac.get("alpha_pattern") or None,
+                        fan_in_fan_out=bool(ac.get("fan_in_fan_out", False)))
 
     def unload_lora(self):
-        if self._base_attn is not None:
-            self._packed["wqkv"], self._packed["wo"] = self._base_attn
-            self._base_attn = None
+        if self._base_w is not None:
+            self._packed.update(self._base_w)
+            self._base_w = None
             self._bind()
+
+    @property
+    def gpt(self):
+        """The reference swaps / parks ``GPT.gpt`` (the LlamaModel) around a LoRA merge (chattts_plus_pipeline.py:425-432,468-470).
+        Here the trunk lives in the library handle; this view keeps attribute access and ``.cpu()`` / ``.to()`` chains harmless.
+        Use ``load_lora`` / ``unload_lora`` for adapters."""
+        return _TrunkView(self)
+
+    @gpt.setter
+    def gpt(self, value):
+        if not isinstance(value, _TrunkView):
+            raise _lib.CtpError("GPT.gpt cannot be replaced by a torch module: the trunk runs in libctp; use GPT.load_lora(dir)")
 
     # ---- get_emb (A1) ------------------------------------------------------------------------------------
     def __call__(self, input_ids: torch.Tensor, text_mask: torch.Tensor) -> torch.Tensor:
@@ -371,17 +453,16 @@ class GPT:
                 return torch.rand(max_new, B * cols, device=dev, dtype=torch.float32)
 
             u = draw_uniforms()
-            # step 0 (+ gpt.py:496-525: if any sequence ends immediately, draw again)
-            for attempt in range(8):
+            # step 0 (+ gpt.py:496-525: if any sequence ends immediately, draw again).  A retry only rewinds the generation state
+            # (the prompt's KV cache and last-position logits are unchanged) and redraws; the draw of the last attempt is kept.
+            attempts = 8 if (ensure_non_empty and uniforms is None) else 1
+            for attempt in range(attempts):
                 _lib.check(lib.ctp_gpt_sample_step(self._handle, C.byref(cfg), _lib.ptr(u[0]), strm), "ctp_gpt_sample_step")
-                if not ensure_non_empty or uniforms is not None:
-                    break
-                if not bool(finish.any().item()):
+                if attempt + 1 == attempts or not bool(finish.any().item()):
                     break
                 self.logger.info("unexpected end at index %s; regenerate in order to ensure non-empty"
                                  % str(finish.nonzero().flatten().tolist()))
-                # logits of the prompt are unchanged: rewind the generation state and redraw step 0
-                _lib.check(lib.ctp_gpt_prefill(self._handle, B, L0, _lib.ptr(emb32), pad_arr, C.byref(bufs), text_flag, strm), "ctp_gpt_prefill")
+                _lib.check(lib.ctp_gpt_rewind(self._handle, strm), "ctp_gpt_rewind")
                 u = draw_uniforms()
 
             pbar = None
@@ -422,6 +503,8 @@ class GPT:
             if evs:
                 evs[2].record()
             torch.cuda.current_stream().synchronize()
+            # raw buffers of the finished run (parity tests compare them with the oracle; finished rows keep decoding, gpt.py:483-494)
+            self._last_run = {"ids_buf": ids_buf, "hid_buf": hid_buf, "end_idx": end_idx, "finish": finish, "steps": done_total}
             if evs:
                 self.timing = {"prefill_ms": evs[0].elapsed_time(evs[1]), "decode_ms": evs[1].elapsed_time(evs[2]),
                                "decode_steps": done_total - 1, "B": B, "L0": L0}
@@ -432,7 +515,9 @@ class GPT:
                     self.logger.info("generation is interrupted")
                 else:
                     self.logger.info(f"incomplete result. hit max_new_token: {max_new_token}")
-            yield outputs()
+            last = outputs()
+            last.is_final = True   # (extra attribute: stream consumers flush their tail on it)
+            yield last
 
     # ---- low-level hooks used by the parity tests and bench ----------------------------------------------
     def logits_view(self, B: int, text: bool = False) -> torch.Tensor:

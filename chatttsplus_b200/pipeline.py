@@ -8,7 +8,8 @@ Kept verbatim from the reference (so ``webui.py`` and ``tests/test_pipelines.py`
   speaker_audio_text, lora_path, slice_size, speaker_save_dir})`` -> generator of ``List[Tensor]`` (:472-579),
   ``sample_random_speaker`` / ``_encode_spk_emb`` (:307-331).
 Differences (all host-side): no hub downloads (offline image: missing checkpoints raise); LoRA is merged natively
-(no peft); utterances are vocoded as one batch; the broken stream slicing (:445-464) is replaced by per-chunk yields.
+(no peft); utterances are vocoded as one batch; the broken stream slicing (:445-464: a Python list indexed like an array) is
+replaced by the evident intent: every yield carries the new samples only (incremental vocoder with a receptive-field halo).
 ``ChatTTSPlusPipeline.from_models`` builds a pipeline from already constructed models (synthetic-weight tests, bench).
 """
 from __future__ import annotations
@@ -122,9 +123,29 @@ class ChatTTSPlusPipeline:
                            logits_warpers=warpers, logits_processors=procs, infer_text=False, return_hidden=use_decoder,
                            stream=stream, show_tqdm=params.show_tqdm, ensure_non_empty=params.ensure_non_empty,
                            stream_batch=params.stream_batch, uniforms=uniforms)
+        if not stream:
+            for result in gen:
+                wavs = self._decode_to_wavs(result.hiddens if use_decoder else result.ids, use_decoder)
+                yield (wavs, result) if return_codes else wavs
+            return
+        # stream mode (chattts_plus_pipeline.py:417-419,445-464): every yield carries only the NEW samples of each utterance, so a caller
+        # that appends the chunks (webui.py:162-166: gr.Audio(streaming=True)) plays each sample once.  The first
+        # ``pass_first_n_batches`` chunks are held back like the reference does and ride along with the next one.
+        sv = _voc_mod.StreamingVocoder(self._engine(use_decoder), int(input_ids.shape[0]))
+        held = None
+        n_chunk = 0
         for result in gen:
-            wavs = self._decode_to_wavs(result.hiddens if use_decoder else result.ids, use_decoder)
-            yield (wavs, result) if return_codes else wavs
+            final = bool(getattr(result, "is_final", False))
+            self.logger.info("Start decode to wavs >>>>")
+            new = sv.push(result.hiddens if use_decoder else result.ids, final=final)
+            n_chunk += 1
+            if held is not None:
+                new = [torch.cat([h, w]) for h, w in zip(held, new)]
+                held = None
+            if not final and n_chunk <= int(getattr(params, "pass_first_n_batches", 0) or 0):
+                held = new
+                continue
+            yield (new, result) if return_codes else new
 
     @torch.no_grad()
     def _infer_code(self, text, stream: bool, return_hidden: bool, params: InferCodeParams):

@@ -192,17 +192,23 @@ def make_vocos_state(cfg: VocosConfig = VocosConfig(), seed: int = 9876) -> Dict
     return sd
 
 
-def make_lora_state(cfg: GPTConfig = GPTConfig(), r: int = 8, seed: int = 777) -> Dict[str, torch.Tensor]:
+def make_lora_state(cfg: GPTConfig = GPTConfig(), r: int = 8, seed: int = 777, mlp: bool = False) -> Dict[str, torch.Tensor]:
     """peft-adapter-shaped tensors (keys as written by peft ``save_pretrained`` for a LlamaModel wrapped in
-    PeftModel: base_model.model.layers.N.self_attn.{q,k,v,o}_proj.lora_{A,B}.weight)."""
+    PeftModel: base_model.model.layers.N.self_attn.{q,k,v,o}_proj.lora_{A,B}.weight; ``mlp=True`` adds the
+    mlp.{gate,up,down}_proj targets configs/train/train_voice_clone_lora.yaml lists as options)."""
     g = _gen(seed)
-    H = cfg.hidden_size
+    H, I = cfg.hidden_size, cfg.intermediate_size
     sd = {}
     for l in range(cfg.num_hidden_layers):
         for nm in ("q_proj", "k_proj", "v_proj", "o_proj"):
             p = f"base_model.model.layers.{l}.self_attn.{nm}."
             sd[p + "lora_A.weight"] = _n(g, r, H, std=0.02)
             sd[p + "lora_B.weight"] = _n(g, H, r, std=0.02)
+        if mlp:
+            for nm, (fin, fout) in (("gate_proj", (H, I)), ("up_proj", (H, I)), ("down_proj", (I, H))):
+                p = f"base_model.model.layers.{l}.mlp.{nm}."
+                sd[p + "lora_A.weight"] = _n(g, r, fin, std=0.02)
+                sd[p + "lora_B.weight"] = _n(g, fout, r, std=0.02)
     return sd
 
 

@@ -240,6 +240,22 @@ class DVAE:
         ind = torch.stack(outs)
         return (ind, torch.stack(feats)) if return_features else ind
 
+    @torch.inference_mode()
+    def quantize_features(self, x: torch.Tensor) -> torch.Tensor:
+        """GFSQ.forward alone (dvae.py:98-126): encoder features ``[B, odim, T]`` -> indices ``[B, G*R, T]`` int64."""
+        if self._enc is None:
+            raise _lib.CtpError("this DVAE has no prompt encoder on a CUDA device")
+        outs = []
+        with torch.cuda.device(self.device):
+            for b in range(x.shape[0]):
+                f = x[b].to(self.device, torch.float32).t().contiguous()          # [T, odim]
+                self._ensure_encoder(64)
+                ids = torch.empty(f.shape[0], self.cfg.vq_G * self.cfg.vq_R, device=self.device, dtype=torch.int32)
+                _lib.check(_lib.lib().ctp_voc_quantize(self._enc_handle, f.shape[0], _lib.ptr(f), _lib.ptr(ids), _lib.stream_ptr()),
+                           "ctp_voc_quantize")
+                outs.append(ids.permute(1, 0).long())
+        return torch.stack(outs)
+
     def __del__(self):
         try:
             if self._enc_handle:
@@ -448,3 +464,61 @@ class VocoderEngine:
             _lib.check(_lib.lib().ctp_voc_decode_mel(self._handle, n, (C.c_int32 * n)(*lens), _lib.ptr(src), _lib.ptr(wav),
                                                      (C.c_int64 * n)(*offs[:-1].tolist()), _lib.stream_ptr()), "ctp_voc_decode_mel")
         return [wav[int(offs[k]): int(offs[k + 1])] for k in range(n)]
+
+
+# receptive field of one waveform sample in mel frames: DVAE conv_in 2 + 12 ConvNeXt blocks x (3 taps x dilation 2) + out_conv 1 = 75,
+# Vocos embed 3 + 8 blocks x 3 = 27, ISTFT overlap (n_fft / hop = 4 frames, i.e. +-2) -> 104 mel frames = 52 code frames each side
+def vocoder_halo_code_frames(dvae: DVAE, vocos: Vocos) -> int:
+    dc, vc = dvae.cfg, vocos.cfg
+    dvae_reach = 1 + 1 + dc.n_layer * (dc.kernel // 2) * dc.dilation + 1
+    voc_reach = 3 + vc.num_layers * 3
+    istft_reach = vc.n_fft // vc.hop_length // 2
+    return (dvae_reach + voc_reach + istft_reach + 1) // 2 + 1
+
+
+class StreamingVocoder:
+    """Incremental ``_decode_to_wavs`` for stream mode (reference intent: chattts_plus_pipeline.py:441-464 yields the NEW slice
+    ``wavs[:, a:b]`` per chunk; gpt.py:533-543 hands over the growing ids / hiddens every ``stream_batch`` steps).
+
+    Each ``push`` decodes, per utterance, only a window of code frames — the frames that are new since the last push plus ``halo``
+    frames of context on either side — and returns the samples that have just become FINAL: sample s is final once every frame
+    inside its receptive field (+-halo code frames) has been generated, or the utterance has ended.  The window's own left edge is
+    ``halo`` frames before the first sample it emits, so the zero padding the kernels apply there cannot reach an emitted sample.
+    Concatenating the returned pieces reproduces the one-shot waveform; the work per chunk is bounded by
+    ``stream_batch + 2 * halo`` frames per utterance, independent of how long the utterance already is."""
+
+    def __init__(self, engine: VocoderEngine, n_utt: int, halo: Optional[int] = None):
+        self.engine = engine
+        self.halo = int(halo) if halo is not None else vocoder_halo_code_frames(engine.dvae, engine.vocos)
+        self.emitted = [0] * n_utt          # samples already returned, per utterance
+        self.frames_decoded = 0             # bookkeeping for tests: code frames sent through the kernels so far
+        self.hop2 = 2 * engine.vocos.cfg.hop_length   # samples per code frame
+
+    @torch.inference_mode()
+    def push(self, items: Sequence[torch.Tensor], final: bool) -> List[torch.Tensor]:
+        dev = self.engine.device
+        hop2, halo = self.hop2, self.halo
+        win, meta = [], []
+        for i, t in enumerate(items):
+            n = int(t.shape[0])
+            total = hop2 * n - hop2 // 2 if n >= 1 else 0                      # hop * (2 n - 1)
+            upto = total if final else max(0, min(total, hop2 * (n - halo)))
+            if upto <= self.emitted[i]:
+                meta.append(None)
+                continue
+            a = max(0, self.emitted[i] // hop2 - halo)                          # first code frame of the window
+            win.append(t[a:n])
+            meta.append((a, upto))
+            self.frames_decoded += n - a
+        out = [torch.zeros(0, device=dev) for _ in items]
+        if win:
+            wavs, _ = self.engine.decode_batch(win)
+            k = 0
+            for i, m in enumerate(meta):
+                if m is None:
+                    continue
+                a, upto = m
+                out[i] = wavs[k][self.emitted[i] - hop2 * a: upto - hop2 * a]
+                self.emitted[i] = upto
+                k += 1
+        return out

@@ -119,6 +119,12 @@ CTP_API ctp_status ctp_gpt_embed_prompt(ctp_gpt* h, int32_t B, int32_t L0, const
 CTP_API ctp_status ctp_gpt_prefill(ctp_gpt* h, int32_t B, int32_t L0, const float* emb, const int32_t* pad_len_host,
                                    const ctp_gen_buffers* bufs, int32_t infer_text, ctp_stream stream);
 
+/* gpt.py:496-525 (a sequence ended on the very first sample: "regenerate in order to ensure non-empty"): put the generation
+ * state back to "prefill done, nothing sampled" — step 0, end_idx / finish cleared.  The prompt's KV cache and the logits of
+ * its last position are untouched, so the retry costs one sampler launch instead of a second prefill.  Only valid while no
+ * decode step has run since the prefill. */
+CTP_API ctp_status ctp_gpt_rewind(ctp_gpt* h, ctp_stream stream);
+
 /* One trunk step on `ids` (dev int32 [B,num_vq]; NULL = the codes written by the last ctp_gpt_sample_step):
  * code embedding sum (gpt.py:398-407) -> 20 decoder layers with KV append (llama.py:689-749) -> final norm ->
  * heads (gpt.py:424-439).  This is LlamaTRTModel.predict's role (llama_trt_model.py:43-81). */
@@ -251,6 +257,10 @@ CTP_API ctp_status ctp_voc_decode_mel(ctp_voc* h, int32_t n_utt, const int32_t* 
  * NULL): dev fp32 [T2][odim] encoder output before the quantiser; *n_frames_host receives T2. */
 CTP_API ctp_status ctp_voc_encode(ctp_voc* h, int32_t n_samples, const float* audio, int32_t* ids_out, float* feat_out,
                                   int32_t* n_frames_host, ctp_stream stream);
+
+/* GFSQ.forward alone (dvae.py:98-126 -> vector_quantize_pytorch GroupedResidualFSQ.forward): encoder features dev fp32
+ * [n_frames][odim] (channels-last) -> indices dev int32 [n_frames][G*R].  Needs a prompt-encoder handle (project_in bound). */
+CTP_API ctp_status ctp_voc_quantize(ctp_voc* h, int32_t n_frames, const float* feat, int32_t* ids_out, ctp_stream stream);
 
 /* ======================================================================================================
  * Building block exposed for tests and profiling: C = epilogue(A[M,K] * B[N,K]^T), fp16 in, fp32 accumulate,

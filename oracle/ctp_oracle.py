@@ -364,19 +364,23 @@ def generate(p: Dict[str, Tensor], emb: Tensor, inputs_ids: Tensor, temperature:
 
 
 def lora_merge(p: Dict[str, Tensor], lora: Dict[str, Tensor], n_layers: int, alpha: float, r: int,
-               prefix: str = "gpt.") -> Dict[str, Tensor]:
-    """peft ``merge_and_unload`` for Linear LoRA: W' = W + (alpha/r) * B @ A on q/k/v/o
-    (chattts_plus_pipeline.py:420-434; configs/train/train_voice_clone_lora.yaml:72-80).  UNPINNED (peft absent)."""
+               prefix: str = "gpt.", use_rslora: bool = False) -> Dict[str, Tensor]:
+    """peft ``merge_and_unload`` for Linear LoRA (peft/tuners/lora/layer.py ``Linear.get_delta_weight``): W' = W + scaling * B @ A
+    with scaling = lora_alpha / r (lora_alpha / sqrt(r) when ``use_rslora``) on every adapted Linear — q/k/v/o
+    (chattts_plus_pipeline.py:420-434; configs/train/train_voice_clone_lora.yaml:72-80) and, when the adapter carries them,
+    mlp.gate/up/down.  UNPINNED against the package itself (peft is absent); pinned by the hand-derived known-answer case in
+    tests/test_oracle_golden.py::test_lora_merge_known_answer."""
     out = dict(p)
-    s = alpha / r
+    s = alpha / (r ** 0.5) if use_rslora else alpha / r
     for l in range(n_layers):
-        for nm in ("q_proj", "k_proj", "v_proj", "o_proj"):
-            a = lora.get(f"base_model.model.layers.{l}.self_attn.{nm}.lora_A.weight")
-            b = lora.get(f"base_model.model.layers.{l}.self_attn.{nm}.lora_B.weight")
-            if a is None:
-                continue
-            key = f"{prefix}layers.{l}.self_attn.{nm}.weight"
-            out[key] = p[key] + s * (b.float() @ a.float())
+        for sub, names in (("self_attn", ("q_proj", "k_proj", "v_proj", "o_proj")), ("mlp", ("gate_proj", "up_proj", "down_proj"))):
+            for nm in names:
+                a = lora.get(f"base_model.model.layers.{l}.{sub}.{nm}.lora_A.weight")
+                b = lora.get(f"base_model.model.layers.{l}.{sub}.{nm}.lora_B.weight")
+                if a is None:
+                    continue
+                key = f"{prefix}layers.{l}.{sub}.{nm}.weight"
+                out[key] = p[key] + s * (b.float() @ a.float())
     return out
 
 
@@ -523,6 +527,27 @@ def gfsq_quantize(p: Dict[str, Tensor], x: Tensor, levels: Sequence[int] = (5, 5
             out[:, :, g, r] = ((q * half_width + half_width) * basis).sum(-1).round().long()
             residual = residual - q * scale
     return out.view(B, T, G * R).transpose(1, 2)       # dvae.py:109-126: [B, T, (g r)] -> [B, G*R, T]
+
+
+def gfsq_pre_round(p: Dict[str, Tensor], x: Tensor, levels: Sequence[int] = (5, 5, 5, 5), G: int = 2, R: int = 2) -> Tensor:
+    """The values gfsq_quantize rounds, in float64: bound(residual / s_r) per (frame, group, residual level, code dimension),
+    [B, T, G, R, len(levels)].  Test helper: an index may legitimately depend on fp32 summation order only where one of these
+    sits within rounding error of k + 1/2 (a numerical tie)."""
+    B, D, T = x.shape
+    xt = x.transpose(1, 2).double()
+    gd = D // G
+    lv = torch.tensor(list(levels), dtype=torch.float64)
+    out = torch.zeros(B, T, G, R, len(levels), dtype=torch.float64)
+    for g in range(G):
+        z = F.linear(xt[..., g * gd:(g + 1) * gd], p[f"vq_layer.quantizer.rvqs.{g}.project_in.weight"].double(),
+                     p[f"vq_layer.quantizer.rvqs.{g}.project_in.bias"].double())
+        residual = fsq_bound(z, levels)
+        for r in range(R):
+            scale = (lv - 1) ** (-r)
+            v = fsq_bound(residual / scale, levels)
+            out[:, :, g, r] = v
+            residual = residual - torch.round(v) / torch.div(lv, 2, rounding_mode="floor") * scale
+    return out
 
 
 def dvae_encode(p: Dict[str, Tensor], audio: Tensor, **kw) -> Tensor:

@@ -222,29 +222,86 @@ def test_generate_end_to_end_matches_oracle_tokens():
             assert rel_rms(out.hiddens[b], ref.hiddens[b]) < 3e-3
 
 
-def test_generate_eos_stops_sequences():
-    """A head rigged to emit EOS: finish / end_idx bookkeeping (gpt.py:483-494,527-532) and early exit."""
+def _rig_eos(scale):
+    def f(sd):   # head 0 scores EOS `scale` times louder: EOS fires at scattered steps, different per sequence
+        sd["head_code.0.parametrizations.weight.original0"][625] *= scale
+    return f
+
+
+def test_generate_eos_bookkeeping_matches_oracle():
+    """A18 (gpt.py:483-494,527-532,545 and 286-311): a head rigged so that EOS really fires.  Sequences end at different steps;
+    end_idx, finish, output lengths (EOS frame excluded), hiddens lengths and the early exit follow the reference rule, and every
+    draw is the oracle's (teacher-forced on the CUDA tokens, shared uniforms, near-greedy)."""
+    from gpu_util import check_generate_against_oracle, make_gpt
+    cfg = synth.GPTConfig(num_hidden_layers=2, num_text_tokens=128)
+    gpt, osd = make_gpt(cfg, seed=70, max_batch=6, mutate=_rig_eos(2.5))
+    B, L0, max_new = 6, 9, 96
+    ids, mask, text_mask = _prompt(cfg, B, L0, seed=71, pads=[0, 2, 0, 5, 0, 1])
+    u = torch.rand(max_new, B * cfg.num_vq, generator=torch.Generator().manual_seed(72))
+    rep = check_generate_against_oracle(gpt, osd, cfg, ids, mask, text_mask, torch.tensor([0.0003] * 4), u, max_new=max_new, min_new=3)
+    print({k: v for k, v in rep.items() if k not in ("out", "ref")})
+    ends = rep["end_idx"]
+    assert min(ends) >= 3, "min_new_token bans EOS for the first 3 steps (gpt.py:477-478)"
+    assert max(ends) < max_new and len(set(ends)) > 1, f"the rig should end sequences early and at different steps: {ends}"
+    assert rep["steps"] < max_new, "early exit once every sequence has finished (gpt.py:545)"
+    assert rep["hidden_rel_rms"] < 3e-3
+    assert rep["near_tie"] <= 0.005 * (rep["exact"] + rep["near_tie"])
+    # and the free-running oracle agrees on every length when no near-tie flipped a draw
+    if rep["near_tie"] == 0:
+        free = O.generate(osd, O.gpt_embed(osd, ids, text_mask, cfg.num_vq), ids, torch.tensor([0.0003] * 4), 625, mask, n_layers=2, n_heads=12,
+                          max_new_token=max_new, min_new_token=3, sampler="uniform", uniforms=u, ensure_non_empty=False)
+        assert [int(i.shape[0]) for i in free.ids] == ends
+
+
+def test_generate_first_step_eos_regenerates_then_keeps_last_draw():
+    """gpt.py:496-525: a sequence that ends on the very first sample triggers a redraw.  With a head that ALWAYS emits EOS every one of
+    the 8 attempts ends immediately; the last draw is kept, the loop exits cleanly and every output is empty (no error from the
+    generate entry)."""
     from gpu_util import make_gpt
-    cfg = synth.GPTConfig(num_hidden_layers=1, num_text_tokens=128)
-    gpt, osd = make_gpt(cfg, seed=70, max_batch=3)
-    B, L0, max_new = 3, 6, 40
-    ids, mask, text_mask = _prompt(cfg, B, L0, seed=71)
     from chatttsplus_b200.processors import gen_logits
+    cfg = synth.GPTConfig(num_hidden_layers=1, num_text_tokens=128)
+    gpt, osd = make_gpt(cfg, seed=73, max_batch=3, mutate=_rig_eos(400.0))
+    ids, mask, text_mask = _prompt(cfg, 3, 6, seed=74)
     warpers, procs = gen_logits(num_code=625, top_P=0.7, top_K=20, repetition_penalty=1.05)
     emb = gpt(ids.cuda(), text_mask.cuda())
-    g = torch.Generator().manual_seed(72)
-    u = torch.rand(max_new, B * cfg.num_vq, generator=g)
-    temp = torch.tensor([1.0] * cfg.num_vq)
-    out = list(gpt.generate(emb, ids.cuda(), temp.cuda(), 625, mask.cuda(), max_new_token=max_new, min_new_token=0,
-                            logits_warpers=warpers, logits_processors=procs, return_hidden=True, show_tqdm=False, uniforms=u))[-1]
-    emb_ref = O.gpt_embed(osd, ids, text_mask, cfg.num_vq)
-    ref = O.generate(osd, emb_ref, ids, temp, 625, mask, n_layers=1, n_heads=cfg.num_attention_heads, max_new_token=max_new,
-                     sampler="uniform", uniforms=u)
-    # lengths follow the same rule even if individual draws differ at T=1: every returned frame precedes an EOS frame
-    for b in range(B):
-        assert 0 <= out.ids[b].shape[0] <= max_new
-        assert not bool((out.ids[b] == 625).any()), "EOS frame must be excluded (gpt.py:286-299)"
-        assert out.hiddens[b].shape[0] == out.ids[b].shape[0]
+    torch.manual_seed(5)
+    out = list(gpt.generate(emb, ids.cuda(), torch.tensor([0.0003] * 4).cuda(), 625, mask.cuda(), max_new_token=20, min_new_token=0,
+                            logits_warpers=warpers, logits_processors=procs, return_hidden=True, show_tqdm=False, ensure_non_empty=True))[-1]
+    # a scaled row flips sign with the hidden state: EOS is the arg-max for the rows whose projection is positive
+    ended = [int(i.shape[0]) == 0 for i in out.ids]
+    assert any(ended), "the rig should end at least one sequence on the first draw"
+    assert all(h.shape[0] == i.shape[0] for h, i in zip(out.hiddens, out.ids))
+    # min_new_token > 0 bans EOS on the first steps: nothing ends immediately, no redraw
+    out2 = list(gpt.generate(emb, ids.cuda(), torch.tensor([0.0003] * 4).cuda(), 625, mask.cuda(), max_new_token=6, min_new_token=2,
+                             logits_warpers=warpers, logits_processors=procs, return_hidden=True, show_tqdm=False, ensure_non_empty=True))[-1]
+    assert all(int(i.shape[0]) >= 2 for i in out2.ids)
+
+
+@pytest.mark.slow
+def test_generate_full_config2_512_steps_vs_oracle():
+    """BASELINE.json configs[1] at full size: B=32, 20 layers, 128-token prompts, 512 generated frames (EOS banned), near-greedy.
+    65 536 draws through prefill + 511 graph replays of the decode step; the CPU oracle (about a minute on the host cores) is
+    teacher-forced on the CUDA tokens: every draw is the oracle's or a near-tie (<= 2e-2 in raw-logit units), >= 99.9 % are the
+    oracle's exactly, hidden states within rel-RMS 3e-3."""
+    from gpu_util import check_generate_against_oracle, make_gpt
+    cfg = synth.GPTConfig()
+    gpt, osd = make_gpt(cfg, seed=1234, max_batch=32)
+    B, L0, max_new = 32, 128, 512
+    ids, mask, text_mask = _prompt(cfg, B, L0, seed=41)
+    u = torch.rand(max_new, B * cfg.num_vq, generator=torch.Generator().manual_seed(42))
+    rep = check_generate_against_oracle(gpt, osd, cfg, ids, mask, text_mask, torch.tensor([0.0003] * 4), u, max_new=max_new, min_new=max_new)
+    print({k: v for k, v in rep.items() if k not in ("out", "ref", "end_idx")})
+    total = rep["exact"] + rep["near_tie"]
+    assert rep["steps"] == max_new and total == B * 4 * max_new
+    assert rep["exact"] >= 0.999 * total, rep["exact"] / total
+    assert rep["hidden_rel_rms"] < 3e-3
+
+
+def test_trunk_context_2176_four_kv_splits():
+    """BASELINE.json configs[3] shape: B=32 at context 2172..2176 — every (b, head) K/V stream is split over four CTAs (interleaved
+    64-slot tiles, the 4-stage ring wraps eight times per CTA), ragged left padding up to 2171."""
+    cfg = synth.GPTConfig(num_hidden_layers=2, num_text_tokens=256)
+    _teacher_forced(cfg, B=32, L0=2172, steps=4, seed=37, pads=[0, 1000, 2171, 64, 2047] + [0] * 27)
 
 
 def test_lora_merge_matches_oracle():
@@ -279,6 +336,47 @@ def test_lora_merge_matches_oracle():
     assert rel_rms(with_lora, first_logits(merged)) < 5e-3
     assert rel_rms(first_logits(merged), first_logits(osd)) > 2e-2, "adapter too weak to test anything"
     assert torch.allclose(base, back, atol=1e-4)  # split-K fp32 atomics: summation order varies run to run
+
+
+def test_lora_mlp_targets_rslora_and_strictness():
+    """Adapters on gate/up/down as well as q/k/v/o (options of configs/train/train_voice_clone_lora.yaml), rsLoRA scaling; tensors the
+    merge cannot place raise instead of being dropped (peft's merge_and_unload would honour them)."""
+    from gpu_util import make_gpt, rel_rms
+    from chatttsplus_b200._lib import CtpError
+    cfg = synth.GPTConfig(num_hidden_layers=2, num_text_tokens=128)
+    gpt, osd = make_gpt(cfg, seed=83, max_batch=2, half_round_oracle=False)
+    lora = synth.make_lora_state(cfg, r=4, seed=84, mlp=True)
+    for k in lora:
+        lora[k] = lora[k] * 3
+    merged = O.lora_merge(osd, lora, cfg.num_hidden_layers, alpha=16, r=4, use_rslora=True)
+    ids, mask, text_mask = _prompt(cfg, 2, 8, seed=85)
+    emb_ref = O.gpt_embed(osd, ids, text_mask, cfg.num_vq)
+
+    def first_logits(sd):
+        return O.generate(sd, emb_ref, ids, torch.ones(4), 625, mask, n_layers=2, n_heads=12, max_new_token=1, sampler="forced",
+                          forced_ids=torch.zeros(2, 1, 4, dtype=torch.long), rep_penalty=None, top_p=None, top_k=None).logits[0]
+
+    def cuda_first_logits():
+        from chatttsplus_b200.processors import gen_logits
+        emb = gpt(ids.cuda(), text_mask.cuda())
+        list(gpt.generate(emb, ids.cuda(), torch.ones(4).cuda(), 625, mask.cuda(), max_new_token=1, logits_warpers=gen_logits(625)[0],
+                          show_tqdm=False, uniforms=torch.zeros(1, 8)))
+        return gpt.logits_view(2).cpu()
+
+    gpt.merge_lora(lora, alpha=16, r=4, use_rslora=True)
+    with_lora = cuda_first_logits()
+    assert rel_rms(with_lora, first_logits(merged)) < 5e-3
+    only_attn = O.lora_merge(osd, {k: v for k, v in lora.items() if "self_attn" in k}, 2, alpha=16, r=4, use_rslora=True)
+    assert rel_rms(first_logits(merged), first_logits(only_attn)) > 2e-2, "the MLP adapters must matter for this test to mean anything"
+    gpt.unload_lora()
+    assert rel_rms(cuda_first_logits(), first_logits(osd)) < 5e-3
+    bad = dict(lora)
+    bad["base_model.model.embed_tokens.lora_embedding_A"] = torch.zeros(4, 10)
+    with pytest.raises(CtpError, match="not consumed"):
+        gpt.merge_lora(bad, alpha=16, r=4)
+    with pytest.raises(CtpError, match="rank mismatch"):
+        gpt.merge_lora(lora, alpha=16, r=8)
+    gpt.unload_lora()
 
 
 def test_refine_text_pass_matches_oracle_tokens():

@@ -182,19 +182,58 @@ def test_zero_shot_speaker_prompt_flow(tmp_path):
     assert len(wavs) == 1 and wavs[0].numel() == 256 * (2 * 6 - 1) and bool(torch.isfinite(wavs[0]).all())
 
 
-def test_stream_mode_yields_growing_audio(tmp_path):
-    """stream=True (scope row f2, evident intent of chattts_plus_pipeline.py:417-464): one yield per stream_batch decode
-    steps, each the audio so far; the last equals the non-streamed result."""
+def test_stream_mode_yields_increments_that_concatenate_to_the_full_waveform(tmp_path):
+    """stream=True (scope row f2, evident intent of chattts_plus_pipeline.py:417-419,445-464): every yield carries the NEW samples
+    only; appended, they are the non-streamed waveform (<= 1e-6), which itself matches the oracle.  Two utterances of different
+    prompt lengths, 2-block DVAE / Vocos (receptive-field halo 13 code frames), stream_batch 8 over 60 frames."""
     from chattts_plus.commons.utils import InferCodeParams, TorchSeedContext
     pipe, *_ = _pipeline(layers=2)
     kw = dict(skip_refine_text=True, do_text_normalization=False, do_homophone_replacement=False, do_text_optimization=False,
-              speaker_save_dir=str(tmp_path))
-    params = InferCodeParams(temperature=0.0003, max_new_token=12, min_new_token=12, show_tqdm=False, stream_batch=4)
+              speaker_save_dir=str(tmp_path), slice_size=2)
+    params = InferCodeParams(temperature=0.0003, max_new_token=60, min_new_token=60, show_tqdm=False, stream_batch=8, pass_first_n_batches=1)
+    texts = ["streaming text", "another, longer streaming text"]
     with TorchSeedContext(11):
-        chunks = [w[0].cpu() for w in pipe.infer(["streaming text"], stream=True, params_infer_code=params, **kw)]
+        chunks = [[w.cpu() for w in ws] for ws in pipe.infer(texts, stream=True, params_infer_code=params, **kw)]
     with TorchSeedContext(11):
-        full = [w[0].cpu() for w in pipe.infer(["streaming text"], stream=False, params_infer_code=params, **kw)][-1]
-    assert len(chunks) >= 3
-    lens = [c.numel() for c in chunks]
-    assert lens == sorted(lens) and lens[-1] == full.numel() == 256 * 23
-    assert torch.allclose(chunks[-1], full, atol=1e-4)
+        full = [[w.cpu() for w in ws] for ws in pipe.infer(texts, stream=False, params_infer_code=params, **kw)][-1]
+    assert len(chunks) >= 5
+    for b in range(2):
+        cat = torch.cat([c[b] for c in chunks])
+        assert cat.numel() == full[b].numel() == 256 * (2 * 60 - 1)
+        assert float((cat - full[b]).abs().max()) <= 1e-6
+        assert sum(c[b].numel() > 0 for c in chunks) >= 4, "audio must arrive in several pieces, not only at the end"
+
+
+def test_streaming_vocoder_matches_oracle_and_work_per_chunk_is_bounded():
+    """StreamingVocoder on a growing utterance with the full-depth DVAE / Vocos stacks (halo 53 code frames): the appended pieces
+    equal the one-shot CUDA waveform to 1e-6 and the ORACLE waveform to the vocoder tolerance (rms 1e-3); the frames sent through the
+    kernels per push stay <= chunk + 2 * halo however long the utterance already is."""
+    from chatttsplus_b200.vocoder import DVAE, StreamingVocoder, VocoderEngine, Vocos, vocoder_halo_code_frames
+    dcfg, vcfg = synth.DVAEConfig(), synth.VocosConfig()
+    dsd, vsd = synth.make_dvae_state(dcfg, 31), synth.make_vocos_state(vcfg, 32)
+    d = DVAE(decoder_config=dict(idim=384, odim=384, hidden=512, n_layer=12, bn_dim=128), dim=384)
+    d.load_state_dict(dsd); d.to("cuda")
+    v = Vocos(backbone_config=dict(input_channels=100, dim=512, intermediate_dim=1536, num_layers=8),
+              head_config=dict(dim=512, n_fft=1024, hop_length=256, padding="center"))
+    v.load_state_dict(vsd); v.to("cuda")
+    eng = VocoderEngine(d, v)
+    assert vocoder_halo_code_frames(d, v) == 53
+    g = torch.Generator().manual_seed(33)
+    hid = [torch.randn(n, 768, generator=g).cuda() for n in (400, 131)]
+    one_shot, _ = eng.decode_batch(hid)
+    sv = StreamingVocoder(eng, 2)
+    pieces = [[], []]
+    chunk, before = 24, 0
+    for n in range(chunk, 400 + chunk, chunk):
+        final = n >= 400
+        new = sv.push([h[: min(n, h.shape[0])] for h in hid], final=final)
+        assert sv.frames_decoded - before <= 2 * (chunk + 2 * sv.halo + 1), "work per chunk must not grow with the utterance"
+        before = sv.frames_decoded
+        for b in range(2):
+            pieces[b].append(new[b].cpu())
+    for b in range(2):
+        cat = torch.cat(pieces[b])
+        assert cat.numel() == one_shot[b].numel()
+        assert float((cat - one_shot[b].cpu()).abs().max()) <= 1e-6
+        ref = O.decode_to_wav(dsd, vsd, hid[b].cpu())
+        assert float((cat - ref).pow(2).mean().sqrt()) < 1e-3

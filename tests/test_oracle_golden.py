@@ -160,3 +160,121 @@ def test_gfsq_quantize_is_consistent_with_embed():
                                                sd[f"vq_layer.quantizer.rvqs.{gi}.project_out.bias"]))
     direct = torch.cat(outs, -1).transpose(1, 2)
     assert float((feat - direct).abs().max()) < 1e-4
+
+
+# ---- third-party arithmetic that has no reference-produced fixture (vector_quantize_pytorch, vocos, peft are absent):
+# ---- hand-derived known-answer cases against the published closed forms ------------------------------------------------------
+
+def _identity_vq_state():
+    """GFSQ projections that expose the 4-d code space: project_out = [I4; 0] (no bias), project_in = [I4 | 0]."""
+    sd = {}
+    for g in range(2):
+        wo = torch.zeros(512, 4); wo[:4] = torch.eye(4)
+        wi = torch.zeros(4, 512); wi[:, :4] = torch.eye(4)
+        sd[f"vq_layer.quantizer.rvqs.{g}.project_out.weight"] = wo
+        sd[f"vq_layer.quantizer.rvqs.{g}.project_out.bias"] = torch.zeros(512)
+        sd[f"vq_layer.quantizer.rvqs.{g}.project_in.weight"] = wi
+        sd[f"vq_layer.quantizer.rvqs.{g}.project_in.bias"] = torch.zeros(4)
+    return sd
+
+
+def test_gfsq_codebook_closed_form_all_625_codes():
+    """FSQ (Mentzer et al. 2023, "Finite Scalar Quantization", sec. 3; vector_quantize_pytorch FSQ.indices_to_codes): with levels
+    [5,5,5,5] index i has digits d_j = (i // 5^j) % 5 and code value (d_j - 2) / 2; ResidualFSQ scales residual level r by 4^-r.
+    Enumerates every index at both residual levels and in both groups (dvae.py:84-94)."""
+    sd = _identity_vq_state()
+    idx = torch.arange(625)
+    for g in range(2):
+        for r in range(2):
+            ids = torch.zeros(1, 4, 625, dtype=torch.long)
+            ids[0, g * 2 + (1 - r)] = 312          # the other level of this group: all digits 2 -> code 0
+            other = 1 - g
+            ids[0, other * 2] = 312; ids[0, other * 2 + 1] = 312
+            ids[0, g * 2 + r] = idx
+            f = O.gfsq_embed(sd, ids)              # [1, 1024, 625]
+            got = f[0, g * 512: g * 512 + 4].t()   # [625, 4]
+            exp = torch.stack([((idx // 5 ** j) % 5 - 2).float() / 2 for j in range(4)], 1) * (4.0 ** -r)
+            assert torch.equal(got, exp), (g, r)
+            assert float(f[0, (1 - g) * 512: (1 - g) * 512 + 4].abs().max()) == 0.0
+
+
+def test_fsq_quantiser_thresholds_closed_form():
+    """ResidualFSQ.forward (vector_quantize_pytorch 1.17.8): residual = bound(project_in(x)); per level FSQ.quantize =
+    round(bound(residual / s_r)) / (L // 2) with bound(z) = tanh(z) * (L-1)(1+eps)/2, L = 5, eps = 1e-3.  The value is therefore
+    bounded TWICE before the first rounding: the level-0 decision boundaries sit at z = atanh(atanh((k + 1/2) / 2.002) / 2.002),
+    k in {-2..1}; the index packs digit_j = 2 q_j + 2 with basis 5^j."""
+    import math
+    sd = _identity_vq_state()
+    half_l = 4 * (1 + 1e-3) / 2
+    for k in (-2, -1, 0, 1):
+        zb = math.atanh(math.atanh((k + 0.5) / half_l) / half_l)
+        for dz, digit in ((-1e-4, k + 2), (1e-4, k + 3)):
+            x = torch.zeros(1, 1024, 1)
+            x[0, 0, 0] = zb + dz                   # group 0, code dimension 0; everything else 0 -> digit 2
+            ids = O.gfsq_quantize(sd, x)
+            assert int(ids[0, 0, 0]) == digit + 2 * 5 + 2 * 25 + 2 * 125, (k, dz, int(ids[0, 0, 0]))
+            assert int(ids[0, 2, 0]) == 312        # the other group saw zeros
+    # second residual level: what is left after level 0, divided by 1/4, goes through the same rule
+    x = torch.zeros(1, 1024, 1)
+    x[0, 1, 0] = 0.3
+    ids = O.gfsq_quantize(sd, x)
+    res = math.tanh(0.3) * half_l                  # .5832
+    q0 = round(math.tanh(res) * half_l) / 2        # tanh(.5832)*2.002 = 1.051 -> 1 -> q0 = .5
+    assert q0 == 0.5 and int(ids[0, 0, 0]) == 312 + 1 * 5          # digit 3 in dimension 1
+    d1 = round(math.tanh((res - q0) / 0.25) * half_l) + 2
+    assert int(ids[0, 1, 0]) == 312 + (d1 - 2) * 5
+
+
+def test_lora_merge_known_answer():
+    """peft LoRA merge (peft/tuners/lora/layer.py Linear.get_delta_weight: B @ A * scaling, scaling = lora_alpha / r, or
+    lora_alpha / sqrt(r) with use_rslora) on a hand-computable case, for an attention and an MLP target."""
+    p = {"gpt.layers.0.self_attn.q_proj.weight": torch.zeros(2, 3), "gpt.layers.0.mlp.down_proj.weight": torch.ones(2, 3)}
+    A = torch.tensor([[1.0, 2.0, 3.0]])            # r = 1
+    B = torch.tensor([[1.0], [2.0]])
+    lora = {"base_model.model.layers.0.self_attn.q_proj.lora_A.weight": A, "base_model.model.layers.0.self_attn.q_proj.lora_B.weight": B,
+            "base_model.model.layers.0.mlp.down_proj.lora_A.weight": A, "base_model.model.layers.0.mlp.down_proj.lora_B.weight": B}
+    m = O.lora_merge(p, lora, 1, alpha=2.0, r=1)
+    assert torch.equal(m["gpt.layers.0.self_attn.q_proj.weight"], torch.tensor([[2.0, 4.0, 6.0], [4.0, 8.0, 12.0]]))
+    assert torch.equal(m["gpt.layers.0.mlp.down_proj.weight"], torch.tensor([[3.0, 5.0, 7.0], [5.0, 9.0, 13.0]]))
+    A4 = torch.cat([A, torch.zeros(3, 3)])         # r = 4 with three dead ranks: rsLoRA scaling = alpha / 2
+    B4 = torch.cat([B, torch.zeros(2, 3)], 1)
+    lora4 = {"base_model.model.layers.0.self_attn.q_proj.lora_A.weight": A4, "base_model.model.layers.0.self_attn.q_proj.lora_B.weight": B4}
+    m4 = O.lora_merge(p, lora4, 1, alpha=2.0, r=4, use_rslora=True)
+    assert torch.equal(m4["gpt.layers.0.self_attn.q_proj.weight"], torch.tensor([[1.0, 2.0, 3.0], [2.0, 4.0, 6.0]]))
+
+
+def _tone_head_state(k0: int, log_mag: float):
+    """ISTFTHead weights that emit one spectral line: |S[k0]| = exp(log_mag), phase(k0, frame f) = (pi/2) k0 f - pi k0 (what a
+    stationary cosine of bin k0 has under hop = n_fft / 4 when frame f starts at sample f*hop - n_fft/2); input row f is [f, 0, ...]."""
+    import math
+    sd = {"head.out.weight": torch.zeros(1026, 512), "head.out.bias": torch.zeros(1026), "head.istft.window": torch.hann_window(1024, periodic=True)}
+    sd["head.out.bias"][:513] = -40.0              # exp(-40): every other line is silent
+    sd["head.out.bias"][k0] = log_mag
+    sd["head.out.weight"][513 + k0, 0] = (math.pi / 2) * k0
+    sd["head.out.bias"][513 + k0] = -math.pi * (k0 % 2)
+    return sd
+
+
+def test_vocos_head_and_istft_pure_tone():
+    """vocos ISTFTHead + ISTFT(padding="center") on an analytic input: ONE spectral line S[k0, f] = c e^{i 2 pi k0 (hop f - N/2) / N}.
+    Every frame's inverse real FFT is (2c/N) cos(2 pi k0 n / N); istft multiplies by the periodic Hann window w, overlap-adds at
+    hop = N/4 and divides by the envelope sum w^2: with sum_f w = 2 and sum_f w^2 = 3/2 the output is (2c/N)(4/3) cos(2 pi k0 n / N).
+    torch.istft(center=True) trims N/2 and returns hop * (T - 1) samples."""
+    import math
+    k0, T = 37, 20
+    c = 64.0                                              # below the 1e2 clip
+    amp = (2 * c / 1024) * (4.0 / 3.0)
+    sd = _tone_head_state(k0, math.log(c))
+    x = torch.zeros(1, T, 512)
+    x[0, :, 0] = torch.arange(T, dtype=torch.float32)
+    S = O.vocos_head_spec(sd, x)
+    assert S.shape == (1, 513, T)
+    wav = torch.istft(S, 1024, 256, 1024, sd["head.istft.window"], center=True)
+    assert wav.shape == (1, 256 * (T - 1))         # centre padding length
+    n = torch.arange(wav.shape[1], dtype=torch.float64)
+    ref = amp * torch.cos(2 * math.pi * k0 * n / 1024)
+    assert float((wav[0].double() - ref)[512:-512].abs().max()) < 1e-4   # interior: full window overlap
+    # magnitude clip: exp(log 1e3) is clipped at 1e2 (ISTFTHead: torch.clip(mag, max=1e2))
+    sd2 = _tone_head_state(k0, math.log(1e3))
+    S2 = O.vocos_head_spec(sd2, x)
+    assert abs(float(S2[0, k0, 0].abs()) - 100.0) < 1e-3
