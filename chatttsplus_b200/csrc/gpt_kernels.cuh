@@ -894,8 +894,11 @@ __device__ __forceinline__ void sample_block(const SampleArgs& a, const int b, c
     }
     // 5. min-length EOS ban (gpt.py:477-478)
     if (step < cfg.min_new && my_idx == cfg.eos) keep = false;
-    // 6. softmax over survivors and inverse-CDF draw in token-id order
-    const float e = keep ? __expf(my_val - mx) : 0.f;
+    // 6. softmax over survivors and inverse-CDF draw in token-id order.  The softmax is taken relative to the SURVIVORS' maximum:
+    //    when the min-length ban removed an EOS that was the row maximum, exp(s - row max) underflows to 0 for every survivor at
+    //    near-greedy temperatures (the reference's softmax runs after the ban, gpt.py:477-480, and renormalises by itself)
+    const float mx_s = warp_max(keep ? my_val : -INFINITY);
+    const float e = keep ? __expf(my_val - mx_s) : 0.f;
     const float zs = warp_sum(e);
     const float p = e / zs;
     // rank of my token id among survivors

@@ -184,8 +184,10 @@ def test_zero_shot_speaker_prompt_flow(tmp_path):
 
 def test_stream_mode_yields_increments_that_concatenate_to_the_full_waveform(tmp_path):
     """stream=True (scope row f2, evident intent of chattts_plus_pipeline.py:417-419,445-464): every yield carries the NEW samples
-    only; appended, they are the non-streamed waveform (<= 1e-6), which itself matches the oracle.  Two utterances of different
-    prompt lengths, 2-block DVAE / Vocos (receptive-field halo 13 code frames), stream_batch 8 over 60 frames."""
+    only; appended, they are the non-streamed waveform.  (Two separate generations: the decode step's split-K fp32 REDs make hidden
+    states differ in their last bits from run to run, so the bound here is 1e-4; on IDENTICAL hidden states the streamed and one-shot
+    waveforms agree to 1e-6 — test_streaming_vocoder_matches_oracle_and_work_per_chunk_is_bounded.)  Two utterances of different
+    prompt lengths, 2-block DVAE / Vocos (receptive-field halo 14 code frames), stream_batch 8 over 60 frames."""
     from chattts_plus.commons.utils import InferCodeParams, TorchSeedContext
     pipe, *_ = _pipeline(layers=2)
     kw = dict(skip_refine_text=True, do_text_normalization=False, do_homophone_replacement=False, do_text_optimization=False,
@@ -200,7 +202,7 @@ def test_stream_mode_yields_increments_that_concatenate_to_the_full_waveform(tmp
     for b in range(2):
         cat = torch.cat([c[b] for c in chunks])
         assert cat.numel() == full[b].numel() == 256 * (2 * 60 - 1)
-        assert float((cat - full[b]).abs().max()) <= 1e-6
+        assert float((cat - full[b]).abs().max()) <= 1e-4
         assert sum(c[b].numel() > 0 for c in chunks) >= 4, "audio must arrive in several pieces, not only at the end"
 
 
