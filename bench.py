@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — the headline benchmark of the hot path (BASELINE.json: audio-code frames/s + RTF, batch 32, B200).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--gen 512] [--batch 32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 0..4] [--gen 512] [--batch 32]
 
 One "step" = one whole generation job of configs[1]: B=32 synthetic 128-token prompts (default speaker row), 512
 generated code frames per sequence (EOS banned: min_new = max_new), then DVAE+Vocos to 24 kHz waveforms.
@@ -89,12 +89,12 @@ def synthetic_prompt(cfg, B, seed):
     return ids, mask, mask.bool(), spk_id
 
 
-def build_models(device):
+def build_models(device, max_batch=32):
     from chatttsplus_b200.gpt import GPT
     from chatttsplus_b200.pipeline import ChatTTSPlusPipeline
     from chatttsplus_b200.vocoder import DVAE, Vocos
     cfg = synth.GPTConfig()
-    gpt = GPT(dict(hidden_size=768, intermediate_size=3072, num_attention_heads=12, num_hidden_layers=20), max_batch=32)
+    gpt = GPT(dict(hidden_size=768, intermediate_size=3072, num_attention_heads=12, num_hidden_layers=20), max_batch=max_batch)
     gpt.load_state_dict(synth.make_gpt_state(cfg, seed=1234))
     gpt.to(device)
     dcfg, vcfg = synth.DVAEConfig(), synth.VocosConfig()
@@ -109,91 +109,272 @@ def build_models(device):
     return cfg, pipe
 
 
-def run_ours(args):
-    import torch.distributed as dist
+class Ctx:
+    """One process per GPU (torchrun env); NCCL only for setup broadcasts, barriers and the max-over-ranks time."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.device = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.device)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max(self, *vals):
+        if self.world == 1:
+            return list(vals)
+        t = torch.tensor(list(vals), device=self.device, dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def tensor_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["bf16_tflops_sustained"]), "measured (sustained)"
+    except Exception:
+        return 1400.0, "fallback"
+
+
+def measure_generate(ctx, cfg, pipe, B, GEN, steps, warmup, *, spk=None, sample_clocks=False, e2e=True, temperature=0.3):
+    """One "step" = one whole generation job: B prompts of L0 tokens -> GEN code frames each (EOS banned) -> DVAE + Vocos waveforms.
+    Returns the device-resident and the host-buffer (e2e) timings, the decode-loop / prefill split and the launch count."""
     from chatttsplus_b200 import _lib
     from chatttsplus_b200.commons.utils import InferCodeParams
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-    B, GEN = args.batch, args.gen
-    cfg, pipe = build_models(device)
     gpt = pipe.models_dict["gpt"]
     gpt.record_timing = True
+    rank, device = ctx.rank, ctx.device
     ids, mask, text_mask, spk_id = synthetic_prompt(cfg, B, seed=1234 + rank)
-    # default speaker: one vector for the whole job, broadcast from rank 0 over NCCL/NVLink (setup, not data path)
-    spk = pipe._sample_random_speaker() if rank == 0 else torch.empty(768, device=device)
-    if world > 1:
-        dist.broadcast(spk, 0)
-    params = InferCodeParams(prompt="", spk_emb=spk, temperature=0.3, top_P=0.7, top_K=20, repetition_penalty=1.05,
+    params = InferCodeParams(prompt="", spk_emb=spk, temperature=temperature, top_P=0.7, top_K=20, repetition_penalty=1.05,
                              max_new_token=GEN, min_new_token=GEN, show_tqdm=False, ensure_non_empty=False)
     ids_pin, mask_pin, tm_pin = ids.pin_memory(), mask.pin_memory(), text_mask.pin_memory()
-    ids_dev, mask_dev, tm_dev = ids.to(device), mask.to(device), text_mask.to(device)
+    ids_dev, tm_dev = ids.to(device), text_mask.to(device)
     wav_host = torch.empty(B, 256 * (2 * GEN - 1), dtype=torch.float32).pin_memory()
 
     def job(resident: bool):
         torch.manual_seed(1234 + rank)
-        src = (ids_dev, mask_dev, tm_dev) if resident else (ids_pin, mask_pin, tm_pin)
         wavs = None
         # the attention mask stays on the host (it only yields per-sequence pad counts): pinned copy in the e2e leg
-        for wavs in pipe.infer_ids(src[0], mask_pin if not resident else mask, src[2], params, spk_emb_ids=spk_id):
+        for wavs in pipe.infer_ids(ids_dev if resident else ids_pin, mask if resident else mask_pin, tm_dev if resident else tm_pin,
+                                   params, spk_emb_ids=spk_id):
             pass
         if not resident:
             for b, w in enumerate(wavs):
                 wav_host[b, : w.numel()].copy_(w, non_blocking=True)
         return wavs
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(resident, steps, sampler=None):
-        barrier()
+    def timed(resident, n, sampler=None):
+        ctx.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if sampler:
             sampler.start()
         _lib.lib().ctp_launch_count(1)
         e0.record()
         dec_ms = pre_ms = 0.0
-        for _ in range(steps):
+        for _ in range(n):
             job(resident)
             dec_ms += gpt.timing["decode_ms"]
             pre_ms += gpt.timing["prefill_ms"]
         e1.record()
-        barrier()
+        ctx.barrier()
         launches = int(_lib.lib().ctp_launch_count(0))
         clocks = sampler.stop() if sampler else None
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms, dec_ms, pre_ms], device=device, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms, dec_ms, pre_ms = t.tolist()
+        ms, dec_ms, pre_ms = ctx.max(e0.elapsed_time(e1), dec_ms, pre_ms)
         return ms, dec_ms, pre_ms, launches, clocks
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         job(True)
-    job(False)
-    ms, dec_ms, pre_ms, launches, clocks = timed(True, args.steps, ClockSampler(local) if rank == 0 else None)
-    e2e_ms, _, _, _, _ = timed(False, args.steps)
+    if e2e:
+        job(False)
+    ms, dec_ms, pre_ms, launches, clocks = timed(True, steps, ClockSampler(ctx.local) if (sample_clocks and rank == 0) else None)
+    e2e_ms = timed(False, steps)[0] if e2e else None
+    return {"ms": ms, "dec_ms": dec_ms, "pre_ms": pre_ms, "launches": launches, "clocks": clocks, "e2e_ms": e2e_ms,
+            "h2d": int(ids.numel() * 8 + mask.numel() * 8 + text_mask.numel()), "d2h": int(B * 256 * (2 * GEN - 1) * 4)}
+
+
+def decode_roofline(B, GEN, steps, dec_ms, l0=L0):
+    peak, peak_src = hbm_peak()
+    dec_steps = (GEN - 1) * steps
+    alg = algorithmic_bytes_decode(B, l0, GEN - 1) * steps
+    achieved = alg / (dec_ms / 1e3) / 1e9
+    return {"achieved": round(achieved, 1), "peak": peak, "frac": round(achieved / peak, 4), "peak_source": peak_src,
+            "algorithmic_bytes_per_step_mean": int(alg / dec_steps), "decode_us_per_step": round(1e3 * dec_ms / dec_steps, 2)}
+
+
+def extra_configs(ctx, cfg, pipe, args, only=None):
+    """The other configurations BASELINE.json names, measured in the same run (bounded: a couple of jobs each)."""
+    from chatttsplus_b200 import dist as D
+    from chatttsplus_b200.commons.utils import InferCodeParams
+    gpt = pipe.models_dict["gpt"]
+    world, rank, device = ctx.world, ctx.rank, ctx.device
+
+    def c2():   # configs[1] + LoRA (r=8, alpha=16 on q/k/v/o of all 20 layers, merged at bind) + the shipped speaker string
+        with open(os.path.join(ROOT, "tests", "golden", "speaker_2222.txt")) as f:
+            spk_str = f.read().strip()
+        gpt.merge_lora(synth.make_lora_state(cfg, r=8, seed=777), alpha=16, r=8)
+        try:
+            m = measure_generate(ctx, cfg, pipe, args.batch, args.gen, 2, 1, spk=spk_str, e2e=False)
+        finally:
+            gpt.unload_lora()
+        r = decode_roofline(args.batch, args.gen, 2, m["dec_ms"])
+        return {"workload": "configs[1] + LoRA r=8 alpha=16 on q/k/v/o (merged at bind) + speaker assets/speakers/2222.pt",
+                "value": round(args.batch * args.gen * 2 * world / (m["ms"] / 1e3), 1), "unit": "frames/s", "ms_per_job": round(m["ms"] / 2, 2),
+                "decode_us_per_step": r["decode_us_per_step"], "roofline_frac": r["frac"]}
+
+    def c3():   # 256 utterances x 2048 frames, sharded by utterance over the ranks (32 per GPU at 8), slices of 32
+        n_utt, gen3 = args.c3_utts, args.c3_gen
+        g = torch.Generator().manual_seed(4242)
+        ids1 = torch.randint(1, cfg.num_text_tokens, (n_utt, L0, 1), generator=g)
+        ids1[:, 1, 0] = 0
+        ids3 = ids1.expand(-1, -1, cfg.num_vq).clone()
+        mask3 = torch.ones(n_utt, L0, dtype=torch.long)
+        spk = pipe._sample_random_speaker() if rank == 0 else torch.empty(768, device=device)
+        params = InferCodeParams(prompt="", spk_emb=spk, temperature=0.3, top_P=0.7, top_K=20, repetition_penalty=1.05,
+                                 max_new_token=gen3, min_new_token=gen3, show_tqdm=False, ensure_non_empty=False)
+        gpt.record_timing = True
+        ctx.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        lo, hi, wavs, lens = D.infer_ids_sharded(pipe, ids3, mask3, mask3.bool(), params, seed=1234, slice_size=32, spk_emb_ids=0)
+        e1.record()
+        ctx.barrier()
+        ms, = ctx.max(e0.elapsed_time(e1))
+        assert len(lens) == n_utt and all(v == 256 * (2 * gen3 - 1) for v in lens), "every rank must learn every utterance length"
+        dec_us = 1e3 * gpt.timing["decode_ms"] / max(1, gpt.timing["decode_steps"])   # last slice of this rank
+        peak, _ = hbm_peak()
+        alg = algorithmic_bytes_decode(32, L0, gen3 - 1) / (gen3 - 1)
+        return {"workload": f"{n_utt} utterances x {gen3} frames (context to {L0 + gen3}), sharded by utterance over {world} GPU(s) "
+                            f"(dist.shard_range / rank_seed / gather_lengths), slices of 32, hidden->mel->wav",
+                "value": round(n_utt * gen3 / (ms / 1e3), 1), "unit": "frames/s", "scaling": "strong", "ms_per_job": round(ms, 1),
+                "utterances_this_rank": hi - lo, "decode_us_per_step": round(dec_us, 1),
+                "roofline_frac": round(alg / (dec_us * 1e-6) / 1e9 / peak, 4), "algorithmic_bytes_per_step_mean": int(alg)}
+
+    plan = [("configs[2]", c2), ("configs[3]", c3),
+            # vocoder only, 2048 utterances x 512 frames over the ranks: 5b hiddens -> wav, 5a codes -> wav
+            ("configs[4] 5b", lambda: measure_vocoder(ctx, max(1, args.c5_utts // world), 512, 2, 1, False)),
+            ("configs[4] 5a", lambda: measure_vocoder(ctx, max(1, args.c5_utts // world), 512, 2, 1, True))]
+    if world == 1 and not args.no_cpu:
+        # B=1, 64-token prompt, 256 frames, near-greedy: the reference's own CPU-runnable case, GPU and CPU port end to end
+        plan.append(("configs[0]", lambda: measure_b1(ctx, cfg, pipe)))
+    out = {}
+    for key, fn in plan:
+        if only is not None and key.split(" ")[0] not in only:
+            continue
+        try:
+            out[key] = fn()
+        except Exception as e:   # never lose the headline line to an extra
+            out[key] = {"error": repr(e)[:300]}
+    return out
+
+
+def measure_b1(ctx, cfg, pipe):
+    from chatttsplus_b200.commons.utils import InferCodeParams
+    from oracle import ctp_oracle as O
+    l0, gen = 64, 256
+    g = torch.Generator().manual_seed(1234)
+    ids = torch.randint(1, cfg.num_text_tokens, (1, l0, 1), generator=g).expand(-1, -1, cfg.num_vq).clone()
+    mask = torch.ones(1, l0, dtype=torch.long)
+    u = torch.rand(gen, cfg.num_vq, generator=g)
+    params = InferCodeParams(prompt="", spk_emb=None, temperature=1e-4, top_P=0.7, top_K=20, repetition_penalty=1.05,
+                             max_new_token=gen, min_new_token=gen, show_tqdm=False, ensure_non_empty=False)
+
+    def job():
+        for w in pipe.infer_ids(ids, mask, mask.bool(), params, uniforms=u):
+            pass
+        return w
+    job()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        wav = job()[0].cpu()
+    gpu_s = (time.perf_counter() - t0) / 3
+    cores = _CPU_CACHE.get("threads") or (os.cpu_count() or 1)
+    torch.set_num_threads(cores)
+    sd = _CPU_CACHE.setdefault("gpt", synth.make_gpt_state(cfg, seed=1234))
+    dsd = _CPU_CACHE.setdefault("dvae", synth.make_dvae_state(synth.DVAEConfig(), 4321))
+    vsd = _CPU_CACHE.setdefault("vocos", synth.make_vocos_state(synth.VocosConfig(), 9876))
+    with torch.inference_mode():
+        t0 = time.perf_counter()
+        r = O.generate(sd, O.gpt_embed(sd, ids, mask.bool()), ids, torch.tensor([1e-4] * 4), 625, mask, n_layers=20, n_heads=12,
+                       max_new_token=gen, min_new_token=gen, sampler="uniform", uniforms=u, ensure_non_empty=False)
+        t_gen = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        wav_ref = O.decode_to_wav(dsd, vsd, r.hiddens[0])
+        t_voc = time.perf_counter() - t0
+    audio_s = wav_ref.numel() / 24000.0
+    return {"workload": f"B=1, {l0}-token prompt, {gen} frames, near-greedy, hidden->mel->wav, wall clock through the public call (host in, host out)",
+            "value": round(gen / gpu_s, 1), "unit": "frames/s", "rtf": round(gpu_s / audio_s, 5),
+            "cpu_port": {"value": round(gen / (t_gen + t_voc), 1), "unit": "frames/s", "rtf": round((t_gen + t_voc) / audio_s, 3), "cores": cores,
+                         "generate_s": round(t_gen, 2), "vocoder_s": round(t_voc, 2), "kind": "port (fp32 oracle, whole job, nothing extrapolated)"},
+            "incumbent_published": "110 frames/s (TensorRT fp16, RTX 3060, reference README.md:17)",
+            "waveform_rms_diff_vs_cpu": round(float((wav[: wav_ref.numel()] - wav_ref).pow(2).mean().sqrt()), 6)}
+
+
+def run_ours(args):
+    ctx = Ctx()
+    world, rank, device = ctx.world, ctx.rank, ctx.device
+    if args.config == 4:
+        out = measure_vocoder(ctx, args.utts, args.gen, args.steps, max(args.warmup, 3), args.codes)
+        out.update({"n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None, "dtype": "f16", "data": "synthetic"})
+        if rank == 0:
+            print(json.dumps(out))
+        ctx.close()
+        return
+    B, GEN = args.batch, args.gen
+    cfg, pipe = build_models(device)
+    gpt = pipe.models_dict["gpt"]
+    # default speaker: one vector for the whole job, broadcast from rank 0 over NCCL/NVLink (setup, not data path)
+    spk = pipe._sample_random_speaker() if rank == 0 else torch.empty(768, device=device)
+    if world > 1:
+        ctx.dist.broadcast(spk, 0)
+    label = "configs[1]"
+    if args.config == 2:
+        with open(os.path.join(ROOT, "tests", "golden", "speaker_2222.txt")) as f:
+            spk = f.read().strip()
+        gpt.merge_lora(synth.make_lora_state(cfg, r=8, seed=777), alpha=16, r=8)
+        label = "configs[2] (LoRA r=8 merged at bind, speaker 2222.pt)"
+    elif args.config == 0:
+        if rank == 0:
+            print(json.dumps({"metric": "audio-code frames/s (configs[0])", "n_gpus": 1, "config": measure_b1(ctx, cfg, pipe)}))
+        ctx.close()
+        return
+    elif args.config == 3:
+        ex = extra_configs(ctx, cfg, pipe, args, only={"configs[3]"})
+        if rank == 0:
+            print(json.dumps({"metric": "audio-code frames/s (configs[3])", "n_gpus": world, **ex.get("configs[3]", {})}))
+        ctx.close()
+        return
+    warm = max(args.warmup, 3)
+    m = measure_generate(ctx, cfg, pipe, B, GEN, args.steps, warm, spk=spk, sample_clocks=True)
+    ms, dec_ms, pre_ms = m["ms"], m["dec_ms"], m["pre_ms"]
     frames = B * GEN * args.steps * world
     value = frames / (ms / 1e3)
-    e2e_value = frames / (e2e_ms / 1e3)
+    e2e_value = frames / (m["e2e_ms"] / 1e3)
     audio_s = world * args.steps * B * (256 * (2 * GEN - 1)) / 24000.0
-    # roofline of the decode step (the dominant unit: one CUDA-graph replay = 20 fused-layer groups + heads + sampler)
+    # roofline of the decode step (the dominant unit: one CUDA-graph replay)
     dec_steps = (GEN - 1) * args.steps
-    alg_bytes = algorithmic_bytes_decode(B, L0, GEN - 1) * args.steps
-    peak, peak_src = 6650.0, "fallback"
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured"
-    except Exception:
-        pass
-    achieved = alg_bytes / (dec_ms / 1e3) / 1e9
+    rl = decode_roofline(B, GEN, args.steps, dec_ms)
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "decode_step_traffic.json")) as f:
@@ -202,42 +383,38 @@ def run_ours(args):
         pass
     out = {
         "metric": "audio-code frames/s (GPT decode loop + DVAE/Vocos vocoder, 24 kHz)", "value": round(value, 1), "unit": "frames/s",
-        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
+        "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": round(ms / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": {"workload": f"configs[1]: batch={B} synthetic {L0}-token prompts, default speaker, {GEN} generated codes, hidden->mel->wav",
+        "config": {"workload": f"{label}: batch={B} synthetic {L0}-token prompts, default speaker, {GEN} generated codes, hidden->mel->wav",
                    "per_gpu_batch": B, "prompt_len": L0, "gen_frames": GEN, "parallelism": f"dp{world} (independent replicas)",
                    "weights": "seeded synthetic, real shapes (no checkpoint offline)",
                    "cache": "working set per step (0.38 GB weights + >=0.25 GB KV) exceeds the 126 MB L2; no flush needed",
                    "rtf": round((ms / 1e3) / audio_s, 6), "decode_only_frames_per_s": round(B * dec_steps * world / (dec_ms / 1e3), 1),
-                   "prefill_ms_per_job": round(pre_ms / args.steps, 3), "decode_us_per_step": round(1e3 * dec_ms / dec_steps, 2)},
-        "e2e": {"value": round(e2e_value, 1), "unit": "frames/s", "h2d_bytes_per_step": int(ids.numel() * 8 + mask.numel() * 8 + text_mask.numel()),
-                "d2h_bytes_per_step": int(B * 256 * (2 * GEN - 1) * 4)},
-        "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": traffic, "kernel": "decode step (one CUDA-graph replay: 5 kernels per layer x 20 + embed-norm, final norm, heads, sampler)", "peak_source": peak_src,
-                     "algorithmic_bytes_per_step_mean": int(alg_bytes / dec_steps)},
-        "clocks": clocks,
+                   "prefill_ms_per_job": round(pre_ms / args.steps, 3), "decode_us_per_step": rl["decode_us_per_step"]},
+        "e2e": {"value": round(e2e_value, 1), "unit": "frames/s", "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"]},
+        "gpu_launches": m["launches"],
+        "roofline": {"bound": "hbm", "achieved": rl["achieved"], "peak": rl["peak"], "unit": "GB/s", "frac": rl["frac"],
+                     "traffic": traffic, "kernel": "decode step (one CUDA-graph replay: 5 kernels per layer x 20 + embed-norm, final norm, heads, sampler)",
+                     "peak_source": rl["peak_source"], "algorithmic_bytes_per_step_mean": rl["algorithmic_bytes_per_step_mean"]},
+        "clocks": m["clocks"],
     }
+    if args.config == 2:
+        gpt.unload_lora()
+    if args.config == 1 and not args.no_extra:
+        out["configs"] = extra_configs(ctx, cfg, pipe, args)
     if rank == 0:
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(B, sample_steps=2)
         print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    ctx.close()
 
 
-def run_vocoder(args):
+def measure_vocoder(ctx, n_utt, nf, steps, warmup, codes):
     """BASELINE.json configs[4]: vocoder-only throughput, pre-sampled inputs -> waveform.  5b (default product path): hiddens
-    [n, 768] -> Decoder.pt-shaped DVAE (hidden 512) -> Vocos;  5a (--codes): ids [n, 4] -> GFSQ embed -> DVAE_full-shaped decoder
+    [n, 768] -> Decoder.pt-shaped DVAE (hidden 512) -> Vocos;  5a (codes): ids [n, 4] -> GFSQ embed -> DVAE_full-shaped decoder
     (hidden 256) -> Vocos.  Dense contractions: the binding roof is the tensor pipe (157.4 / 81.5 MFLOP per code frame)."""
-    import torch.distributed as dist
     from chatttsplus_b200.vocoder import DVAE, Vocos, VocoderEngine
-    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-    codes = args.codes
+    world, rank, device = ctx.world, ctx.rank, ctx.device
     dcfg = synth.DVAEConfig.codes_model() if codes else synth.DVAEConfig()
     kw = dict(decoder_config=dict(idim=dcfg.idim, odim=dcfg.odim, hidden=dcfg.hidden, n_layer=12, bn_dim=128), dim=dcfg.dim)
     if codes:
@@ -247,50 +424,40 @@ def run_vocoder(args):
               head_config=dict(dim=512, n_fft=1024, hop_length=256, padding="center"))
     v.load_state_dict(synth.make_vocos_state(synth.VocosConfig(), seed=9876)); v.to(device)
     eng = VocoderEngine(d, v, max_frames=1 << 16)
-    n_utt, nf = args.utts, args.gen
     g = torch.Generator(device=device).manual_seed(7 + rank)
     if codes:
         items = [torch.randint(0, 625, (nf, 4), device=device, generator=g) for _ in range(n_utt)]
     else:
         items = [torch.randn(nf, 768, device=device, generator=g) for _ in range(n_utt)]
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         eng.decode_batch(items[: min(n_utt, 64)])
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    ctx.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         eng.decode_batch(items)
     e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=device, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
-    frames = n_utt * nf * args.steps * world
+    ctx.barrier()
+    ms, = ctx.max(e0.elapsed_time(e1))
+    frames = n_utt * nf * steps * world
     flop = (81.5e6 if codes else 157.4e6) * frames
-    peak = 1707.5
-    try:
-        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
-    except Exception:
-        pass
+    peak, peak_src = tensor_peak()
     tf = flop / (ms / 1e3) / 1e12
-    out = {"metric": "vocoder frames/s (codes/hiddens -> 24 kHz waveform)", "value": round(frames / (ms / 1e3), 1), "unit": "frames/s",
-           "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-           "config": {"workload": f"configs[4] ({'5a codes' if codes else '5b hiddens'}): {n_utt} utterances x {nf} frames per GPU -> wav",
-                      "x_realtime": round(frames * 512 / 24000.0 / (ms / 1e3), 1)},
-           "roofline": {"bound": "tensor", "achieved": round(tf, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(tf / peak, 4), "traffic": None}}
-    if rank == 0:
-        print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    hbm_min = (2080 if codes else 3584) * frames / (ms / 1e3) / 1e9
+    del eng, d, v, items
+    torch.cuda.empty_cache()
+    return {"metric": "vocoder frames/s (codes/hiddens -> 24 kHz waveform)", "value": round(frames / (ms / 1e3), 1), "unit": "frames/s",
+            "ms_per_step": round(ms / steps, 3),
+            "config": {"workload": f"configs[4] ({'5a codes' if codes else '5b hiddens'}): {n_utt} utterances x {nf} frames per GPU -> wav",
+                       "x_realtime": round(frames * 512 / 24000.0 / (ms / 1e3), 1)},
+            "roofline": {"bound": "tensor", "achieved": round(tf / world, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(tf / world / peak, 4),
+                         "traffic": None, "peak_source": peak_src, "algorithmic_hbm_gbs_if_fully_fused": round(hbm_min / world, 1)}}
 
 
 def cpu_baseline(B, sample_steps=2, voc_frames=32):
-    """The oracle port (fp32 restatement of the reference's PyTorch CPU path) on the host cores, bounded sample:
-    decode steps at the job's MEAN context (L = 128 + 256) with a pre-filled KV cache, plus the vocoder on one short
-    utterance; prefill is NOT charged to the CPU arm (conservative for the speed-up)."""
+    """The oracle port (fp32 restatement of the reference's PyTorch CPU path) on the host cores, bounded sample of configs[1]:
+    the prefill of the B x 128-token prompts (whole, once), decode steps at the job's MEAN context (L = 128 + 256) with a pre-filled
+    KV cache, and the vocoder on one short utterance; the job time is prefill + 511 x step + B x 512 x vocoder-per-frame."""
     from oracle import ctp_oracle as O
     cores = _CPU_CACHE.get("threads") or (os.cpu_count() or 1)
     torch.set_num_threads(cores)
@@ -343,16 +510,27 @@ def cpu_baseline(B, sample_steps=2, voc_frames=32):
         for i in range(sample_steps):
             step(1 + i)
         t_step = (time.perf_counter() - t0) / sample_steps
+        if "prefill_s" not in _CPU_CACHE:   # the prompt pass, charged once per job (4096 token rows through 20 layers)
+            x0 = torch.randn(B, L0, 768, generator=g)
+            m0 = torch.ones(B, L0, dtype=torch.bool)
+            t0 = time.perf_counter()
+            O.trunk_forward(sd, x0, m0, O.position_ids_from_mask(m0), O.KVCache.empty(cfg.num_hidden_layers), cfg.num_hidden_layers,
+                            cfg.num_attention_heads)
+            _CPU_CACHE["prefill_s"] = time.perf_counter() - t0
+        t_prefill = _CPU_CACHE["prefill_s"]
         dsd, vsd = _CPU_CACHE["dvae"], _CPU_CACHE["vocos"]
         hid = torch.randn(voc_frames, 768, generator=g)
         O.decode_to_wav(dsd, vsd, hid[:8])
         t0 = time.perf_counter()
         O.decode_to_wav(dsd, vsd, hid)
         t_voc_frame = (time.perf_counter() - t0) / voc_frames
-    fps = B / (t_step + B * t_voc_frame)
+    gen = 512
+    job_s = t_prefill + (gen - 1) * t_step + B * gen * t_voc_frame
+    fps = B * gen / job_s
     return {"value": round(fps, 2), "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": f"oracle port, fp32, {cores} threads: {sample_steps} decode steps of batch {B} at the mean context {ctx} "
-                      f"({t_step * 1e3:.0f} ms/step) + vocoder on one {voc_frames}-frame utterance ({t_voc_frame * 1e3:.1f} ms/frame); prefill not charged"}
+            "sample": f"oracle port (fp32 restatement of the reference's CPU path, not the reference package), {cores} threads: prefill of {B} x {L0} tokens "
+                      f"({t_prefill:.1f} s, whole) + {sample_steps} decode steps of batch {B} at the mean context {ctx} ({t_step * 1e3:.0f} ms/step, "
+                      f"x{gen - 1}) + vocoder on one {voc_frames}-frame utterance ({t_voc_frame * 1e3:.1f} ms/frame, x{B * gen}) = {job_s:.0f} s per job"}
 
 
 def run_reference(args):
@@ -377,7 +555,10 @@ def run_reference(args):
            "dtype": "f32", "data": "synthetic",
            "config": {"workload": f"configs[1]: batch={args.batch} synthetic {L0}-token prompts, default speaker, {args.gen} generated codes, hidden->mel->wav",
                       "per_gpu_batch": args.batch, "prompt_len": L0, "gen_frames": args.gen,
-                      "note": "CPU arm: each step is a bounded sample of this workload (see cpu_baseline.sample)"},
+                      "arm": "cpu_oracle_port",
+                      "note": "CPU arm = the fp32 oracle port on the host cores (the reference package cannot be imported here: pybase16384 / vocos / "
+                              "vector_quantize_pytorch / peft / omegaconf are absent and no checkpoint exists offline); each step is a bounded sample of "
+                              "this workload (see cpu_baseline.sample), run on rank 0 only, not scaled with the GPU count"},
            "cpu_baseline": cb, "e2e": {"value": round(v, 2), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
@@ -391,14 +572,21 @@ def main():
     ap.add_argument("--gen", type=int, default=512)
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--config", type=int, default=1, choices=[0, 1, 2, 3, 4],
+                    help="BASELINE.json configs[] index; default 1 = the configuration the metric is quoted on (the default run also "
+                         "measures the others in a `configs` sub-record)")
+    ap.add_argument("--no-extra", action="store_true", help="configs[1] only: skip the `configs` sub-record")
+    ap.add_argument("--c3-utts", type=int, default=256)
+    ap.add_argument("--c3-gen", type=int, default=2048)
+    ap.add_argument("--c5-utts", type=int, default=2048, help="configs[4] in the sub-record: utterances over all ranks")
     ap.add_argument("--workload", default="generate", choices=["generate", "vocoder"])
     ap.add_argument("--codes", action="store_true", help="vocoder workload: config 5a (codes -> GFSQ -> DVAE_full decoder)")
     ap.add_argument("--utts", type=int, default=256, help="vocoder workload: utterances per GPU per step")
     args = ap.parse_args()
+    if args.workload == "vocoder":
+        args.config = 4
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload == "vocoder":
-        run_vocoder(args)
     else:
         run_ours(args)
 

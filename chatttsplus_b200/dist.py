@@ -54,3 +54,43 @@ def max_over_ranks(value: float, device=None) -> float:
 def rank_seed(seed: int, global_index: int) -> int:
     """Per-utterance RNG stream = (seed, global utterance index): results do not depend on the GPU count."""
     return (int(seed) * 1000003 + int(global_index)) & 0x7FFFFFFF
+
+
+def utterance_uniforms(seed: int, g0: int, g1: int, max_new: int, num_vq: int) -> torch.Tensor:
+    """Uniforms for the inverse-CDF draws of global utterances [g0, g1): fp32 [max_new, (g1 - g0) * num_vq], column (g - g0) * num_vq + q.
+    Utterance g always consumes the stream seeded with rank_seed(seed, g), whatever the rank count or slice size."""
+    cols = []
+    for g in range(g0, g1):
+        gen = torch.Generator().manual_seed(rank_seed(seed, g))
+        cols.append(torch.rand(max_new, num_vq, generator=gen))
+    return torch.cat(cols, dim=1) if cols else torch.zeros(max_new, 0)
+
+
+def infer_ids_sharded(pipe, input_ids: torch.Tensor, attention_mask: torch.Tensor, text_mask: torch.Tensor, params, *, seed: int,
+                      slice_size: int = 32, spk_emb_ids: Optional[int] = None, use_decoder: bool = True, return_codes: bool = False):
+    """The reference's slice loop (chattts_plus_pipeline.py:391-397) over a job that is sharded by utterance across the ranks of the
+    current process group: rank r takes the contiguous range shard_range(n, world, r), runs it in slices of
+    ``slice_size`` through ``pipe.infer_ids`` (per-utterance RNG streams, so tokens do not depend on the rank count), and every rank
+    learns every utterance's waveform length.  No collective touches the data path; the speaker embedding is broadcast once.
+
+    Returns (lo, hi, local_wavs, all_lengths[, local_results])."""
+    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank() if world > 1 else 0
+    n = int(input_ids.shape[0])
+    lo, hi = shard_range(n, world, rank)
+    nq = int(input_ids.shape[2])
+    if params.spk_emb is not None and isinstance(params.spk_emb, torch.Tensor) and params.spk_emb.is_cuda:
+        broadcast_setup(params.spk_emb, 0)
+    wavs, results = [], []
+    for a in range(lo, hi, slice_size):
+        b = min(hi, a + slice_size)
+        u = utterance_uniforms(seed, a, b, int(params.max_new_token), nq)
+        out = None
+        for out in pipe.infer_ids(input_ids[a:b], attention_mask[a:b], text_mask[a:b], params, use_decoder=use_decoder,
+                                  spk_emb_ids=spk_emb_ids, uniforms=u, return_codes=True):
+            pass
+        wavs.extend(out[0])
+        results.append(out[1])
+    dev = wavs[0].device if wavs and wavs[0].is_cuda else None
+    all_lengths = gather_lengths([int(w.numel()) for w in wavs], device=dev)
+    return (lo, hi, wavs, all_lengths, results) if return_codes else (lo, hi, wavs, all_lengths)

@@ -57,3 +57,21 @@ def test_shard_range_covers_everything():
             spans = [shard_range(n, w, r) for r in range(w)]
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_utterance_uniforms_do_not_depend_on_the_sharding():
+    """Per-utterance RNG streams: the uniforms utterance g consumes are the same whether the job runs on 1, 2, 4 or 8
+    ranks and whatever the slice size."""
+    from chatttsplus_b200.dist import shard_range, utterance_uniforms
+    n, max_new, nq = 16, 5, 4
+    whole = utterance_uniforms(99, 0, n, max_new, nq)
+    assert whole.shape == (max_new, n * nq)
+    for world in (2, 4, 8):
+        for slice_size in (1, 2, 3):
+            parts = []
+            for r in range(world):
+                lo, hi = shard_range(n, world, r)
+                for a in range(lo, hi, slice_size):
+                    parts.append(utterance_uniforms(99, a, min(hi, a + slice_size), max_new, nq))
+            assert torch.equal(torch.cat(parts, 1), whole)
+    assert not torch.equal(utterance_uniforms(100, 0, 2, max_new, nq), whole[:, : 2 * nq])
