@@ -216,3 +216,64 @@ def make_spk_stat(seed: int = 2468, dim: int = 768) -> torch.Tensor:
     """``spk_stat.pt``: ``[2*dim]`` = (std, mean) halves (reference chattts_plus_pipeline.py:140-145)."""
     g = _gen(seed)
     return torch.cat([_u(g, dim, lo=0.5, hi=2.0), _n(g, dim, std=1.0)])
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# A complete synthetic ``CHATTTS_PLUS_CHECKPOINT_DIR`` (the files configs/infer/chattts_plus.yaml names), so the reference's own
+# callers (tests/test_pipelines.py, webui.py) can run end to end without the hub download (chattts_plus_pipeline.py:70-92).
+# ------------------------------------------------------------------------------------------------------------------------
+_SPECIAL_TOKENS = ["[Stts]", "[Ptts]", "[spk_emb]", "[empty_spk]", "[Sbreak]", "[Pbreak]", "[Ebreak]", "[uv_break]", "[v_break]", "[lbreak]",
+                   "[llbreak]", "[undefine]", "[laugh]", "[music]"] + [f"[speed_{i}]" for i in range(10)] + [f"[break_{i}]" for i in range(8)] + \
+                  [f"[oral_{i}]" for i in range(10)] + [f"[laugh_{i}]" for i in range(3)]
+
+
+def make_bert_tokenizer(texts=(), extra_chars: str = ""):
+    """A small ``BertTokenizerFast`` (what asset/tokenizer.pt pickles, tokenizer.py:27-31) with ChatTTS's control tokens and one
+    vocabulary entry per character of ``texts`` (CJK characters are split by the BERT normaliser, Latin text falls back to
+    characters through WordPiece continuation pieces)."""
+    from tokenizers import Tokenizer as _Tok, models, normalizers, pre_tokenizers
+    from transformers import BertTokenizerFast
+    base = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"]
+    chars = sorted(set("".join(texts) + extra_chars + "abcdefghijklmnopqrstuvwxyz0123456789,.!?;:'\"-") - set(" \t\n[]"))
+    vocab = base + chars + ["##" + c for c in chars] + _SPECIAL_TOKENS   # control tokens above the text ids, like the real vocabulary
+                                                                          # (the refine pass keeps ids < [break_0], chattts_plus_pipeline.py:406)
+    tok = _Tok(models.WordPiece({t: i for i, t in enumerate(dict.fromkeys(vocab))}, unk_token="[UNK]", max_input_chars_per_word=200))
+    tok.normalizer = normalizers.BertNormalizer(lowercase=True, handle_chinese_chars=True)
+    tok.pre_tokenizer = pre_tokenizers.BertPreTokenizer()
+    fast = BertTokenizerFast(tokenizer_object=tok, unk_token="[UNK]", pad_token="[PAD]", sep_token="[SEP]", cls_token="[CLS]", mask_token="[MASK]")
+    fast.add_special_tokens({"additional_special_tokens": list(_SPECIAL_TOKENS)})
+    return fast
+
+
+def write_checkpoint_dir(root: str, *, gpt_cfg: Optional[GPTConfig] = None, texts=(), lora_dir: Optional[str] = None, lora_r: int = 8,
+                         seed: int = 1234, half: bool = True) -> Dict[str, str]:
+    """Writes asset/{GPT,Decoder,DVAE_full,Vocos,spk_stat,tokenizer}.pt under ``root`` (the layout of the ChatTTS hub snapshot the
+    reference downloads) from the seeded synthetic states, and optionally a peft-format LoRA adapter directory
+    (adapter_config.json + adapter_model.safetensors, webui.py:48-62).  Shapes follow configs/infer/chattts_plus.yaml."""
+    import json
+    import os
+    gpt_cfg = gpt_cfg or GPTConfig()
+    asset = os.path.join(root, "asset")
+    os.makedirs(asset, exist_ok=True)
+    cast = (lambda sd: {k: (v.half() if v.is_floating_point() and half else v) for k, v in sd.items()})
+    paths = {}
+
+    def save(name, obj):
+        paths[name] = os.path.join(asset, name)
+        torch.save(obj, paths[name])
+
+    save("GPT.pt", cast(make_gpt_state(gpt_cfg, seed=seed)))
+    save("Decoder.pt", cast(make_dvae_state(DVAEConfig(), seed=seed + 1)))
+    save("DVAE_full.pt", cast(make_dvae_state(DVAEConfig.codes_model(encoder=True), seed=seed + 2)))
+    save("Vocos.pt", cast(make_vocos_state(VocosConfig(), seed=seed + 3)))
+    save("spk_stat.pt", make_spk_stat(seed + 4))
+    save("tokenizer.pt", make_bert_tokenizer(texts))
+    if lora_dir:
+        from safetensors.torch import save_file
+        os.makedirs(lora_dir, exist_ok=True)
+        save_file({k: v.contiguous() for k, v in make_lora_state(gpt_cfg, r=lora_r, seed=seed + 5).items()}, os.path.join(lora_dir, "adapter_model.safetensors"))
+        with open(os.path.join(lora_dir, "adapter_config.json"), "w", encoding="utf-8") as f:
+            json.dump({"peft_type": "LORA", "r": lora_r, "lora_alpha": 16, "lora_dropout": 0.05, "bias": "none", "use_rslora": False,
+                       "target_modules": ["q_proj", "v_proj", "k_proj", "o_proj"], "task_type": None, "fan_in_fan_out": False}, f)
+        paths["lora"] = lora_dir
+    return paths

@@ -50,7 +50,9 @@ class Tokenizer:
             assert prompt.size(0) == num_vq, "prompt dim 0 must equal to num_vq"
             prompt_size = prompt.size(1)
         for t in text:
-            x = self._tokenizer.encode_plus(t, return_tensors="pt", add_special_tokens=False, padding=True)
+            # tokenizer.py:69-71 calls encode_plus; transformers >= 5 dropped that alias of __call__
+            enc = getattr(self._tokenizer, "encode_plus", None) or self._tokenizer
+            x = enc(t, return_tensors="pt", add_special_tokens=False, padding=True)
             ids_lst.append(x["input_ids"].squeeze(0))
             mask_lst.append(x["attention_mask"].squeeze(0))
         L = max(i.size(0) for i in ids_lst) + prompt_size

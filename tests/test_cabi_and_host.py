@@ -126,3 +126,40 @@ def test_tokenizer_layout_and_speaker_hook():
     assert torch.allclose(emb[0, 1], torch.nn.functional.normalize(spk, dim=0)) and float(emb[0, 0].abs().sum()) == 0
     s = Tokenizer._encode_spk_emb(torch.randn(768))
     assert Tokenizer._decode_spk_emb(s).shape == (768,)
+
+
+def test_omegaconf_shim_defers_to_an_installed_package(tmp_path):
+    """the repo-root ``omegaconf`` must not shadow a real distribution.  A stand-in 'real' package later on sys.path is
+    loaded in place of the shim (and its submodules resolve); without one the PyYAML stand-in answers."""
+    import subprocess
+    import sys
+    real = tmp_path / "site" / "omegaconf"
+    real.mkdir(parents=True)
+    (real / "__init__.py").write_text("REAL = True\nclass OmegaConf:\n    @staticmethod\n    def load(p):\n        return 'real'\n")
+    (real / "sub.py").write_text("X = 1\n")
+    code = ("import sys; sys.path.insert(0, {root!r}); {extra}"
+            "import omegaconf; print(getattr(omegaconf, 'REAL', False), type(omegaconf.OmegaConf.load({yaml!r})).__name__)")
+    yaml = os.path.join(ROOT, "configs", "infer", "chattts_plus.yaml")
+    lite = subprocess.run([sys.executable, "-c", code.format(root=ROOT, extra="", yaml=yaml)], capture_output=True, text=True, check=True).stdout
+    assert lite.split() == ["False", "DictConfig"]
+    both = subprocess.run([sys.executable, "-c", code.format(root=ROOT, extra=f"sys.path.append({str(tmp_path / 'site')!r}); ", yaml=yaml)
+                           + "; import omegaconf.sub as s; print(s.X)"], capture_output=True, text=True, check=True).stdout
+    assert both.split() == ["True", "str", "1"]
+
+
+def test_synthetic_checkpoint_tokenizer_round_trip(tmp_path):
+    """asset/tokenizer.pt as the reference stores it (a pickled BertTokenizerFast, tokenizer.py:27-31) loads through ``Tokenizer(model_path)``
+    under the installed transformers (>= 5: no ``encode_plus``) and yields the left-padded [B, L, num_vq] layout of tokenizer.py:50-137."""
+    import torch
+    from chatttsplus_b200 import synth
+    from chatttsplus_b200.tokenizer import Tokenizer
+    text = "我们针对对话式任务进行了优化"
+    p = tmp_path / "tokenizer.pt"
+    torch.save(synth.make_bert_tokenizer([text]), p)
+    tok = Tokenizer(str(p))
+    assert tok.spk_emb_ids > 0 and tok.break_0_ids > tok._tokenizer.convert_tokens_to_ids("我") and tok.eos_token != tok.break_0_ids
+    ids, mask, text_mask = tok.encode([f"[Stts][spk_emb][speed_3]{text} [uv_break][Ptts]", "[Stts][empty_spk]hi[Ptts]"], 4)
+    assert ids.shape[0] == 2 and ids.shape[2] == 4 and mask.shape == ids.shape[:2]
+    assert int(mask[1].sum()) < int(mask[0].sum()) and int(mask[1, 0]) == 0, "shorter text is LEFT padded"
+    assert (ids[..., 0] == ids[..., 3]).all() and int((ids[0, :, 0] == tok.spk_emb_ids).sum()) == 1
+    assert "[UNK]" not in tok.decode(ids[:1, :, 0])[0]
