@@ -167,8 +167,8 @@ int gemm_launch_maps(const CUtensorMap& tmA, const CUtensorMap& tmB, long long a
         const int tiles_m = (int)((a_rows + GEMM_BM - 1) / GEMM_BM), tiles_n = (int)((b_rows + block_n - 1) / block_n);
         const int grid = std::min(tiles_m * tiles_n, g_sm_count);
         cudaError_t e;
-        if (block_n == 256) e = launch_k(gemm_tcgen05_persistent<256>, dim3(grid), dim3(GEMM_THREADS), (size_t)GemmPSmem<256>::TOTAL, stream, false, tmA, tmB, shp, epi, tiles_m, tiles_n);
-        else e = launch_k(gemm_tcgen05_persistent<128>, dim3(grid), dim3(GEMM_THREADS), (size_t)GemmPSmem<128>::TOTAL, stream, false, tmA, tmB, shp, epi, tiles_m, tiles_n);
+        if (block_n == 256) e = launch_k(gemm_tcgen05_persistent<256>, dim3(grid), dim3(GEMM_P_THREADS), (size_t)GemmPSmem<256>::TOTAL, stream, false, tmA, tmB, shp, epi, tiles_m, tiles_n);
+        else e = launch_k(gemm_tcgen05_persistent<128>, dim3(grid), dim3(GEMM_P_THREADS), (size_t)GemmPSmem<128>::TOTAL, stream, false, tmA, tmB, shp, epi, tiles_m, tiles_n);
         ctp_count_launch();
         if (e == cudaSuccess) e = cudaGetLastError();
         if (e != cudaSuccess) { ctp_set_error("persistent gemm launch failed: %s", cudaGetErrorString(e)); return CTP_ERR_CUDA; }

@@ -58,6 +58,7 @@ struct GemmShape {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_P_THREADS = 320;   // persistent kernel: 8 epilogue warps (0-3, 6-9) + TMA warp 4 + MMA warp 5
 
 // XMODE: 0 = token operand by TMA (fp16 matrix), 1 = XNORM, 2 = XSILU (see GemmShape)
 template <int BN, int XMODE = 0>
@@ -430,7 +431,7 @@ struct GemmPSmem {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_P_THREADS, 1)
 gemm_tcgen05_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape shp,
                         const GemmEpilogue epi, const int tiles_m, const int tiles_n) {
     using S = GemmPSmem<BN>;
@@ -454,7 +455,7 @@ gemm_tcgen05_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_co
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -505,37 +506,41 @@ gemm_tcgen05_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_co
             }
         }
     } else {
-        // epilogue warps 0..3 (128 threads): thread = one token row of the tile, 32 columns at a time
-        const int et = threadIdx.x;
+        // epilogue: EIGHT warps (0-3 and 6-9).  A warp reads the TMEM lane quarter (warp % 4); the two warps of a quarter split the
+        // tile's columns in halves, so the per-tile epilogue (up to 256 GELUs per accumulator row, which outlasted the MMAs of a
+        // K = 512 tile with four warps: tensor pipe 27 %, profiles/r2_voc_kernels_full_summary.csv) takes half as long.
+        const int q = warp & 3;                       // TMEM lanes [32 q, 32 q + 32) = tile rows
+        const int half = warp < 4 ? 0 : 1;            // columns [half * BN/2, (half + 1) * BN/2)
+        const int et = (warp < 4 ? warp : warp - 2) * 32 + lane;   // 0..255
         int j = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++j) {
             const int acc = j & 1;
             const int m0 = (t % tiles_m) * GEMM_BM, n0 = (t / tiles_m) * BN;
             // stage the per-feature vectors of this tile (previous tile's readers are past their last use: see bar below)
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int i = et; i < BN; i += 128) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            for (int i = et; i < BN; i += 256) {
                 const int f = n0 + i;
                 s_bias[i] = (epi.bias && f < epi.F) ? epi.bias[f] : 0.f;
                 s_gamma[i] = (epi.gamma && f < epi.F) ? epi.gamma[f] : 1.f;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(&tfull[acc], (j >> 1) & 1);
             tc_fence_after();
-            const int row = m0 + warp * 32 + lane;
+            const int row = m0 + q * 32 + lane;
             const bool row_ok = row < epi.T;
             const bool valid = row_ok && (epi.row_valid ? (epi.row_valid[row] != 0) : true);
+            const int c_lo = half * (BN / 2), c_hi = c_lo + BN / 2;
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
+            for (int c = c_lo; c < c_hi; c += 32) {
                 float v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c), v);
-                if (c + 32 >= BN) {   // last read of this accumulator: hand it back to the MMA warp as early as possible
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c), v);
+                if (c + 32 >= c_hi) {   // last read of this accumulator by this warp: hand it back to the MMA warp as early as possible
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[acc]);
                 }
-                if (!row_ok) continue;
                 const int f0 = n0 + c;
-                if (f0 >= epi.F) continue;
+                if (row_ok && f0 < epi.F) {   // (a block, not `continue`: the warp reconverges before the next aligned tcgen05.ld)
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] += s_bias[c + i];
                 if (epi.act_gelu) {
@@ -584,6 +589,7 @@ gemm_tcgen05_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_co
                     } else {
                         for (int i = 0; i < 32; ++i) if (f0 + i < epi.F) o[i] = v[i];
                     }
+                }
                 }
             }
         }

@@ -862,7 +862,14 @@ __device__ __forceinline__ void sample_block(const SampleArgs& a, const int b, c
         float vals[REG_V];
 #pragma unroll
         for (int i = 0; i < REG_V; ++i) { const int v = lane + 32 * i; vals[i] = v < V ? sc[v] : -INFINITY; }
+        const float inv_z = 1.0f / z;
+        const bool stop_on_mass = cfg.top_p > 0.f && cfg.top_p < 1.f;
+        float mass = 0.f;   // probability mass of the candidates selected so far (all lanes hold the same value)
         for (int k = 0; k < K; ++k) {
+            // TopP removes every rank whose mass strictly above reaches top_p (unless rank < min_keep): once the selected candidates
+            // hold that much, no further rank can survive and the remaining rounds are skipped (peaked rows need 2-4 rounds, not 20)
+            // (margin: the decision itself is taken below from the prefix sums, exactly as before; this only prunes rounds)
+            if (stop_on_mass && k >= cfg.min_keep && mass >= cfg.top_p + 1e-3f) break;
             // local arg-max as four independent chains of five, then merged (ties keep the smaller index)
             float cv[4];
             int ci[4];
@@ -884,6 +891,7 @@ __device__ __forceinline__ void sample_block(const SampleArgs& a, const int b, c
             const int bi = __reduce_min_sync(0xffffffffu, cand);
             const float bv = __shfl_sync(0xffffffffu, lv, bi & 31);
             if (lane == k) { my_val = bv; my_idx = bi; }
+            mass += __expf(bv - mx) * inv_z;
             if ((bi & 31) == lane) {
 #pragma unroll
                 for (int i = 0; i < REG_V; ++i) if (i == (bi >> 5)) vals[i] = -INFINITY;
