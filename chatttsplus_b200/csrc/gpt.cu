@@ -666,8 +666,8 @@ extern "C" ctp_status ctp_gpt_decode_step(ctp_gpt* h, const int32_t* ids, ctp_st
 
 static int check_sample_cfg(const ctp_gpt_cfg* c, const ctp_sample_cfg* cfg, int num_vq) {
     CTP_REQUIRE(cfg, "sample: null cfg");
-    CTP_REQUIRE(cfg->top_k >= 1 && cfg->top_k <= SAMPLE_MAX_K, "sample: top_k must be in [1,%d] (got %d)", SAMPLE_MAX_K, cfg->top_k);
-    CTP_REQUIRE(cfg->min_keep >= 1 && cfg->min_keep <= SAMPLE_MAX_K, "sample: min_keep out of range");
+    CTP_REQUIRE(cfg->top_k >= 0, "sample: top_k must be >= 0 (0 = no TopK warper; got %d)", cfg->top_k);
+    CTP_REQUIRE(cfg->min_keep >= 1, "sample: min_keep must be >= 1");
     CTP_REQUIRE(cfg->rep_window >= 0 && cfg->rep_window <= 32, "sample: rep_window must be <= 32");
     CTP_REQUIRE(cfg->rep_penalty > 0.f, "sample: rep_penalty must be > 0");
     for (int q = 0; q < num_vq; ++q) CTP_REQUIRE(cfg->temperature[q] > 0.f, "sample: temperature[%d] must be > 0", q);

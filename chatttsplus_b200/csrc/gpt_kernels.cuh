@@ -849,123 +849,198 @@ __device__ __forceinline__ void sample_block(const SampleArgs& a, const int b, c
     float z = 0.f;
     for (int v = lane; v < V; v += 32) z += __expf(sc[v] - mx);
     z = warp_sum(z);
-    // 3. the K best scores in rank order (K = max(top_k, min_keep), or all-by-mass when top_k is disabled)
-    int K = cfg.top_k > 0 ? max(cfg.top_k, cfg.min_keep) : SAMPLE_MAX_K;
-    K = min(min(K, SAMPLE_MAX_K), V);
-    float my_val = -INFINITY;  // lane k holds rank-k candidate
-    int my_idx = -1;
-    constexpr int REG_V = 20;   // audio vocab (626) fits 20 scores per lane: selection runs out of registers
-    if (V <= 32 * REG_V) {
-        // lane owns scores v = lane + 32*i.  Per round: warp arg-max over the lanes' local maxima with three redux.sync
-        // (max of an order-preserving integer key, then the smallest token id among the ties), the owner retires its entry
-        // and rescans its 20 registers.  ~2 us for K = 20 instead of ~13 us through shared memory (tests/prof_trace.py).
-        float vals[REG_V];
-#pragma unroll
-        for (int i = 0; i < REG_V; ++i) { const int v = lane + 32 * i; vals[i] = v < V ? sc[v] : -INFINITY; }
-        const float inv_z = 1.0f / z;
-        const bool stop_on_mass = cfg.top_p > 0.f && cfg.top_p < 1.f;
-        float mass = 0.f;   // probability mass of the candidates selected so far (all lanes hold the same value)
-        for (int k = 0; k < K; ++k) {
-            // TopP removes every rank whose mass strictly above reaches top_p (unless rank < min_keep): once the selected candidates
-            // hold that much, no further rank can survive and the remaining rounds are skipped (peaked rows need 2-4 rounds, not 20)
-            // (margin: the decision itself is taken below from the prefix sums, exactly as before; this only prunes rounds)
-            if (stop_on_mass && k >= cfg.min_keep && mass >= cfg.top_p + 1e-3f) break;
-            // local arg-max as four independent chains of five, then merged (ties keep the smaller index)
-            float cv[4];
-            int ci[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                cv[c] = vals[5 * c]; ci[c] = 5 * c;
-#pragma unroll
-                for (int i = 1; i < 5; ++i) if (vals[5 * c + i] > cv[c]) { cv[c] = vals[5 * c + i]; ci[c] = 5 * c + i; }
+    // How many ranks TopK lets through: max(top_k, min_keep) (transformers TopKLogitsWarper), or the whole row when there is no TopK
+    // warper (processors.py:43-47 with top_K=None).  Up to SAMPLE_MAX_K ranks are handled out of registers (lane k = rank k); wider
+    // settings take the general path below.
+    int K_req = cfg.top_k > 0 ? max(cfg.top_k, cfg.min_keep) : V;
+    K_req = min(K_req, V);
+    int chosen;
+    if (K_req <= SAMPLE_MAX_K) {
+        // 3. the K best scores in rank order (K = max(top_k, min_keep))
+        const int K = K_req;
+        float my_val = -INFINITY;  // lane k holds rank-k candidate
+        int my_idx = -1;
+        constexpr int REG_V = 20;   // audio vocab (626) fits 20 scores per lane: selection runs out of registers
+        if (V <= 32 * REG_V) {
+            // lane owns scores v = lane + 32*i.  Per round: warp arg-max over the lanes' local maxima with three redux.sync
+            // (max of an order-preserving integer key, then the smallest token id among the ties), the owner retires its entry
+            // and rescans its 20 registers.  ~2 us for K = 20 instead of ~13 us through shared memory (tests/prof_trace.py).
+            float vals[REG_V];
+    #pragma unroll
+            for (int i = 0; i < REG_V; ++i) { const int v = lane + 32 * i; vals[i] = v < V ? sc[v] : -INFINITY; }
+            const float inv_z = 1.0f / z;
+            const bool stop_on_mass = cfg.top_p > 0.f && cfg.top_p < 1.f;
+            float mass = 0.f;   // probability mass of the candidates selected so far (all lanes hold the same value)
+            for (int k = 0; k < K; ++k) {
+                // TopP removes every rank whose mass strictly above reaches top_p (unless rank < min_keep): once the selected candidates
+                // hold that much, no further rank can survive and the remaining rounds are skipped (peaked rows need 2-4 rounds, not 20)
+                // (margin: the decision itself is taken below from the prefix sums, exactly as before; this only prunes rounds)
+                if (stop_on_mass && k >= cfg.min_keep && mass >= cfg.top_p + 1e-3f) break;
+                // local arg-max as four independent chains of five, then merged (ties keep the smaller index)
+                float cv[4];
+                int ci[4];
+    #pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    cv[c] = vals[5 * c]; ci[c] = 5 * c;
+    #pragma unroll
+                    for (int i = 1; i < 5; ++i) if (vals[5 * c + i] > cv[c]) { cv[c] = vals[5 * c + i]; ci[c] = 5 * c + i; }
+                }
+                if (cv[1] > cv[0]) { cv[0] = cv[1]; ci[0] = ci[1]; }
+                if (cv[3] > cv[2]) { cv[2] = cv[3]; ci[2] = ci[3]; }
+                float lv = cv[0];
+                int li = ci[0];
+                if (cv[2] > lv) { lv = cv[2]; li = ci[2]; }
+                const unsigned u = __float_as_uint(lv);
+                const unsigned key = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+                const unsigned kmax = __reduce_max_sync(0xffffffffu, key);
+                const int cand = (key == kmax) ? (lane + 32 * li) : 0x7fffffff;
+                const int bi = __reduce_min_sync(0xffffffffu, cand);
+                const float bv = __shfl_sync(0xffffffffu, lv, bi & 31);
+                if (lane == k) { my_val = bv; my_idx = bi; }
+                mass += __expf(bv - mx) * inv_z;
+                if ((bi & 31) == lane) {
+    #pragma unroll
+                    for (int i = 0; i < REG_V; ++i) if (i == (bi >> 5)) vals[i] = -INFINITY;
+                }
             }
-            if (cv[1] > cv[0]) { cv[0] = cv[1]; ci[0] = ci[1]; }
-            if (cv[3] > cv[2]) { cv[2] = cv[3]; ci[2] = ci[3]; }
-            float lv = cv[0];
-            int li = ci[0];
-            if (cv[2] > lv) { lv = cv[2]; li = ci[2]; }
-            const unsigned u = __float_as_uint(lv);
-            const unsigned key = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-            const unsigned kmax = __reduce_max_sync(0xffffffffu, key);
-            const int cand = (key == kmax) ? (lane + 32 * li) : 0x7fffffff;
-            const int bi = __reduce_min_sync(0xffffffffu, cand);
-            const float bv = __shfl_sync(0xffffffffu, lv, bi & 31);
-            if (lane == k) { my_val = bv; my_idx = bi; }
-            mass += __expf(bv - mx) * inv_z;
-            if ((bi & 31) == lane) {
-#pragma unroll
-                for (int i = 0; i < REG_V; ++i) if (i == (bi >> 5)) vals[i] = -INFINITY;
+        } else {
+            for (int k = 0; k < K; ++k) {
+                float bv = -INFINITY;
+                int bi = 0x7fffffff;
+                for (int v = lane; v < V; v += 32) {
+                    const float s = sc[v];
+                    if (s > bv) { bv = s; bi = v; }
+                }
+    #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                }
+                if (lane == k) { my_val = bv; my_idx = bi; }
+                if (lane == 0 && bi < V) sc[bi] = -INFINITY;  // remove from the pool
+                __syncwarp();
             }
         }
+        if (!FUSED && threadIdx.x == 0) trace_mark(a.trace, 5);
+        // 4. TopP on rank order: token at rank k survives iff (mass strictly above it) < top_p, or k < min_keep.
+        //    (reference: cumulative prob from the bottom <= 1 - top_p is removed.)
+        const float pk = (lane < K && my_idx >= 0 && my_idx < V) ? __expf(my_val - mx) / z : 0.f;
+        float above = pk;  // inclusive prefix sum over lanes, then make exclusive
+    #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float t = __shfl_up_sync(0xffffffffu, above, o);
+            if (lane >= o) above += t;
+        }
+        above -= pk;
+        bool keep = (lane < K) && (my_idx >= 0 && my_idx < V) && (my_val > -INFINITY);
+        if (cfg.top_p > 0.f && cfg.top_p < 1.f) {
+            // removed iff 1 - above <= 1 - top_p  (written like the reference's comparison on the ascending cumsum)
+            const float cum_from_bottom = 1.0f - above;
+            if (lane >= cfg.min_keep && cum_from_bottom <= (1.0f - cfg.top_p)) keep = false;
+        }
+        // 5. min-length EOS ban (gpt.py:477-478)
+        if (step < cfg.min_new && my_idx == cfg.eos) keep = false;
+        // 6. softmax over survivors and inverse-CDF draw in token-id order.  The softmax is taken relative to the SURVIVORS' maximum:
+        //    when the min-length ban removed an EOS that was the row maximum, exp(s - row max) underflows to 0 for every survivor at
+        //    near-greedy temperatures (the reference's softmax runs after the ban, gpt.py:477-480, and renormalises by itself)
+        const float mx_s = warp_max(keep ? my_val : -INFINITY);
+        const float e = keep ? __expf(my_val - mx_s) : 0.f;
+        const float zs = warp_sum(e);
+        const float p = e / zs;
+        // rank of my token id among survivors
+        float cdf_before = 0.f;  // mass of surviving tokens with a smaller id
+        for (int t = 0; t < K; ++t) {
+            const int oi = __shfl_sync(0xffffffffu, my_idx, t);
+            const float op = __shfl_sync(0xffffffffu, p, t);
+            if (oi < my_idx) cdf_before += op;
+        }
+        // chosen = survivor with cdf_before <= u < cdf_before + p; fall back to the largest id survivor
+        const bool hit = keep && (cdf_before <= uu) && (uu < cdf_before + p);
+        unsigned ballot = __ballot_sync(0xffffffffu, hit);
+        if (ballot) {
+            chosen = __shfl_sync(0xffffffffu, my_idx, __ffs(ballot) - 1);
+        } else {
+            int best = keep ? my_idx : -1;
+    #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+            chosen = best;
+        }
+        if (a.probs_out) {
+            float* po = a.probs_out + (long long)row * V;
+            for (int v = lane; v < V; v += 32) po[v] = 0.f;
+            __syncwarp();
+            if (keep) po[my_idx] = p;
+        }
     } else {
-        for (int k = 0; k < K; ++k) {
-            float bv = -INFINITY;
+        // ---- general path (top_K > 32 or no TopK at all): survivors are described by a cut-off key instead of being held one per lane.
+        // Pass 1 walks the ranks in order (score descending, ties by token id ascending) WITHOUT removing anything: each round takes
+        // the best key strictly after the previous one; rank n survives iff n < K_req and (n < min_keep or the mass strictly above it
+        // is < top_p).  Pass 2 takes the softmax over {key <= cut-off} minus a banned EOS and draws by inverse CDF in token-id order.
+        const bool use_p = cfg.top_p > 0.f && cfg.top_p < 1.f;
+        float prev_s = INFINITY, cut_s = INFINITY, mass = 0.f;
+        int prev_i = -1, cut_i = -1, n_sel = 0;
+        while (n_sel < K_req) {
+            float bs = -INFINITY;
             int bi = 0x7fffffff;
             for (int v = lane; v < V; v += 32) {
-                const float s = sc[v];
-                if (s > bv) { bv = s; bi = v; }
+                const float sv = sc[v];
+                const bool after = (sv < prev_s) || (sv == prev_s && v > prev_i);
+                if (after && (sv > bs || (sv == bs && v < bi))) { bs = sv; bi = v; }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const float ov = __shfl_xor_sync(0xffffffffu, bs, o);
                 const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                if (ov > bs || (ov == bs && oi < bi)) { bs = ov; bi = oi; }
             }
-            if (lane == k) { my_val = bv; my_idx = bi; }
-            if (lane == 0 && bi < V) sc[bi] = -INFINITY;  // remove from the pool
-            __syncwarp();
+            if (bi == 0x7fffffff || bs == -INFINITY) break;                       // nothing finite is left
+            if (use_p && n_sel >= cfg.min_keep && (1.0f - mass) <= (1.0f - cfg.top_p)) break;   // same comparison as the reference's cumsum test
+            cut_s = bs; cut_i = bi;
+            mass += __expf(bs - mx) / z;
+            prev_s = bs; prev_i = bi;
+            ++n_sel;
         }
-    }
-    if (!FUSED && threadIdx.x == 0) trace_mark(a.trace, 5);
-    // 4. TopP on rank order: token at rank k survives iff (mass strictly above it) < top_p, or k < min_keep.
-    //    (reference: cumulative prob from the bottom <= 1 - top_p is removed.)
-    const float pk = (lane < K && my_idx >= 0 && my_idx < V) ? __expf(my_val - mx) / z : 0.f;
-    float above = pk;  // inclusive prefix sum over lanes, then make exclusive
+        const bool ban = step < cfg.min_new;
+        float mx_s = -INFINITY;
+        for (int v = lane; v < V; v += 32) {
+            const float sv = sc[v];
+            const bool surv = n_sel > 0 && (sv > cut_s || (sv == cut_s && v <= cut_i)) && !(ban && v == cfg.eos);
+            if (surv) mx_s = fmaxf(mx_s, sv);
+        }
+        mx_s = warp_max(mx_s);
+        float zs = 0.f;
+        for (int v = lane; v < V; v += 32) {
+            const float sv = sc[v];
+            const bool surv = n_sel > 0 && (sv > cut_s || (sv == cut_s && v <= cut_i)) && !(ban && v == cfg.eos);
+            if (surv) zs += __expf(sv - mx_s);
+        }
+        zs = warp_sum(zs);
+        float running = 0.f;
+        int last_surv = -1;
+        chosen = -1;
+        float* po = a.probs_out ? a.probs_out + (long long)row * V : nullptr;
+        for (int base = 0; base < V; base += 32) {
+            const int v = base + lane;
+            const float sv = v < V ? sc[v] : -INFINITY;
+            const bool surv = v < V && n_sel > 0 && (sv > cut_s || (sv == cut_s && v <= cut_i)) && !(ban && v == cfg.eos);
+            const float pv = surv ? __expf(sv - mx_s) / zs : 0.f;
+            if (po && v < V) po[v] = pv;
+            float incl = pv;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const float t = __shfl_up_sync(0xffffffffu, above, o);
-        if (lane >= o) above += t;
-    }
-    above -= pk;
-    bool keep = (lane < K) && (my_idx >= 0 && my_idx < V) && (my_val > -INFINITY);
-    if (cfg.top_p > 0.f && cfg.top_p < 1.f) {
-        // removed iff 1 - above <= 1 - top_p  (written like the reference's comparison on the ascending cumsum)
-        const float cum_from_bottom = 1.0f - above;
-        if (lane >= cfg.min_keep && cum_from_bottom <= (1.0f - cfg.top_p)) keep = false;
-    }
-    // 5. min-length EOS ban (gpt.py:477-478)
-    if (step < cfg.min_new && my_idx == cfg.eos) keep = false;
-    // 6. softmax over survivors and inverse-CDF draw in token-id order.  The softmax is taken relative to the SURVIVORS' maximum:
-    //    when the min-length ban removed an EOS that was the row maximum, exp(s - row max) underflows to 0 for every survivor at
-    //    near-greedy temperatures (the reference's softmax runs after the ban, gpt.py:477-480, and renormalises by itself)
-    const float mx_s = warp_max(keep ? my_val : -INFINITY);
-    const float e = keep ? __expf(my_val - mx_s) : 0.f;
-    const float zs = warp_sum(e);
-    const float p = e / zs;
-    // rank of my token id among survivors
-    float cdf_before = 0.f;  // mass of surviving tokens with a smaller id
-    for (int t = 0; t < K; ++t) {
-        const int oi = __shfl_sync(0xffffffffu, my_idx, t);
-        const float op = __shfl_sync(0xffffffffu, p, t);
-        if (oi < my_idx) cdf_before += op;
-    }
-    // chosen = survivor with cdf_before <= u < cdf_before + p; fall back to the largest id survivor
-    const bool hit = keep && (cdf_before <= uu) && (uu < cdf_before + p);
-    unsigned ballot = __ballot_sync(0xffffffffu, hit);
-    int chosen;
-    if (ballot) {
-        chosen = __shfl_sync(0xffffffffu, my_idx, __ffs(ballot) - 1);
-    } else {
-        int best = keep ? my_idx : -1;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
-        chosen = best;
-    }
-    if (a.probs_out) {
-        float* po = a.probs_out + (long long)row * V;
-        for (int v = lane; v < V; v += 32) po[v] = 0.f;
-        __syncwarp();
-        if (keep) po[my_idx] = p;
+            for (int o = 1; o < 32; o <<= 1) {
+                const float t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const float before = running + incl - pv;
+            const bool hit = surv && before <= uu && uu < before + pv;
+            const unsigned hb = __ballot_sync(0xffffffffu, hit);
+            const unsigned sb = __ballot_sync(0xffffffffu, surv);
+            if (chosen < 0 && hb) chosen = base + __ffs(hb) - 1;
+            if (sb) last_surv = base + 31 - __clz(sb);
+            running += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (chosen < 0) chosen = last_surv;   // u beyond the rounded total: the largest-id survivor, like the register path
     }
     if (a.next_ids && lane == 0) a.next_ids[row] = chosen;
     if (!FUSED && threadIdx.x == 0) trace_mark(a.trace, 6);

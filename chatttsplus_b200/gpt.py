@@ -29,6 +29,20 @@ from .processors import flatten as _flatten_processors
 from .synth import GPTConfig
 
 
+class _nvtx:
+    """NVTX range (reference precedent: chattts_plus/trt_models/predictor.py:92,142,159,164) — shows up in nsys / ncu timelines."""
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *a):
+        torch.cuda.nvtx.range_pop()
+        return False
+
+
 class _EmbInfo:
     """Stand-in for nn.Embedding where callers only read ``num_embeddings`` (chattts_plus_pipeline.py:209)."""
 
@@ -443,7 +457,8 @@ class GPT:
             if evs:
                 evs[0].record()
             text_flag = 1 if infer_text else 0
-            _lib.check(lib.ctp_gpt_prefill(self._handle, B, L0, _lib.ptr(emb32), pad_arr, C.byref(bufs), text_flag, strm), "ctp_gpt_prefill")
+            with _nvtx("ctp.gpt.prefill"):
+                _lib.check(lib.ctp_gpt_prefill(self._handle, B, L0, _lib.ptr(emb32), pad_arr, C.byref(bufs), text_flag, strm), "ctp_gpt_prefill")
 
             def draw_uniforms():
                 if uniforms is not None:
@@ -489,8 +504,9 @@ class GPT:
             while remaining > 0 and not all_done and not context.get():
                 n_it = min(chunk, remaining)
                 steps_done = C.c_int32(0)
-                _lib.check(lib.ctp_gpt_generate(self._handle, C.byref(cfg), n_it, _lib.ptr(u), 16, C.byref(steps_done), strm),
-                           "ctp_gpt_generate")
+                with _nvtx("ctp.gpt.decode_steps"):
+                    _lib.check(lib.ctp_gpt_generate(self._handle, C.byref(cfg), n_it, _lib.ptr(u), 16, C.byref(steps_done), strm),
+                               "ctp_gpt_generate")
                 remaining -= n_it
                 done_total += steps_done.value
                 if pbar is not None:

@@ -80,7 +80,7 @@ def flatten(logits_warpers, logits_processors) -> SamplerParams:
         else:
             raise TypeError(f"unsupported logits warper {type(w).__name__}: the fused sampler implements TopP and TopK")
     if not saw_k:
-        raise ValueError("the fused B200 sampler needs a TopK warper (top_K in [1, 32]); top_K=None is not supported")
+        p.top_k = 0   # no TopK warper (gen_logits(top_K=None), processors.py:43-47): only TopP / min_keep limit the survivors
     for q in logits_processors or []:
         if hasattr(q, "penalty") and hasattr(q, "past_window"):
             p.rep_penalty = float(q.penalty)

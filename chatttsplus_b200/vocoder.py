@@ -435,8 +435,12 @@ class VocoderEngine:
             n = len(glens)
             lens_arr = (C.c_int32 * n)(*glens)
             offs_arr = (C.c_int64 * n)(*offs[:-1].tolist())
-            _lib.check(_lib.lib().ctp_voc_decode(self._handle, n, lens_arr, _lib.ptr(src), _lib.ptr(wav), offs_arr, _lib.ptr(mel),
-                                                 _lib.stream_ptr()), "ctp_voc_decode")
+            torch.cuda.nvtx.range_push("ctp.voc.decode")   # (reference precedent for NVTX: trt_models/predictor.py:92,142,159,164)
+            try:
+                _lib.check(_lib.lib().ctp_voc_decode(self._handle, n, lens_arr, _lib.ptr(src), _lib.ptr(wav), offs_arr, _lib.ptr(mel),
+                                                     _lib.stream_ptr()), "ctp_voc_decode")
+            finally:
+                torch.cuda.nvtx.range_pop()
         wavs: List[torch.Tensor] = [torch.zeros(0, device=dev) for _ in items]
         mels: List[torch.Tensor] = [torch.zeros(0, 100, device=dev) for _ in items]
         mrow = 0
