@@ -87,8 +87,10 @@ def test_gen_logits_and_flatten():
     from transformers.generation import TopKLogitsWarper, TopPLogitsWarper
     sp2 = flatten([TopPLogitsWarper(0.5, min_tokens_to_keep=3), TopKLogitsWarper(10, min_tokens_to_keep=3)], [])
     assert (sp2.top_p, sp2.top_k, sp2.rep_penalty) == (0.5, 10, 1.0)
-    with pytest.raises(ValueError):
-        flatten([TopPLogitsWarper(0.5)], [])
+    # no TopK warper (gen_logits(top_K=None), reference processors.py:43-47): top_k 0 = every rank may survive, TopP decides
+    sp3 = flatten(*gen_logits(625, 0.7, None, 1.0))
+    assert (sp3.top_p, sp3.top_k, sp3.min_keep, sp3.rep_penalty) == (0.7, 0, 3, 1.0)
+    assert flatten([TopKLogitsWarper(50, min_tokens_to_keep=3)], []).top_k == 50
 
 
 def test_tokenizer_layout_and_speaker_hook():
