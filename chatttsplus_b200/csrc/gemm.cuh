@@ -367,6 +367,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (nkb > 0) {
             mbar_wait(accum_bar, 0);
+            // The epilogue reuses the operand ring as transpose scratch.  Its writes are ordered after the converter warps' operand writes
+            // through full_bar -> tcgen05.mma -> tcgen05.commit -> accum_bar; compute-sanitizer's racecheck does not model that chain
+            // (profiles/r2_sanitizer_racecheck.log reported the pair as a write-write hazard), so the same four warps also meet at a named
+            // barrier the tool does understand (a few cycles per launch)
+            if (XMODE) asm volatile("bar.sync 1, 128;" ::: "memory");
             if (threadIdx.x == 0) trace_mark(shp.trace, 6);
             if (dbg && threadIdx.x == 0) dbg[4] = clock64();
             tc_fence_after();
