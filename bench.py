@@ -394,7 +394,7 @@ def run_ours(args):
         "e2e": {"value": round(e2e_value, 1), "unit": "frames/s", "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"]},
         "gpu_launches": m["launches"],
         "roofline": {"bound": "hbm", "achieved": rl["achieved"], "peak": rl["peak"], "unit": "GB/s", "frac": rl["frac"],
-                     "traffic": traffic, "kernel": "decode step (one CUDA-graph replay: 5 kernels per layer x 20 + embed-norm, final norm, heads, sampler)",
+                     "traffic": traffic, "kernel": "decode step (one CUDA-graph replay: 4 kernels per layer x 20 (q|k|v GEMM, attention, o_proj GEMM, fused cluster MLP) + embed-norm, final norm, heads, sampler)",
                      "peak_source": rl["peak_source"], "algorithmic_bytes_per_step_mean": rl["algorithmic_bytes_per_step_mean"]},
         "clocks": m["clocks"],
     }

@@ -82,6 +82,28 @@ int make_tmap_kmajor(CUtensorMap* out, const void* base, long long rows, long lo
     return CTP_OK;
 }
 
+// K-major fp16 matrix [rows, K]: box = 32 k x box_rows, 64-byte swizzle (the 32-wide K slices of W_down in the fused MLP kernel)
+int make_tmap_k32_sw64(CUtensorMap* out, const void* base, long long rows, long long K, long long ld_elems, int box_rows) {
+    int st = gemm_init();
+    if (st) return st;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ((ld_elems * 2) & 15) != 0) {
+        ctp_set_error("tensor map: base %p / row pitch %lld elements must be 16-byte aligned", base, ld_elems);
+        return CTP_ERR_INVALID;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)(ld_elems * 2)};
+    cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        ctp_set_error("cuTensorMapEncodeTiled (64B swizzle) failed (%d): rows=%lld K=%lld ld=%lld box_rows=%d", (int)r, rows, K, ld_elems, box_rows);
+        return CTP_ERR_CUDA;
+    }
+    return CTP_OK;
+}
+
 int make_tmap_f32(CUtensorMap* out, const void* base, long long rows, long long K, long long ld_elems, int box_rows) {
     int st = gemm_init();
     if (st) return st;

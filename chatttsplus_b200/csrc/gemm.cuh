@@ -633,6 +633,7 @@ int gemm_launch_x(int xmode, const CUtensorMap& tmA, const CUtensorMap& tmX, lon
                   const GemmEpilogue& epi, const GemmShape& extra, cudaStream_t stream, bool pdl);
 // fp32 matrix [rows, K] with row pitch `ld` elements -> 2-D tensor map, box = 64 x box_rows, no swizzle.
 int make_tmap_f32(CUtensorMap* out, const void* base, long long rows, long long K, long long ld_elems, int box_rows);
+int make_tmap_k32_sw64(CUtensorMap* out, const void* base, long long rows, long long K, long long ld_elems, int box_rows);
 int gemm_init();  // resolves cuTensorMapEncodeTiled, sets max dynamic smem attributes
 
 }  // namespace ctp

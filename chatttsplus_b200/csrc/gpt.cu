@@ -2,7 +2,7 @@
 // C-ABI entry points are declared in include/ctp.h (each cites the reference interface it replaces).
 #include "gemm.cuh"
 #include "gpt_kernels.cuh"
-#include "layer_kernel.cuh"
+#include "mlp_kernel.cuh"
 
 #include <map>
 #include <math.h>
@@ -16,6 +16,7 @@ namespace {
 
 struct LayerMaps {
     CUtensorMap wqkv, wo, wgu, wdown;
+    CUtensorMap mlp_gu, mlp_d;   // fused MLP kernel: W_gu in boxes of 32 rows, W_down in [128 x 32] tiles (64B swizzle)
 };
 
 struct ActMaps {  // activation operands (N side) for one N-tile width
@@ -38,6 +39,7 @@ struct ctp_gpt {
     // device workspace (rows = max(max_batch, prefill tokens))
     long long ws_rows = 0;
     float* x = nullptr;        // [rows][H] residual stream
+    float* x2 = nullptr;       // [64][H] decode only: the fused MLP kernel reads one residual buffer and reduces into the other
     __half* xn = nullptr;      // [rows][H]
     float* acc_qkv = nullptr;  // [rows][3H]
     __half* attn = nullptr;    // [rows][H]
@@ -69,10 +71,10 @@ struct ctp_gpt {
     int sm_count = 0;
     bool use_pdl = true;       // programmatic dependent launch between the kernels of the decode step graph (CTP_PDL=0 disables)
     bool fuse_norm = true;     // RMSNorm folded into the QKV / gate|up GEMMs (XNORM kernel); CTP_FUSE_NORM=0: stand-alone norm kernels
-    bool use_chain = false;    // CTP_DECODE=chain: layer-chain kernel (layer_kernel.cuh): o_proj -> gate|up -> down -> next q|k|v in ONE launch per
-                               // layer (two launches per layer with attention).  Parity-green; measured 633 vs 600 us/step for one launch per GEMM
-                               // (profiles/README.md: an in-kernel grid-wide exchange costs what a PDL kernel boundary costs), so opt-in
     CUtensorMap x_map{};       // fp32 map over the first 64 rows of the residual stream
+    CUtensorMap x2_map{};      // ... of the second residual buffer
+    int mlp_m64 = 1;           // MMA 1 of the fused MLP kernel as M = 64 (CTP_MLP_M64=0: M = 128 with idle rows)
+    int mlp_cluster = 0;       // fused MLP kernel (mlp_kernel.cuh): cluster size H/128; 0 = shape / device not eligible or CTP_MLP=0
     CUtensorMap gu_map{};      // fp32 map over the decode gate|up accumulator
     // decode only, re-armable scratch: ss1[64] | ss2[64] | gate|up accumulator [64][2I].  ss1 / ss2 = sum(x^2) per token row as seen by
     // the QKV / gate|up GEMM (input / post-attention RMSNorm folded in)
@@ -80,12 +82,6 @@ struct ctp_gpt {
     float* ss1() const { return dec_gu; }
     float* ss2() const { return dec_gu + 64; }
     float* gu_acc() const { return dec_gu + 128; }
-    unsigned int* chain_flags = nullptr;   // layer-chain kernel: [0..2] phase counters, [3] epoch (zeroed by every prefill)
-    int chain_grid = 0;                    // CTAs of the layer-chain kernel (0: shape / device not eligible)
-    LkPhase chain_ph[4]{};
-    bool attn_prefetch = false;            // CTP_ATTN_PREFETCH=1: the attention kernel (not the previous layer-chain launch) warms L2 with the chain's weights
-    bool kv_prefetch = false;              // CTP_KV_PREFETCH=1: layer-chain kernel warms L2 with the next attention's K/V streams (measured: competes with the chain's own weight tiles, 631 -> 700 us/step)
-    unsigned long long kvpf_cap = 96 * 1024;   // per-stream cap in bytes (CTP_KV_PREFETCH_CAP, KiB): 768 streams x 96 KB = 72 MB of the 126 MB L2
     int attn_cta_target = 296;   // split the KV range until B*heads*nsplit reaches this many CTAs (CTP_ATTN_CTAS)
     // bring-up: in-graph timeline (CTP_TRACE=1): one 8-stamp record per kernel of the step graph, in launch order
     unsigned long long* trace = nullptr;
@@ -128,6 +124,7 @@ static int ensure_workspace(ctp_gpt* h, long long rows) {
         if ((st = make_tmap_kmajor(&am.hmid, h->hmid, mb, I, I, bn))) return st;
     }
     if ((st = make_tmap_f32(&h->x_map, h->x, mb, H, H, 32))) return st;
+    if (h->x2 && (st = make_tmap_f32(&h->x2_map, h->x2, mb, H, H, 32))) return st;
     if (h->dec_gu && (st = make_tmap_f32(&h->gu_map, h->gu_acc(), mb, 2 * I, 2 * I, 32))) return st;
     // captured graphs hold the old pointers
     for (auto& kvp : h->graphs) cudaGraphExecDestroy(kvp.second);
@@ -188,40 +185,33 @@ extern "C" ctp_status ctp_gpt_create(ctp_gpt** out, const ctp_gpt_cfg* cfg) {
         const int I = cfg->inter;
         if (const char* e = getenv("CTP_PDL")) h->use_pdl = atoi(e) != 0;
         if (const char* e = getenv("CTP_FUSE_NORM")) h->fuse_norm = atoi(e) != 0;
-        if (const char* e = getenv("CTP_DECODE")) h->use_chain = (strcmp(e, "chain") == 0);
         if (const char* e = getenv("CTP_ATTN_CTAS")) h->attn_cta_target = atoi(e);
-        if (const char* e = getenv("CTP_KV_PREFETCH")) h->kv_prefetch = atoi(e) != 0;
-        if (const char* e = getenv("CTP_ATTN_PREFETCH")) h->attn_prefetch = atoi(e) != 0;
-        if (const char* e = getenv("CTP_KV_PREFETCH_CAP")) h->kvpf_cap = (unsigned long long)atoi(e) * 1024ULL;
         CK(cudaMalloc(&h->dec_gu, sizeof(float) * (128 + (size_t)64 * 2 * I)));
         CK(cudaMemset(h->dec_gu, 0, sizeof(float) * (128 + (size_t)64 * 2 * I)));
-        CK(cudaMalloc(&h->chain_flags, sizeof(unsigned int) * 4));
-        CK(cudaMemset(h->chain_flags, 0, sizeof(unsigned int) * 4));
+        CK(cudaMalloc(&h->x2, sizeof(float) * 64 * H));
+        CK(cudaMemset(h->x2, 0, sizeof(float) * 64 * H));
+        {   // fused MLP kernel: clusters of H/128 CTAs, 32 intermediate features per CTA (CTP_MLP=0 keeps the two-GEMM path)
+            const int C = H / 128;
+            if (const char* e = getenv("CTP_MLP_M64")) h->mlp_m64 = atoi(e) != 0;
+            bool ok = H % 128 == 0 && C >= 2 && C <= 8 && I % (MLP_UW * C) == 0 && (int)prop.sharedMemPerBlockOptin >= mlp_smem_bytes(H);
+            if (const char* e = getenv("CTP_MLP")) if (!atoi(e)) ok = false;
+            if (ok) {
+                CK(cudaFuncSetAttribute(k_mlp_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp_smem_bytes(H)));
+                // the cluster must be schedulable (C SMs of one GPC with this much shared memory each)
+                cudaLaunchConfig_t qc{};
+                qc.gridDim = dim3((unsigned)(I / MLP_UW)); qc.blockDim = dim3(MLP_THREADS); qc.dynamicSmemBytes = (size_t)mlp_smem_bytes(H);
+                cudaLaunchAttribute qa[1];
+                qa[0].id = cudaLaunchAttributeClusterDimension; qa[0].val.clusterDim.x = (unsigned)C; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+                qc.attrs = qa; qc.numAttrs = 1;
+                int n_clusters = 0;
+                if (cudaOccupancyMaxActiveClusters(&n_clusters, k_mlp_fused, &qc) != cudaSuccess || n_clusters < 1) { ok = false; cudaGetLastError(); }
+            }
+            h->mlp_cluster = ok ? C : 0;
+        }
         CK(cudaFuncSetAttribute(k_attn_decode_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-        CK(cudaFuncSetAttribute(k_layer_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, LK_SMEM));
         if (const char* e = getenv("CTP_TRACE")) if (atoi(e)) {
             CK(cudaMalloc(&h->trace, sizeof(unsigned long long) * (8 * 256 + 128)));
             CK(cudaMemset(h->trace, 0, sizeof(unsigned long long) * (8 * 256 + 128)));
-        }
-        // layer-chain plan: one (128-row weight tile, k-slice) unit per CTA and GEMM; every CTA must be resident (one per SM)
-        h->chain_grid = 0;
-        if (H % 128 == 0 && (2 * I) % 128 == 0 && I % 64 == 0 && (int)prop.sharedMemPerBlockOptin >= LK_SMEM) {
-            const int G = h->sm_count;
-            const int mt[4] = {H / 128, 2 * I / 128, H / 128, 3 * H / 128};
-            const int kb[4] = {H / 64, H / 64, I / 64, H / 64};
-            const int cap[4] = {LK_MAX_KB, LK_MAX_KB, LK_MAX_KB / 2, LK_MAX_KB};   // phase 2 lands a gate and an up tile per k-block
-            int slots = 0;
-            bool ok = true;
-            for (int p = 0; p < 4; ++p) {
-                int sp = mt[p] <= G ? G / mt[p] : 0;
-                if (sp > kb[p]) sp = kb[p];
-                if (sp < 1) { ok = false; break; }
-                const int kmax = (kb[p] + sp - 1) / sp;
-                if (kmax > cap[p]) { ok = false; break; }
-                h->chain_ph[p].m_tiles = mt[p]; h->chain_ph[p].k_blocks = kb[p]; h->chain_ph[p].splits = sp; h->chain_ph[p].w_slot0 = slots;
-                slots += kmax;
-            }
-            if (ok && slots <= LK_W_SLOTS) h->chain_grid = G;
         }
     }
 #undef CK
@@ -235,7 +225,7 @@ extern "C" void ctp_gpt_destroy(ctp_gpt* h) {
     if (!h) return;
     for (auto& kvp : h->graphs) cudaGraphExecDestroy(kvp.second);
     cudaFree(h->x); cudaFree(h->xn); cudaFree(h->acc_qkv); cudaFree(h->attn); cudaFree(h->acc_gu); cudaFree(h->hmid);
-    cudaFree(h->trace); cudaFree(h->dec_gu); cudaFree(h->chain_flags);
+    cudaFree(h->trace); cudaFree(h->dec_gu); cudaFree(h->x2);
     cudaFree(h->x_last); cudaFree(h->hidden); cudaFree(h->logits); cudaFree(h->kv); cudaFree(h->attn_part);
     cudaFree(h->attn_cnt); cudaFree(h->pad_len); cudaFree(h->inv_freq); cudaFree(h->st);
     if (h->st_pin) cudaFreeHost(h->st_pin);
@@ -261,6 +251,8 @@ extern "C" ctp_status ctp_gpt_bind_weights(ctp_gpt* h, const ctp_gpt_weights* w)
         if ((st = make_tmap_kmajor(&m.wo, wo, H, H, H, GEMM_BM))) return (ctp_status)st;
         if ((st = make_tmap_kmajor(&m.wgu, wgu, 2 * I, H, H, GEMM_BM))) return (ctp_status)st;
         if ((st = make_tmap_kmajor(&m.wdown, wd, H, I, I, GEMM_BM))) return (ctp_status)st;
+        if (h->mlp_cluster && (st = make_tmap_kmajor(&m.mlp_gu, wgu, 2 * I, H, H, MLP_UW))) return (ctp_status)st;
+        if (h->mlp_cluster && (st = make_tmap_k32_sw64(&m.mlp_d, wd, H, I, I, 128))) return (ctp_status)st;
     }
     if ((st = make_tmap_kmajor(&h->head_map, w->head_code, (long long)c.num_vq * c.num_audio, H, H, GEMM_BM))) return (ctp_status)st;
     h->have_head_text = false;
@@ -322,89 +314,15 @@ static int launch_heads(ctp_gpt* h, int B, cudaStream_t s, bool pdl = false, boo
 // One decode trunk step for B sequences (ids_ext == nullptr -> codes of the previous sample step).
 #define CTP_LAUNCH(kern, grid, block, smem, ...) do { cudaError_t _le = launch_k(kern, grid, block, (size_t)(smem), s, pdl, __VA_ARGS__); ctp_count_launch(); if (_le == cudaSuccess) _le = cudaGetLastError(); if (_le != cudaSuccess) { ctp_set_error("%s:%d launch %s: %s", __FILE__, __LINE__, #kern, cudaGetErrorString(_le)); return CTP_ERR_CUDA; } } while (0)
 
-static int launch_attn(ctp_gpt* h, int l, int B, int nsplit, bool row_factor, cudaStream_t s, bool pdl, bool prefetch_chain) {
+static int launch_attn(ctp_gpt* h, int l, int B, int nsplit, bool row_factor, cudaStream_t s, bool pdl) {
     const ctp_gpt_cfg& c = h->cfg;
-    const size_t H = c.hidden, I = c.inter;
     AttnDecArgs aa{};
     aa.qkv = h->acc_qkv; aa.kcache = h->kplane(l); aa.vcache = h->vplane(l); aa.out = h->attn; aa.part = h->attn_part;
     aa.counters = h->attn_cnt; aa.pad_len = h->pad_len; aa.st = h->st; aa.inv_freq = h->inv_freq;
     aa.H = c.hidden; aa.nH = c.n_heads; aa.max_seq = c.max_seq; aa.eps = c.rms_eps;
     if (row_factor) aa.ss = h->ss1();   // input_layernorm's row factor (llama.py:718), deferred from the QKV GEMM
-    if (prefetch_chain) {   // warm L2 with everything the layer-chain kernel behind this launch streams
-        aa.pf_ptr[0] = (const __half*)h->w.wo + (size_t)l * H * H;         aa.pf_bytes[0] = sizeof(__half) * H * H;
-        aa.pf_ptr[1] = (const __half*)h->w.wgu + (size_t)l * 2 * I * H;    aa.pf_bytes[1] = sizeof(__half) * 2 * I * H;
-        aa.pf_ptr[2] = (const __half*)h->w.wdown + (size_t)l * H * I;      aa.pf_bytes[2] = sizeof(__half) * H * I;
-        if (l + 1 < c.n_layers) { aa.pf_ptr[3] = (const __half*)h->w.wqkv + (size_t)(l + 1) * 3 * H * H; aa.pf_bytes[3] = sizeof(__half) * 3 * H * H; }
-        else { aa.pf_ptr[3] = h->text_mode ? h->w.head_text : h->w.head_code; aa.pf_bytes[3] = sizeof(__half) * H * (size_t)(h->text_mode ? c.num_text : c.num_vq * c.num_audio); }
-    }
     aa.trace = h->trace_rec();
     CTP_LAUNCH(k_attn_decode_tma, dim3(c.n_heads, B, nsplit), dim3(AT_THREADS), AT_SMEM, aa);
-    return CTP_OK;
-}
-
-// Layer-chain path (CTP_DECODE=chain, batch <= 32): per layer TWO launches — attention, then k_layer_chain (o_proj -> gate|up -> down ->
-// next layer's q|k|v; layer_kernel.cuh) — instead of five; 45 kernels per step at 20 layers.
-static int run_decode_trunk_chain(ctp_gpt* h, int B, int nsplit, const int* ids_ext, cudaStream_t s) {
-    const ctp_gpt_cfg& c = h->cfg;
-    const bool pdl = h->use_pdl;
-    const int H = c.hidden, I = c.inter, L = c.n_layers;
-    int st;
-    {   // layer 0: code-embedding front end + input_layernorm, then q|k|v as a stand-alone GEMM
-        NormArgs na{};
-        na.x = h->x; na.w = h->w.ln1; na.xn = h->xn; na.H = H; na.eps = c.rms_eps;
-        na.st = h->st; na.ids_ext = ids_ext; na.emb_code = (const __half*)h->w.emb_code; na.num_vq = c.num_vq; na.num_audio = c.num_audio;
-        na.emb_text = h->text_mode ? (const __half*)h->w.emb_text : nullptr;
-        na.trace = h->trace_rec();
-        CTP_LAUNCH(k_rmsnorm, dim3(B), dim3(256), 0, na);
-        GemmEpilogue e = epi_swap_atomic(h->acc_qkv, 3 * H, B, 3 * H);
-        if ((st = gemm_launch_maps(h->lmaps[0].wqkv, h->act32.xn, 3 * H, B, H, 32, split_for(H / 64, 3 * H / GEMM_BM), e, s, nullptr, 0, pdl,
-                                   nullptr, 0, h->trace_rec()))) return st;
-    }
-    for (int l = 0; l < L; ++l) {
-        if ((st = launch_attn(h, l, B, nsplit, l > 0, s, pdl, h->attn_prefetch))) return st;
-        LayerArgs a{};
-        for (int p = 0; p < 4; ++p) a.ph[p] = h->chain_ph[p];
-        a.ph[0].out = h->x; a.ph[0].ldo = H;                  // o_proj accumulated straight into the residual stream (llama.py:663-666,737)
-        a.ph[1].out = h->gu_acc(); a.ph[1].ldo = 2 * I;       // gate_proj | up_proj (llama.py:214), post_attention_layernorm (llama.py:741) folded
-        a.ph[2].out = h->x; a.ph[2].ldo = H;                  // down_proj + residual (llama.py:214,745), silu(gate)*up folded
-        a.ph[3].out = h->acc_qkv; a.ph[3].ldo = 3 * H;        // next layer's q,k,v (llama.py:619-621), its input_layernorm (llama.py:718) folded
-        a.n_phases = (l + 1 < L) ? 4 : 3;
-        a.T = B; a.I = I; a.ss_dim = (float)H; a.eps = c.rms_eps;
-        a.ln_post = h->w.ln2 + (size_t)l * H;
-        a.ln_next = h->w.ln1 + (size_t)(l + 1 < L ? l + 1 : l) * H;
-        a.ss1 = h->ss1(); a.ss2 = h->ss2();
-        a.rearm_ptr = h->ss2(); a.rearm_f4 = (unsigned long long)(64 + (size_t)B * 2 * I) / 4;
-        a.flags = h->chain_flags;
-        if (!h->attn_prefetch) {   // warm L2 with the weight stream of the next layer-chain launch (and the heads / first q|k|v of the next step)
-            const size_t Hs = H, Is = I;
-            const __half* wqkv = (const __half*)h->w.wqkv; const __half* wo = (const __half*)h->w.wo;
-            const __half* wgu = (const __half*)h->w.wgu; const __half* wdn = (const __half*)h->w.wdown;
-            const int ln = (l + 1) % L;
-            a.pf_ptr[0] = wo + (size_t)ln * Hs * Hs;          a.pf_bytes[0] = sizeof(__half) * Hs * Hs;
-            a.pf_ptr[1] = wgu + (size_t)ln * 2 * Is * Hs;     a.pf_bytes[1] = sizeof(__half) * 2 * Is * Hs;
-            a.pf_ptr[2] = wdn + (size_t)ln * Hs * Is;         a.pf_bytes[2] = sizeof(__half) * Hs * Is;
-            if (l + 2 < L) { a.pf_ptr[3] = wqkv + (size_t)(l + 2) * 3 * Hs * Hs; a.pf_bytes[3] = sizeof(__half) * 3 * Hs * Hs; }
-            if (l + 2 == L) {   // the launch before the last: the heads GEMM follows the last layer-chain launch
-                a.pf_ptr[3] = h->text_mode ? h->w.head_text : h->w.head_code;
-                a.pf_bytes[3] = sizeof(__half) * Hs * (size_t)(h->text_mode ? c.num_text : c.num_vq * c.num_audio);
-            }
-            if (l + 1 == L) {   // the last launch: the next step starts with q|k|v of layer 0 and needs layer 1's in its first chain launch
-                a.pf_ptr[3] = wqkv; a.pf_bytes[3] = sizeof(__half) * 3 * Hs * Hs;
-                if (L > 1) { a.pf_ptr[4] = wqkv + 3 * Hs * Hs; a.pf_bytes[4] = sizeof(__half) * 3 * Hs * Hs; }
-            }
-        }
-        if (h->kv_prefetch) {   // warm L2 with the K/V streams of the next attention launch (layer l+1, or layer 0 of the next step)
-            const int ln = (l + 1) % L;
-            a.kv_k = (const char*)h->kplane(ln); a.kv_v = (const char*)h->vplane(ln);
-            a.kv_stream_bytes = sizeof(__half) * (size_t)c.max_seq * HEAD_DIM; a.kv_cap = h->kvpf_cap;
-            a.kv_streams = B * c.n_heads; a.nH = c.n_heads; a.pad_len = h->pad_len; a.cur_len = &h->st->cur_len;
-        }
-        a.trace = h->trace_rec();
-        a.dbg = (h->trace && l == L / 2) ? h->trace + 8 * 256 : nullptr;   // fine-grained stamps of one mid-stack launch
-        const LayerMaps& m = h->lmaps[l];
-        const CUtensorMap& next_qkv = h->lmaps[l + 1 < L ? l + 1 : l].wqkv;
-        CTP_LAUNCH(k_layer_chain, dim3(h->chain_grid), dim3(LK_THREADS), LK_SMEM, m.wo, m.wgu, m.wdown, next_qkv, h->act32.attn, a);
-    }
     return CTP_OK;
 }
 
@@ -418,18 +336,22 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
     h->trace_n = 0;
     // Batch <= 32: RMSNorm is folded into the QKV / gate|up GEMMs and silu(gate)*up into down_proj (in-kernel token operands).
     const bool fuse = h->fuse_norm && B <= 32;
-    const bool chain = fuse && h->use_chain && h->chain_grid > 0;
-    if (chain) {
-        if ((st = run_decode_trunk_chain(h, B, nsplit, ids_ext, s))) return st;
-    }
     float* gu = fuse ? h->gu_acc() : h->acc_gu;
-    const unsigned long long rearm_f4 = (unsigned long long)(64 + (size_t)B * 2 * I) / 4;   // ss2 | gate|up rows of the live batch (from ss2())
+    // fused MLP kernel (mlp_kernel.cuh): gate|up -> silu*up -> down in one launch per layer.  The residual stream then alternates between
+    // two buffers: layer l reads / accumulates o_proj into cur, the MLP kernel reduces cur + mlp(cur) into the other buffer, which this
+    // layer's QKV GEMM cleared (its last reader was the previous layer's MLP kernel).
+    const bool mlp = fuse && h->mlp_cluster > 0;
+    float* xcur = h->x;
+    unsigned long long rearm_f4 = (unsigned long long)(64 + (size_t)B * 2 * I) / 4;   // ss2 | gate|up rows of the live batch (from ss2())
+    if (mlp) rearm_f4 = (unsigned long long)((size_t)B * H) / 4;
     // default (batches of 33..64 rows use the 64-token N tile with stand-alone norm / SiLU kernels): one launch per op
-    for (int l = 0; l < (chain ? 0 : c.n_layers); ++l) {
+    for (int l = 0; l < c.n_layers; ++l) {
         const bool f1 = fuse && l > 0;   // layer 0 keeps the norm kernel: it is also the code-embedding front end
+        float* xoth = (xcur == h->x) ? h->x2 : h->x;
+        float* rearm = mlp ? xoth : h->ss2();
         if (!f1) {
             NormArgs na{};
-            na.x = h->x; na.w = h->w.ln1 + (size_t)l * H; na.xn = h->xn; na.H = H; na.eps = c.rms_eps;
+            na.x = xcur; na.w = h->w.ln1 + (size_t)l * H; na.xn = h->xn; na.H = H; na.eps = c.rms_eps;
             if (l == 0) { na.st = h->st; na.ids_ext = ids_ext; na.emb_code = (const __half*)h->w.emb_code; na.num_vq = c.num_vq; na.num_audio = c.num_audio;
                           na.emb_text = h->text_mode ? (const __half*)h->w.emb_text : nullptr; }
             na.trace = h->trace_rec();
@@ -442,21 +364,39 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
             const size_t pfb = sizeof(__half) * (size_t)H * H;
             if (f1) {
                 GemmShape ex{};
-                ex.pf_ptr = pf; ex.pf_bytes = pfb; ex.norm_w = h->w.ln1 + (size_t)l * H; ex.zero_ptr = h->ss2(); ex.zero_f4 = rearm_f4;
+                ex.pf_ptr = pf; ex.pf_bytes = pfb; ex.norm_w = h->w.ln1 + (size_t)l * H; ex.zero_ptr = rearm; ex.zero_f4 = rearm_f4;
                 ex.ss_out = h->ss1(); ex.trace = h->trace_rec();
-                st = gemm_launch_x(1, h->lmaps[l].wqkv, h->x_map, 3 * H, B, H, split_for(H / 64, 3 * H / GEMM_BM), e, ex, s, pdl);
+                st = gemm_launch_x(1, h->lmaps[l].wqkv, xcur == h->x ? h->x_map : h->x2_map, 3 * H, B, H, split_for(H / 64, 3 * H / GEMM_BM), e, ex, s, pdl);
             } else {
                 st = gemm_launch_maps(h->lmaps[l].wqkv, am.xn, 3 * H, B, H, bn, split_for(H / 64, 3 * H / GEMM_BM), e, s, pf, pfb, pdl,
-                                      fuse ? h->ss2() : nullptr, fuse ? rearm_f4 : 0, h->trace_rec());
+                                      fuse ? rearm : nullptr, fuse ? rearm_f4 : 0, h->trace_rec());
             }
             if (st) return st;
         }
-        if ((st = launch_attn(h, l, B, nsplit, f1, s, pdl, false))) return st;
+        if ((st = launch_attn(h, l, B, nsplit, f1, s, pdl))) return st;
         {   // o_proj accumulated straight into the residual stream (llama.py:663-666,737)
-            GemmEpilogue e = epi_swap_atomic(h->x, H, B, H);
+            GemmEpilogue e = epi_swap_atomic(xcur, H, B, H);
             if ((st = gemm_launch_maps(h->lmaps[l].wo, am.attn, H, B, H, bn, split_for(H / 64, (H + GEMM_BM - 1) / GEMM_BM), e, s,
                                        (const __half*)h->w.wgu + (size_t)l * 2 * I * H, sizeof(__half) * (size_t)2 * I * H, pdl,
                                        fuse ? h->ss1() : nullptr, fuse ? 16 : 0, h->trace_rec()))) return st;   // re-arms ss1 (read by this layer's attention)
+        }
+        if (mlp) {
+            MlpArgs ma{};
+            ma.x_in = xcur; ma.x_out = xoth; ma.ln_w = h->w.ln2 + (size_t)l * H; ma.T = B; ma.H = H; ma.I = I; ma.eps = c.rms_eps;
+            ma.pf_ptr = (l + 1 < c.n_layers) ? (const void*)((const __half*)h->w.wqkv + (size_t)(l + 1) * 3 * H * H) : h->w.head_code;
+            ma.pf_bytes = (l + 1 < c.n_layers) ? sizeof(__half) * (size_t)3 * H * H : sizeof(__half) * (size_t)c.num_vq * c.num_audio * H;
+            ma.trace = h->trace_rec();
+            ma.m64 = h->mlp_m64;
+            const LayerMaps& m = h->lmaps[l];
+            {
+                cudaError_t le = launch_kc(k_mlp_fused, dim3((unsigned)(I / MLP_UW)), dim3(MLP_THREADS), (size_t)mlp_smem_bytes(H), s, pdl, (unsigned)h->mlp_cluster,
+                                           m.mlp_gu, m.mlp_d, ma);
+                ctp_count_launch();
+                if (le == cudaSuccess) le = cudaGetLastError();
+                if (le != cudaSuccess) { ctp_set_error("%s:%d launch k_mlp_fused: %s", __FILE__, __LINE__, cudaGetErrorString(le)); return CTP_ERR_CUDA; }
+            }
+            xcur = xoth;
+            continue;
         }
         if (!fuse) {
             NormArgs nb{};
@@ -499,7 +439,7 @@ static int run_decode_trunk(ctp_gpt* h, int B, int nsplit, const int* ids_ext, c
     }
     // final norm (llama.py:1002) -> hidden state of this step (gpt.py:422-423) + operand of the heads
     NormArgs nf{};
-    nf.x = h->x; nf.w = h->w.norm_f; nf.xn = h->xn; nf.out_f32 = h->hidden; nf.H = H; nf.eps = c.rms_eps;
+    nf.x = xcur; nf.w = h->w.norm_f; nf.xn = h->xn; nf.out_f32 = h->hidden; nf.H = H; nf.eps = c.rms_eps;
     nf.zero_buf = h->logits; nf.zero_n = h->text_mode ? c.num_text : c.num_vq * c.num_audio; nf.st = h->st; nf.write_hid = 1;
     nf.trace = h->trace_rec();
     CTP_LAUNCH(k_rmsnorm, dim3(B), dim3(256), 0, nf);
@@ -633,7 +573,6 @@ extern "C" ctp_status ctp_gpt_prefill(ctp_gpt* h, int32_t B, int32_t L0, const f
     CTP_CUDA_OK(cudaMemsetAsync(h->acc_qkv, 0, sizeof(float) * (size_t)c.max_batch * 3 * H, s));
     CTP_CUDA_OK(cudaMemsetAsync(h->acc_gu, 0, sizeof(float) * (size_t)c.max_batch * 2 * I, s));
     CTP_CUDA_OK(cudaMemsetAsync(h->dec_gu, 0, sizeof(float) * (128 + (size_t)64 * 2 * I), s));
-    CTP_CUDA_OK(cudaMemsetAsync(h->chain_flags, 0, sizeof(unsigned int) * 4, s));   // phase counters + epoch of the layer-chain kernel
     h->B = B; h->cur_len = L0; h->prompt_len = L0; h->step = 0; h->max_new = bufs->max_new; h->have_bufs = true;
     return CTP_OK;
 }
@@ -773,12 +712,24 @@ extern "C" __attribute__((visibility("default"))) int ctp_debug_trace(ctp_gpt* h
     return n;
 }
 
-// bring-up hook (not in include/ctp.h): the 2 x 64 fine-grained stamps of the mid-stack layer-chain launch (CTA 0, last CTA)
-extern "C" __attribute__((visibility("default"))) int ctp_debug_chain_stamps(ctp_gpt* h, unsigned long long* out) {
-    if (!h || !h->trace) return 0;
-    cudaDeviceSynchronize();
-    cudaMemcpy(out, h->trace + 8 * 256, sizeof(unsigned long long) * 128, cudaMemcpyDeviceToHost);
-    return 128;
+// Bring-up / unit-test entry (not part of include/ctp.h): the fused MLP kernel of layer `layer` alone.  x_in, x_out: device fp32
+// [>= 32][H]; x_out is cleared here.  Returns CTP_ERR_INVALID when the handle's shape is not eligible for the kernel.
+extern "C" __attribute__((visibility("default"))) int ctp_debug_mlp(ctp_gpt* h, int layer, const float* x_in, float* x_out, int T, void* stream) {
+    if (!h || !h->bound || !h->mlp_cluster || layer < 0 || layer >= h->cfg.n_layers || T < 1 || T > 32) { ctp_set_error("ctp_debug_mlp: not eligible"); return CTP_ERR_INVALID; }
+    const ctp_gpt_cfg& c = h->cfg;
+    const int H = c.hidden, I = c.inter;
+    cudaStream_t s = (cudaStream_t)stream;
+    CTP_CUDA_OK(cudaMemsetAsync(x_out, 0, sizeof(float) * 32 * H, s));
+    MlpArgs ma{};
+    ma.x_in = x_in; ma.x_out = x_out; ma.ln_w = h->w.ln2 + (size_t)layer * H; ma.T = T; ma.H = H; ma.I = I; ma.eps = c.rms_eps;
+    ma.m64 = h->mlp_m64;
+    const LayerMaps& m = h->lmaps[layer];
+    cudaError_t le = launch_kc(k_mlp_fused, dim3((unsigned)(I / MLP_UW)), dim3(MLP_THREADS), (size_t)mlp_smem_bytes(H), s, false, (unsigned)h->mlp_cluster,
+                               m.mlp_gu, m.mlp_d, ma);
+    ctp_count_launch();
+    if (le == cudaSuccess) le = cudaGetLastError();
+    if (le != cudaSuccess) { ctp_set_error("%s:%d launch k_mlp_fused: %s", __FILE__, __LINE__, cudaGetErrorString(le)); return CTP_ERR_CUDA; }
+    return CTP_OK;
 }
 
 extern "C" const float* ctp_gpt_logits(ctp_gpt* h) { return h ? h->logits : nullptr; }

@@ -180,9 +180,6 @@ struct AttnDecArgs {
     // (llama.py:85) is applied here; sum(x^2) per row arrives in ss
     const float* ss;        // [B] or null (rows already normalised)
     float eps;
-    // optional: regions the kernel BEHIND this one streams (the layer-chain kernel's weights); every CTA prefetches a share into L2
-    const void* pf_ptr[4];
-    unsigned long long pf_bytes[4];
     unsigned long long* trace;
 };
 
@@ -248,25 +245,6 @@ __global__ void __launch_bounds__(AT_THREADS) k_attn_decode_tma(AttnDecArgs a) {
             bulk_load_1d(st + AT_HALF_BYTES, vc + p0 * HEAD_DIM, AT_HALF_BYTES, &full_bar[i]);
         }
         s_pre = pre;
-        // warm L2 with the next kernel's weight stream (after our own loads are in flight)
-        const unsigned long long n_cta = (unsigned long long)gridDim.x * gridDim.y * gridDim.z;
-        const unsigned long long cta = ((unsigned long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            if (a.pf_ptr[r] == nullptr) continue;
-            const unsigned long long per = ((a.pf_bytes[r] + n_cta - 1) / n_cta + 127) & ~127ULL;
-            const unsigned long long off = cta * per;
-            if (off >= a.pf_bytes[r]) continue;
-            unsigned long long n = a.pf_bytes[r] - off < per ? a.pf_bytes[r] - off : per;
-            n &= ~15ULL;
-            const char* src = reinterpret_cast<const char*>(a.pf_ptr[r]) + off;
-            while (n > 0) {
-                const unsigned int chunk = n > 32768ULL ? 32768u : (unsigned int)n;
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(chunk) : "memory");
-                src += chunk;
-                n -= chunk;
-            }
-        }
     }
     pdl_wait();
     if (tid == 0) trace_mark(a.trace, 1);

@@ -40,7 +40,7 @@ recs = [tuple(buf[8 * i + j] for j in range(8)) for i in range(n)]
 t0 = recs[0][0]
 print(f"{n} kernels of the last replayed step, launch order; times in us.  enter / wait_ret / exit0 / exit_last are relative to kernel 0's enter "
       f"(CTA 0 enters, its griddepcontrol.wait returns, CTA 0 leaves, the last CTA leaves); body = exit_last - wait_ret; handoff = wait_ret - previous "
-      f"exit_last; s4..s7 = kernel-specific phase stamps relative to wait_ret (layer-chain kernel: s4/s5/s6 = phase counters 0/1/2 observed complete)")
+      f"exit_last; s4..s7 = kernel-specific phase stamps relative to wait_ret (fused MLP kernel: s4 operand + row sums of all ranks landed, s5 D1 complete, s6 silu*up slice written, s7 D2 complete)")
 prev_end = None
 tot_body = tot_hand = 0.0
 for i, r in enumerate(recs):
@@ -57,18 +57,3 @@ for i, r in enumerate(recs):
     prev_end = d
 print(f"sum of bodies {tot_body:.1f} us, sum of hand-offs {tot_hand:.1f} us, span (first enter -> last exit) {(recs[-1][3] - t0) / 1e3:.1f} us")
 
-# fine-grained stamps of the mid-stack layer-chain launch (CTA 0 and the last CTA)
-lib.ctp_debug_chain_stamps.restype = C.c_int
-lib.ctp_debug_chain_stamps.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong)]
-fb = (C.c_ulonglong * 128)()
-if lib.ctp_debug_chain_stamps(gpt._handle, fb) == 128:
-    names = ["pred_done", "weights_in", "tiles_in", "operand_ok", "mma_issued", "accum_ok", "reds_issued", "arrived"]
-    for who, base in (("CTA 0", 0), ("last CTA", 64)):
-        v = [fb[base + i] for i in range(64)]
-        if not v[2]:
-            continue
-        w = v[2]
-        print(f"layer-chain fine stamps, {who} (us relative to its griddepcontrol.wait return): enter {(v[0] - w) / 1e3:.2f}  weights_requested {(v[1] - w) / 1e3:.2f}  exit {(v[3] - w) / 1e3:.2f}")
-        for p_ in range(4):
-            row = "  ".join(f"{names[j]} {(v[8 + 8 * p_ + j] - w) / 1e3:6.2f}" for j in range(8) if v[8 + 8 * p_ + j])
-            print(f"   phase {p_}: {row}")

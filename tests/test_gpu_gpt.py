@@ -111,13 +111,12 @@ def test_trunk_long_context_two_kv_splits():
     _teacher_forced(cfg, B=25, L0=1040, steps=3, seed=36, pads=[0, 700, 1039] + [0] * 22)
 
 
-@pytest.mark.parametrize("env", [{"CTP_DECODE": "chain"}, {"CTP_DECODE": "chain", "CTP_PDL": "0"}, {"CTP_DECODE": "chain", "CTP_KV_PREFETCH": "1"},
-                                 {"CTP_DECODE": "chain", "CTP_ATTN_PREFETCH": "1"}, {"CTP_PDL": "0"}, {"CTP_FUSE_NORM": "0"}])
+@pytest.mark.parametrize("env", [{"CTP_MLP": "0"}, {"CTP_MLP": "0", "CTP_PDL": "0"}, {"CTP_PDL": "0"}, {"CTP_FUSE_NORM": "0"}, {"CTP_MLP_M64": "0"}])
 def test_trunk_opt_in_variants(env, monkeypatch):
-    """The default decode layer is five launches (q|k|v, attention, o_proj, gate|up, down).  The switches stay parity-green: the
-    layer-chain kernel (attention + ONE persistent launch for the four GEMMs, phases separated by release/acquire counters), with
-    and without its L2 warm-up variants; launches without programmatic dependent launch; stand-alone norm / SiLU kernels (eight per
-    layer, the path batches of 33..64 rows take).  (Read at handle creation.)"""
+    """The default decode layer is four launches (q|k|v, attention, o_proj, fused MLP).  The switches stay parity-green: gate|up and
+    down as two split-K GEMMs (the path shapes the fused kernel does not cover take); launches without programmatic dependent
+    launch; stand-alone norm / SiLU kernels (eight per layer, the path batches of 33..64 rows take); the fused kernel's first MMA as
+    M = 128.  (Read at handle creation.)"""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     cfg = synth.GPTConfig(num_hidden_layers=3, num_text_tokens=256)
@@ -143,11 +142,36 @@ def test_trunk_full_depth_config2_shape():
     _teacher_forced(cfg, B=32, L0=128, steps=4, seed=40, tol_rms=2e-3, tol_abs=2e-2)
 
 
-def test_trunk_full_depth_layer_chain(monkeypatch):
-    """Same shape through the layer-chain kernel (CTP_DECODE=chain): all 148 CTAs hold a unit in the gate|up / down phases."""
-    monkeypatch.setenv("CTP_DECODE", "chain")
-    cfg = synth.GPTConfig()
-    _teacher_forced(cfg, B=32, L0=128, steps=4, seed=40, tol_rms=2e-3, tol_abs=2e-2)
+@pytest.mark.parametrize("T", [32, 17, 5, 1])
+def test_fused_mlp_kernel_matches_fp32(T):
+    """mlp_kernel.cuh alone (clusters of 6 CTAs, 32 intermediate features per CTA): x + down(silu(gate(n)) * up(n)), n = RMSNorm(x) * w
+    (llama.py:82-87,214,741-745) against torch fp32 on the same fp16-rounded matrices.  The kernel rounds w*x and silu*up to fp16
+    (relative 4.9e-4 each, like the reference's fp16 path), so the bound is rel-RMS 1e-3 / max-abs 2e-2 on an output of RMS ~1."""
+    from gpu_util import make_gpt, max_abs, rel_rms
+    cfg = synth.GPTConfig(num_hidden_layers=2, num_text_tokens=128)
+    gpt, osd = make_gpt(cfg, seed=77)
+    gpt._ensure_handle(32, 64)
+    lib = C.CDLL(_lib.LIB_PATH)   # (same library object the package loaded: dlopen is reference-counted)
+    lib.ctp_debug_mlp.restype = C.c_int
+    lib.ctp_debug_mlp.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    H = cfg.hidden_size
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(32, H, generator=g) * torch.linspace(0.2, 3.0, 32)[:, None]   # rows of very different scale: the row factor matters
+    for layer in (0, 1):
+        xd = x.cuda().contiguous()
+        out = torch.full((32, H), 7.0, device="cuda")
+        _lib.check(lib.ctp_debug_mlp(gpt._handle, layer, xd.data_ptr(), out.data_ptr(), T, _lib.stream_ptr().value), "ctp_debug_mlp")
+        torch.cuda.synchronize()
+        w_ln = osd[f"gpt.layers.{layer}.post_attention_layernorm.weight"].float()
+        wg = osd[f"gpt.layers.{layer}.mlp.gate_proj.weight"].float()
+        wu = osd[f"gpt.layers.{layer}.mlp.up_proj.weight"].float()
+        wd = osd[f"gpt.layers.{layer}.mlp.down_proj.weight"].float()
+        n = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + cfg.rms_norm_eps) * w_ln
+        ref = x + (torch.nn.functional.silu(n @ wg.T) * (n @ wu.T)) @ wd.T
+        got = out.cpu()
+        assert rel_rms(got[:T], ref[:T]) < 1e-3 and max_abs(got[:T], ref[:T]) < 2e-2, (T, layer, rel_rms(got[:T], ref[:T]), max_abs(got[:T], ref[:T]))
+        if T < 32:
+            assert float(got[T:].abs().max()) == 0.0   # rows past the live batch are never written (the entry cleared them)
 
 
 def test_trunk_full_depth_vs_unrounded_fp32_oracle():
