@@ -421,7 +421,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 // ---------------------------------------------------------------------------------------------------------
 // Persistent variant for the large, compute-bound GEMMs (prefill M = B*L0, vocoder M = mel frames): one CTA per SM loops
-// over output tiles (n-major so that concurrently running CTAs share the weight tile in L2); TWO accumulator tiles in TMEM
+// over output tiles (grouped order, gemm_p_tile below); TWO accumulator tiles in TMEM
 // so the epilogue of tile i (TMEM -> registers -> bias / GELU / layer-scale / residual -> vectorised global stores) overlaps
 // the tcgen05.mma stream of tile i+1.  Normal orientation only (rows = tokens), no split-K.
 // ---------------------------------------------------------------------------------------------------------
@@ -434,6 +434,19 @@ struct GemmPSmem {
     static constexpr int VEC_BYTES = 2 * BN * 4;            // per-tile bias / gamma staging
     static constexpr int TOTAL = STAGES * STAGE_BYTES + VEC_BYTES + 256 + 1024;
 };
+
+// Tile order of the persistent kernel: groups of G = gridDim.x / tiles_n m-tiles, and inside a group all n-tiles of those m-tiles.
+// One wave of CTAs then covers every n-tile of G m-tiles: an activation tile is pulled from HBM once and shared through L2 by the
+// tiles_n CTAs that need it at the same time (n-major order re-read the whole activation matrix from HBM once per n-tile: 800 MB
+// instead of 134 MB for the [131072, 512] x [1536, 512] pointwise conv, ncu dram__bytes_read), the weight matrix stays L2-resident.
+__device__ __forceinline__ void gemm_p_tile(int t, int tiles_m, int tiles_n, int G, int& tm, int& tn) {
+    const int per = G * tiles_n;
+    const int g = t / per, r = t - g * per;
+    const int m_base = g * G;
+    const int ge = tiles_m - m_base < G ? tiles_m - m_base : G;   // last group may be short
+    tn = r / ge;
+    tm = m_base + (r - tn * ge);
+}
 
 template <int BN>
 __global__ void __launch_bounds__(GEMM_P_THREADS, 1)
@@ -455,6 +468,7 @@ gemm_tcgen05_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_co
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = tiles_m * tiles_n;
     const int nkb = shp.k_blocks;
+    const int G = (int)gridDim.x / tiles_n > 0 ? (int)gridDim.x / tiles_n : 1;
 
     if (warp == 4 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -474,7 +488,9 @@ gemm_tcgen05_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_co
         if (lane == 0) {
             uint32_t it = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const int m0 = (t % tiles_m) * GEMM_BM, n0 = (t / tiles_m) * BN;
+                int tm, tn;
+                gemm_p_tile(t, tiles_m, tiles_n, G, tm, tn);
+                const int m0 = tm * GEMM_BM, n0 = tn * BN;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % STAGES;
                     mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
@@ -520,7 +536,9 @@ gemm_tcgen05_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_co
         int j = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++j) {
             const int acc = j & 1;
-            const int m0 = (t % tiles_m) * GEMM_BM, n0 = (t / tiles_m) * BN;
+            int tm, tn;
+            gemm_p_tile(t, tiles_m, tiles_n, G, tm, tn);
+            const int m0 = tm * GEMM_BM, n0 = tn * BN;
             // stage the per-feature vectors of this tile (previous tile's readers are past their last use: see bar below)
             asm volatile("bar.sync 1, 256;" ::: "memory");
             for (int i = et; i < BN; i += 256) {

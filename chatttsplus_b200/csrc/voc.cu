@@ -170,6 +170,11 @@ __global__ void k_cvt_rows(const float* __restrict__ x, __half* __restrict__ y, 
         y[(long long)r * Cpad + c] = (ok && c < C) ? __float2half_rn(x[(long long)r * C + c]) : __half(0);
 }
 
+// Row pitch of the ISTFT head buffer [rows][n_fft + 2 -> 1028]: a multiple of four floats so that the GEMM epilogue's float4 stores
+// apply (with the natural pitch of 1026 every second row is only 8-byte aligned and the whole tile fell back to scalar stores: the
+// head GEMM ran at 115 TFLOP/s against 740 for the same K at N = 1536)
+constexpr int HEAD_PITCH = 1028;
+
 // ---- ISTFT head (vocos ISTFTHead + ISTFT(padding="center") == torch.istft(center=True)) ---------------------------
 // One CTA (256 threads) per mel frame: S = exp(mag) clipped at 1e2 times (cos p, sin p); 1024-point inverse real FFT in
 // shared memory (radix-2, Hermitian extension); multiply by the synthesis window; store the windowed frame.
@@ -180,7 +185,7 @@ __global__ void __launch_bounds__(256) k_istft_frame(const float* __restrict__ h
     const int r = blockIdx.x;
     if (!valid[r]) return;
     __shared__ float2 a[N];
-    const float* hp = head + (long long)r * (2 * NB);
+    const float* hp = head + (long long)r * HEAD_PITCH;
     for (int k = threadIdx.x; k < N; k += 256) {
         const int kk = (k <= 512) ? k : (N - k);
         float mag = __expf(hp[kk]);
@@ -401,7 +406,7 @@ extern "C" ctp_status ctp_voc_create(ctp_voc** out, const ctp_voc_cfg* c) {
     if (!st) st = voc_alloc(h, &h->o1, R, c->dvae_odim);
     if (!st) st = voc_alloc(h, &h->mel32, R, c->n_mels);
     if (!st) st = voc_alloc(h, &h->mel16, R, MEL_PAD);
-    if (!st) st = voc_alloc(h, &h->head, R, c->n_fft + 2);
+    if (!st) st = voc_alloc(h, &h->head, R, HEAD_PITCH);
     if (!st) st = voc_alloc(h, &h->frames, R, c->n_fft);
     if (!st) st = voc_alloc(h, &h->valid, R, 1);
     if (!st) st = voc_alloc(h, &h->row_src, R, 1);
@@ -589,7 +594,7 @@ static int voc_run_vocos(ctp_voc* h, const GroupLayout& L, int n_utt, float* wav
     VLAUNCH_OK();
     {   // ISTFTHead.out: Linear(512 -> n_fft + 2)
         GemmEpilogue e{};
-        e.out = h->head; e.ldo = c.n_fft + 2; e.bias = h->w.head_b; e.row_valid = h->valid;
+        e.out = h->head; e.ldo = HEAD_PITCH; e.bias = h->w.head_b; e.row_valid = h->valid;
         if ((st = voc_gemm(h->y16, c.voc_dim, 1, rows, h->w.head_w, c.n_fft + 2, e, s))) return st;
     }
     k_istft_frame<<<rows, 256, 0, s>>>(h->head, h->frames, h->valid, h->w.window, h->twiddle);
