@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <math.h>
+#include <string.h>
 #include <vector>
 
 using namespace ctp;
@@ -118,6 +119,121 @@ __global__ void __launch_bounds__(128) k_dwconv_ln(const float* __restrict__ x, 
     for (int i = 0; i < PER; ++i) {
         const int c = threadIdx.x + i * 128;
         o[c] = __float2half_rn((v[i] - mean) * rstd * ln_w[c] + ln_b[c]);
+    }
+}
+
+// Same operator, R consecutive rows per CTA with a sliding tap window in registers: a row of the residual stream is pulled from L2
+// (R + 6 dil) / R times instead of 7 times (one CTA per row re-read every row for each of its seven taps: 14 KB of L2 traffic per
+// 2 KB row, 60 us per 32000 rows against a 15 us HBM floor), the 7 tap weights per channel are fetched once per CTA, and the two
+// LayerNorm reductions are shared by four rows.  Rows of one residue class mod dil form one sliding chain.  The per-row arithmetic
+// (tap order, reduction order) is that of k_dwconv_ln, so the results are bit-identical.
+template <int C, int R>
+__global__ void __launch_bounds__(128) k_dwconv_ln_tile(const float* __restrict__ x, __half* __restrict__ y, const unsigned char* __restrict__ valid,
+                                                         const float* __restrict__ dw_w, const float* __restrict__ dw_b,
+                                                         const float* __restrict__ ln_w, const float* __restrict__ ln_b, int dil, int rows) {
+    constexpr int PER = C / 128;
+    const int r0 = blockIdx.x * R;
+    const int warp = threadIdx.x >> 5;
+    __shared__ float red[2][4][4];   // [mean | variance pass][row of the batch][warp]
+    float w[PER][7], bias[PER], lw[PER], lb[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int c = threadIdx.x + i * 128;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) w[i][k] = dw_w[c * 7 + k];
+        bias[i] = dw_b[c]; lw[i] = ln_w[c]; lb[i] = ln_b[c];
+    }
+    const long long lim = (long long)rows + GAP;   // rows [rows, rows + GAP) are the zero guard; nothing is addressable past it
+    for (int p = 0; p < dil; ++p) {
+        float win[PER][7];
+        const int rf = r0 + p;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const long long q = (long long)rf + (k - 3) * dil;
+                win[i][k] = q < lim ? x[q * C + threadIdx.x + i * 128] : 0.f;
+            }
+        }
+        // the newest tap row of each of the next four output rows is requested one round ahead (16 independent loads in flight per
+        // thread while the current round computes and reduces); a load issued right where it is consumed left every row exposed to a
+        // full L2 / HBM latency (230 us per 32000 rows, measured)
+        float nxt[4][PER];
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) {
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                const long long q = (long long)rf + (long long)bb * dil + 3 * dil;
+                nxt[bb][i] = q < lim ? x[q * C + threadIdx.x + i * 128] : 0.f;
+            }
+        }
+        for (int j0 = 0; j0 < R / dil; j0 += 4) {   // four rows of this residue class per reduction round
+            float cur[4][PER];
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb) {
+#pragma unroll
+                for (int i = 0; i < PER; ++i) cur[bb][i] = nxt[bb][i];
+            }
+            if (j0 + 4 < R / dil) {
+#pragma unroll
+                for (int bb = 0; bb < 4; ++bb) {
+#pragma unroll
+                    for (int i = 0; i < PER; ++i) {
+                        const long long q = (long long)rf + (long long)(j0 + 4 + bb) * dil + 3 * dil;
+                        nxt[bb][i] = q < lim ? x[q * C + threadIdx.x + i * 128] : 0.f;
+                    }
+                }
+            }
+            float v[4][PER], s4[4];
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb) {
+                float sacc = 0.f;
+#pragma unroll
+                for (int i = 0; i < PER; ++i) {
+                    win[i][6] = cur[bb][i];
+                    float acc = bias[i];
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) acc += w[i][k] * win[i][k];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) win[i][k] = win[i][k + 1];
+                    v[bb][i] = acc;
+                    sacc += acc;
+                }
+                s4[bb] = warp_sum(sacc);
+            }
+            if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+                for (int bb = 0; bb < 4; ++bb) red[0][bb][warp] = s4[bb];
+            }
+            __syncthreads();
+            float mean[4];
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb) {
+                mean[bb] = (red[0][bb][0] + red[0][bb][1] + red[0][bb][2] + red[0][bb][3]) / (float)C;
+                float q = 0.f;
+#pragma unroll
+                for (int i = 0; i < PER; ++i) { const float d = v[bb][i] - mean[bb]; q += d * d; }
+                s4[bb] = warp_sum(q);
+            }
+            if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+                for (int bb = 0; bb < 4; ++bb) red[1][bb][warp] = s4[bb];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb) {
+                const int r = rf + (j0 + bb) * dil;
+                if (r >= rows) continue;
+                const float rstd = rsqrtf((red[1][bb][0] + red[1][bb][1] + red[1][bb][2] + red[1][bb][3]) / (float)C + 1e-6f);
+                const bool ok = valid[r] != 0;
+                __half* o = y + (long long)r * C;
+#pragma unroll
+                for (int i = 0; i < PER; ++i)
+                    o[threadIdx.x + i * 128] = ok ? __float2half_rn((v[bb][i] - mean[bb]) * rstd * lw[i] + lb[i]) : __half(0);
+            }
+            // (the next round's first write to red[0] is ordered behind this round's reads of red[0] by the second barrier, and its
+            // writes to red[1] behind these reads of red[1] by its first barrier)
+        }
     }
 }
 
@@ -354,7 +470,8 @@ struct ctp_voc {
     __half* o1 = nullptr;     // [rows][odim]
     float* mel32 = nullptr;   // [rows][n_mels]
     __half* mel16 = nullptr;  // [rows][MEL_PAD]
-    float* head = nullptr;    // [rows][n_fft+2]
+    bool dw_tile = true;      // k_dwconv_ln_tile (16 rows per CTA); CTP_DWCONV=row keeps one CTA per row
+    float* head = nullptr;    // [rows][n_fft + 2, pitch HEAD_PITCH]
     float* frames = nullptr;  // [rows][n_fft]
     unsigned char* valid = nullptr;  // [rows]
     int* row_src = nullptr;   // [rows]
@@ -392,6 +509,7 @@ extern "C" ctp_status ctp_voc_create(ctp_voc** out, const ctp_voc_cfg* c) {
     if (gi) return (ctp_status)gi;
     ctp_voc* h = new ctp_voc();
     h->cfg = *c;
+    if (const char* e = getenv("CTP_DWCONV")) h->dw_tile = strcmp(e, "row") != 0;
     const long long R = c->max_frames;
     h->cap_rows = R;
     const int cw = std::max(c->dvae_hidden, c->voc_dim);
@@ -472,7 +590,9 @@ static int voc_gemm(const __half* act, int act_C, int taps, int rows, const void
 
 template <int C>
 static int convnext_block(ctp_voc* h, const ctp_convnext_w& b, int rows, int inter, int dil, cudaStream_t s) {
-    k_dwconv_ln<C><<<rows, 128, 0, s>>>(h->xres, h->y16, h->valid, b.dw_w, b.dw_b, b.ln_w, b.ln_b, dil);
+    constexpr int DW_R = 16;
+    if (h->dw_tile && (dil == 1 || dil == 2)) k_dwconv_ln_tile<C, DW_R><<<(rows + DW_R - 1) / DW_R, 128, 0, s>>>(h->xres, h->y16, h->valid, b.dw_w, b.dw_b, b.ln_w, b.ln_b, dil, rows);
+    else k_dwconv_ln<C><<<rows, 128, 0, s>>>(h->xres, h->y16, h->valid, b.dw_w, b.dw_b, b.ln_w, b.ln_b, dil);
     VLAUNCH_OK();
     GemmEpilogue e1{};
     e1.out = h->hm; e1.ldo = inter; e1.out_f16 = 1; e1.bias = b.pw1_b; e1.act_gelu = 1; e1.row_valid = h->valid;

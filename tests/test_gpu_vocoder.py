@@ -102,6 +102,24 @@ def test_hidden_to_wav_end_to_end_batch():
         assert e / _rms(ref) <= 1e-2
 
 
+def test_tiled_dwconv_ln_is_bit_identical_to_row_kernel(monkeypatch):
+    """k_dwconv_ln_tile (16 rows per CTA, sliding tap window, dilation 2 in the DVAE decoder and 1 in Vocos) keeps the per-row tap and
+    reduction order of the one-CTA-per-row kernel: the waveforms of a ragged batch (utterance lengths not multiples of 16, rows
+    running into the guard band) are bit-identical."""
+    dcfg, vcfg = synth.DVAEConfig(), synth.VocosConfig()
+    g = torch.Generator().manual_seed(9)
+    lens = [37, 5, 64, 1, 18]
+    hid = [torch.randn(n, 768, generator=g).cuda() for n in lens]
+    outs = []
+    for mode in ("row", "tile"):
+        monkeypatch.setenv("CTP_DWCONV", mode)
+        d, v, eng, dsd, vsd = _models(dcfg, vcfg, seed=15)
+        wavs, _ = eng.decode_batch(hid)
+        outs.append([w.cpu() for w in wavs])
+    for a_, b_ in zip(*outs):
+        assert torch.equal(a_, b_)
+
+
 def test_vocoder_grouping_when_workspace_is_small():
     """Utterances are processed in groups that fit the workspace; results do not depend on the grouping."""
     from chatttsplus_b200.vocoder import VocoderEngine
