@@ -205,6 +205,33 @@ int gemm_launch_maps(const CUtensorMap& tmA, const CUtensorMap& tmB, long long a
     }
 }
 
+int gemm_launch_swiglu(const void* A, long long a_rows, long long lda, const void* Wgu, long long I, long long K, __half* out, long long ldo,
+                       cudaStream_t stream) {
+    int st = gemm_init();
+    if (st) return st;
+    if ((I % 128) != 0 || (ldo % 8) != 0 || (reinterpret_cast<uintptr_t>(out) & 15) != 0) {
+        ctp_set_error("gemm_launch_swiglu: I %% 128, output pitch %% 8 and a 16-byte aligned output are required");
+        return CTP_ERR_INVALID;
+    }
+    CUtensorMap tmA, tmB;
+    if ((st = make_tmap_kmajor(&tmA, A, a_rows, K, lda, GEMM_BM))) return st;
+    if ((st = make_tmap_kmajor(&tmB, Wgu, 2 * I, K, K, 128))) return st;   // two 128-row boxes per 256-column tile
+    GemmShape shp{};
+    shp.k_blocks = (int)((K + GEMM_BK - 1) / GEMM_BK);
+    shp.desc_lbo = g_desc[0]; shp.desc_sbo = g_desc[1]; shp.desc_layout = g_desc[2]; shp.desc_kadv = g_desc[3];
+    shp.swiglu_up_row = (int)I;
+    GemmEpilogue epi{};
+    epi.out = out; epi.ldo = ldo; epi.out_f16 = 1; epi.T = (int)a_rows; epi.F = (int)I;
+    const int tiles_m = (int)((a_rows + GEMM_BM - 1) / GEMM_BM), tiles_n = (int)(I / 128);
+    const int grid = std::min(tiles_m * tiles_n, g_sm_count);
+    cudaError_t e = launch_k(gemm_tcgen05_persistent<256>, dim3(grid), dim3(GEMM_P_THREADS), (size_t)GemmPSmem<256>::TOTAL, stream, false, tmA, tmB, shp, epi,
+                             tiles_m, tiles_n);
+    ctp_count_launch();
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { ctp_set_error("swiglu gemm launch failed: %s", cudaGetErrorString(e)); return CTP_ERR_CUDA; }
+    return CTP_OK;
+}
+
 int gemm_launch(const GemmLaunch& g, cudaStream_t stream) {
     CUtensorMap tmA, tmB;
     int st = make_tmap_kmajor(&tmA, g.A, g.a_rows, g.K, g.lda, GEMM_BM);

@@ -53,6 +53,10 @@ struct GemmShape {
     // its last readers ran in an earlier kernel of the step
     float* zero_ptr;
     unsigned long long zero_f4;
+    // persistent kernel, SwiGLU mode (prefill gate|up GEMM, llama.py:214): the 256-column weight tile is TWO boxes of 128 rows — gate rows
+    // [n0/2, n0/2+128) and up rows [swiglu_up_row + n0/2, ...) of the packed [gate | up] matrix — so that an accumulator row holds gate(f) in
+    // column j and up(f) in column 128 + j, and the epilogue writes fp16 silu(gate) * up [T][I] directly (no fp32 [T][2I] round trip)
+    int swiglu_up_row;        // 0: off
 };
 
 constexpr int GEMM_BM = 128;
@@ -497,7 +501,12 @@ gemm_tcgen05_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_co
                     uint8_t* a = ring + s * S::STAGE_BYTES;
                     mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
                     tma_load_2d(&tmA, &full_bar[s], a, kb * GEMM_BK, m0);
-                    tma_load_2d(&tmB, &full_bar[s], a + S::A_BYTES, kb * GEMM_BK, n0);
+                    if (shp.swiglu_up_row) {
+                        tma_load_2d(&tmB, &full_bar[s], a + S::A_BYTES, kb * GEMM_BK, n0 / 2);
+                        tma_load_2d(&tmB, &full_bar[s], a + S::A_BYTES + S::B_BYTES / 2, kb * GEMM_BK, shp.swiglu_up_row + n0 / 2);
+                    } else {
+                        tma_load_2d(&tmB, &full_bar[s], a + S::A_BYTES, kb * GEMM_BK, n0);
+                    }
                 }
             }
         }
@@ -552,6 +561,37 @@ gemm_tcgen05_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_co
             const int row = m0 + q * 32 + lane;
             const bool row_ok = row < epi.T;
             const bool valid = row_ok && (epi.row_valid ? (epi.row_valid[row] != 0) : true);
+            if (shp.swiglu_up_row) {
+                // SwiGLU epilogue: this warp owns features [n0/2 + half * BN/4, + BN/4) of its 32 token rows: gate from columns
+                // [half * BN/4, ...), up from the same columns of the second half of the tile
+#pragma unroll 1
+                for (int c = half * (BN / 4); c < (half + 1) * (BN / 4); c += 32) {
+                    float g[32], u[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c), g);
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + BN / 2 + c), u);
+                    if (c + 32 >= (half + 1) * (BN / 4)) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[acc]);
+                    }
+                    const int f0 = n0 / 2 + c;
+                    if (row_ok && f0 < epi.F) {
+                        __half* o = reinterpret_cast<__half*>(epi.out) + (long long)row * epi.ldo + f0;
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            uint4 pk;
+                            __half2 h0 = __floats2half2_rn(silu(g[i]) * u[i], silu(g[i + 1]) * u[i + 1]);
+                            __half2 h1 = __floats2half2_rn(silu(g[i + 2]) * u[i + 2], silu(g[i + 3]) * u[i + 3]);
+                            __half2 h2 = __floats2half2_rn(silu(g[i + 4]) * u[i + 4], silu(g[i + 5]) * u[i + 5]);
+                            __half2 h3 = __floats2half2_rn(silu(g[i + 6]) * u[i + 6], silu(g[i + 7]) * u[i + 7]);
+                            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                            *reinterpret_cast<uint4*>(o + i) = pk;
+                        }
+                    }
+                }
+                continue;
+            }
             const int c_lo = half * (BN / 2), c_hi = c_lo + BN / 2;
 #pragma unroll 1
             for (int c = c_lo; c < c_hi; c += 32) {
@@ -639,6 +679,10 @@ struct GemmLaunch {
     GemmEpilogue epi;
 };
 int gemm_launch(const GemmLaunch& g, cudaStream_t stream);
+// Prefill gate|up projection with the SwiGLU epilogue: out[t][f] = fp16(silu(A[t] . Wgu[f]) * (A[t] . Wgu[I + f])), Wgu = [2I][K] packed
+// gate rows then up rows (I % 128 == 0, out pitch ldo % 8 == 0).  Persistent 128x256 tcgen05 kernel.
+int gemm_launch_swiglu(const void* A, long long a_rows, long long lda, const void* Wgu, long long I, long long K, __half* out, long long ldo,
+                       cudaStream_t stream);
 // Variant with prebuilt tensor maps (decode path: maps are created once at bind time).
 int gemm_launch_maps(const CUtensorMap& tmA, const CUtensorMap& tmB, long long a_rows, long long b_rows, long long K,
                      int block_n, int split_k, const GemmEpilogue& epi, cudaStream_t stream, const void* pf_ptr = nullptr,

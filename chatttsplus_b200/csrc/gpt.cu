@@ -501,10 +501,15 @@ extern "C" ctp_status ctp_gpt_prefill(ctp_gpt* h, int32_t B, int32_t L0, const f
     CTP_CUDA_OK(cudaStreamSynchronize(s));  // pads / gs are stack/heap temporaries
     CTP_CUDA_OK(cudaMemcpyAsync(h->x, emb, sizeof(float) * T * H, cudaMemcpyDeviceToDevice, s));
 
+    const bool fast_norm = H % 128 == 0;   // (k_rmsnorm: one 256-thread CTA per row, any H <= 1024)
     for (int l = 0; l < c.n_layers; ++l) {
-        NormArgs na{};
-        na.x = h->x; na.w = h->w.ln1 + (size_t)l * H; na.xn = h->xn; na.H = H; na.eps = c.rms_eps;
-        k_rmsnorm<<<(unsigned)T, 256, 0, s>>>(na);
+        if (fast_norm) {
+            k_rmsnorm_rows<<<(unsigned)((T + 7) / 8), 256, 0, s>>>(h->x, h->w.ln1 + (size_t)l * H, h->xn, T, H, c.rms_eps);
+        } else {
+            NormArgs na{};
+            na.x = h->x; na.w = h->w.ln1 + (size_t)l * H; na.xn = h->xn; na.H = H; na.eps = c.rms_eps;
+            k_rmsnorm<<<(unsigned)T, 256, 0, s>>>(na);
+        }
         LAUNCH_OK();
         {   // tokens are the M operand here (T = B*L0 rows): compute-bound, 128x256 tiles
             GemmLaunch g{};
@@ -533,19 +538,24 @@ extern "C" ctp_status ctp_gpt_prefill(ctp_gpt* h, int32_t B, int32_t L0, const f
             g.epi.out = h->x; g.epi.ldo = H; g.epi.residual = h->x; g.epi.ldr = H; g.epi.T = (int)T; g.epi.F = H;
             if ((st = gemm_launch(g, s))) return (ctp_status)st;
         }
-        NormArgs nb{};
-        nb.x = h->x; nb.w = h->w.ln2 + (size_t)l * H; nb.xn = h->xn; nb.H = H; nb.eps = c.rms_eps;
-        k_rmsnorm<<<(unsigned)T, 256, 0, s>>>(nb);
+        if (fast_norm) {
+            k_rmsnorm_rows<<<(unsigned)((T + 7) / 8), 256, 0, s>>>(h->x, h->w.ln2 + (size_t)l * H, h->xn, T, H, c.rms_eps);
+        } else {
+            NormArgs nb{};
+            nb.x = h->x; nb.w = h->w.ln2 + (size_t)l * H; nb.xn = h->xn; nb.H = H; nb.eps = c.rms_eps;
+            k_rmsnorm<<<(unsigned)T, 256, 0, s>>>(nb);
+        }
         LAUNCH_OK();
-        {
+        if (I % 128 == 0) {
+            // gate_proj | up_proj with silu(gate) * up in the GEMM epilogue (llama.py:214): fp16 [T][I] out, no fp32 [T][2I] round trip
+            if ((st = gemm_launch_swiglu(h->xn, T, H, (const __half*)h->w.wgu + (size_t)l * 2 * I * H, I, H, h->hmid, I, s))) return (ctp_status)st;
+        } else {
             GemmLaunch g{};
             g.A = h->xn; g.a_rows = T; g.lda = H;
             g.B = (const __half*)h->w.wgu + (size_t)l * 2 * I * H; g.b_rows = 2 * I; g.ldb = H;
             g.K = H; g.block_n = 256; g.split_k = 1;
             g.epi.out = h->acc_gu; g.epi.ldo = 2 * I; g.epi.T = (int)T; g.epi.F = 2 * I;
             if ((st = gemm_launch(g, s))) return (ctp_status)st;
-        }
-        {
             const long long total = T * I;
             k_silu_mul<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(h->acc_gu, h->hmid, I, total, 0);
             LAUNCH_OK();

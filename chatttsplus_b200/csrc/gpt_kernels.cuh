@@ -143,6 +143,39 @@ __global__ void __launch_bounds__(256) k_rmsnorm(NormArgs a) {
     if (threadIdx.x == 0) trace_end(a.trace);
 }
 
+// RMSNorm of many rows (prefill: rows = B * L0): one warp per row, float4 loads, no block-level barrier.  H % 128 == 0, H <= 1024.
+__global__ void __launch_bounds__(256) k_rmsnorm_rows(const float* __restrict__ x, const float* __restrict__ w, __half* __restrict__ xn,
+                                                       long long rows, int H, float eps) {
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31, nf = H >> 7;
+    const float4* xr = reinterpret_cast<const float4*>(x + row * H);
+    float4 v[8];
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (j < nf) {
+            v[j] = xr[lane + 32 * j];
+            ss += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+        }
+    }
+    ss = warp_sum(ss);
+    const float rstd = rsqrtf(ss / (float)H + eps);
+    uint2* o = reinterpret_cast<uint2*>(xn + row * H);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (j < nf) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(w) + lane + 32 * j);
+            const __half2 h0 = __floats2half2_rn(g.x * (v[j].x * rstd), g.y * (v[j].y * rstd));
+            const __half2 h1 = __floats2half2_rn(g.z * (v[j].z * rstd), g.w * (v[j].w * rstd));
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+            pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+            o[lane + 32 * j] = pk;
+        }
+    }
+}
+
 // h = silu(gate) * up   (llama.py:214), gate/up read from the fp32 accumulator [rows][2I]
 // zero_after: the split-K accumulator is consumed exactly once per step, so its reader re-arms it for the next step
 // (saves the 24 KB-per-row clear that used to sit in the RMSNorm kernel's critical path)
