@@ -292,16 +292,20 @@ __global__ void k_cvt_rows(const float* __restrict__ x, __half* __restrict__ y, 
 constexpr int HEAD_PITCH = 1028;
 
 // ---- ISTFT head (vocos ISTFTHead + ISTFT(padding="center") == torch.istft(center=True)) ---------------------------
-// One CTA (256 threads) per mel frame: S = exp(mag) clipped at 1e2 times (cos p, sin p); 1024-point inverse real FFT in
-// shared memory (radix-2, Hermitian extension); multiply by the synthesis window; store the windowed frame.
+// One CTA (256 threads) per mel frame: S = exp(mag) clipped at 1e2 times (cos p, sin p), Hermitian extension, 1024-point inverse
+// FFT in shared memory as FIVE radix-4 Stockham passes (natural order in and out, no bit reversal; one 4-point butterfly per thread
+// and pass, reads at stride 256 are conflict-free), multiply by the synthesis window; store the windowed frame.  (The first version ran
+// ten radix-2 passes with two butterflies per thread and a barrier each: 565 us per 32000 frames against a 40 us HBM floor.)
 __global__ void __launch_bounds__(256) k_istft_frame(const float* __restrict__ head, float* __restrict__ frames,
                                                       const unsigned char* __restrict__ valid, const float* __restrict__ window,
                                                       const float2* __restrict__ twiddle /*[512] exp(+2 pi i k/1024)*/) {
     constexpr int N = 1024, NB = 513;
     const int r = blockIdx.x;
     if (!valid[r]) return;
-    __shared__ float2 a[N];
+    __shared__ float2 buf0[N], buf1[N];
+    __shared__ float2 tw[512];
     const float* hp = head + (long long)r * HEAD_PITCH;
+    for (int k = threadIdx.x; k < 512; k += 256) tw[k] = twiddle[k];
     for (int k = threadIdx.x; k < N; k += 256) {
         const int kk = (k <= 512) ? k : (N - k);
         float mag = __expf(hp[kk]);
@@ -311,26 +315,41 @@ __global__ void __launch_bounds__(256) k_istft_frame(const float* __restrict__ h
         float re = mag * cs, im = mag * sn;
         if (kk == 0 || kk == 512) im = 0.f;  // c2r ignores the imaginary part of DC / Nyquist
         if (k > 512) im = -im;
-        const int rev = __brev((unsigned)k) >> 22;  // 10-bit reversal
-        a[rev] = make_float2(re, im);
+        buf0[k] = make_float2(re, im);
     }
     __syncthreads();
-#pragma unroll 1
-    for (int s = 1; s <= 10; ++s) {
-        const int half = 1 << (s - 1);
-        for (int j = threadIdx.x; j < N / 2; j += 256) {
-            const int grp = j >> (s - 1), pos = j & (half - 1);
-            const int i0 = (grp << s) + pos, i1 = i0 + half;
-            const float2 w = twiddle[pos << (10 - s)];
-            const float2 x1 = a[i1], x0 = a[i0];
-            const float2 t = make_float2(w.x * x1.x - w.y * x1.y, w.x * x1.y + w.y * x1.x);
-            a[i1] = make_float2(x0.x - t.x, x0.y - t.y);
-            a[i0] = make_float2(x0.x + t.x, x0.y + t.y);
+    const int j = threadIdx.x;
+    float2* in = buf0;
+    float2* out = buf1;
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        const int Ns = 1 << (2 * s);          // 1, 4, 16, 64, 256
+        const int k = j & (Ns - 1);
+        const int step = 256 >> (2 * s);      // twiddle of input q: exp(+2 pi i q k / (4 Ns)) = W1024^(q k step)
+        float2 v0 = in[j], v1 = in[j + 256], v2 = in[j + 512], v3 = in[j + 768];
+        if (s > 0) {
+            const int i1 = k * step, i2 = 2 * k * step, i3 = 3 * k * step;   // < 1024
+            float2 w1 = tw[i1 & 511], w2 = tw[i2 & 511], w3 = tw[i3 & 511];
+            if (i1 & 512) { w1.x = -w1.x; w1.y = -w1.y; }
+            if (i2 & 512) { w2.x = -w2.x; w2.y = -w2.y; }
+            if (i3 & 512) { w3.x = -w3.x; w3.y = -w3.y; }
+            v1 = make_float2(v1.x * w1.x - v1.y * w1.y, v1.x * w1.y + v1.y * w1.x);
+            v2 = make_float2(v2.x * w2.x - v2.y * w2.y, v2.x * w2.y + v2.y * w2.x);
+            v3 = make_float2(v3.x * w3.x - v3.y * w3.y, v3.x * w3.y + v3.y * w3.x);
         }
+        const float2 t0 = make_float2(v0.x + v2.x, v0.y + v2.y), t1 = make_float2(v0.x - v2.x, v0.y - v2.y);
+        const float2 t2 = make_float2(v1.x + v3.x, v1.y + v3.y);
+        const float2 t3 = make_float2(-(v1.y - v3.y), v1.x - v3.x);   // +i (v1 - v3): inverse transform
+        const int j0 = ((j - k) << 2) + k;
+        out[j0] = make_float2(t0.x + t2.x, t0.y + t2.y);
+        out[j0 + Ns] = make_float2(t1.x + t3.x, t1.y + t3.y);
+        out[j0 + 2 * Ns] = make_float2(t0.x - t2.x, t0.y - t2.y);
+        out[j0 + 3 * Ns] = make_float2(t1.x - t3.x, t1.y - t3.y);
         __syncthreads();
+        float2* t = in; in = out; out = t;
     }
     float* o = frames + (long long)r * N;
-    for (int n = threadIdx.x; n < N; n += 256) o[n] = a[n].x * (1.0f / N) * window[n];
+    for (int n = threadIdx.x; n < N; n += 256) o[n] = in[n].x * (1.0f / N) * window[n];
 }
 
 // overlap-add with window-envelope normalisation and centre trimming.  grid (ceil(max_len/256), n_utt)
