@@ -18,6 +18,7 @@ static std::once_flag g_once;
 static int g_init_status = 0;
 long long* g_dbg = nullptr;  // set by ctp_debug_gemm_stamps
 static int g_sm_count = 148;
+static int g_pair = 1;             // cta_group::2 pair per 256x256 tile when the problem fills a wave of pairs (CTP_GEMM_2CTA=0: never, 2: whenever eligible)
 static bool g_persistent = true;   // CTP_GEMM_PERSISTENT=0 selects the one-tile-per-CTA kernel for the large GEMMs too
 static uint32_t g_desc[4] = {1, 64, 2, 2};  // LBO>>4, SBO>>4, layout type, K-advance per UMMA_K (in 16-byte units)
 
@@ -38,12 +39,14 @@ int gemm_init() {
         }
         g_encode = reinterpret_cast<EncodeTiledFn>(fn);
         if (const char* pe = getenv("CTP_GEMM_PERSISTENT")) g_persistent = atoi(pe) != 0;
+        if (const char* pe = getenv("CTP_GEMM_2CTA")) g_pair = atoi(pe);
         if (const char* d = getenv("CTP_DESC")) {  // bring-up diagnostics only
             unsigned a, b, c, e;
             if (sscanf(d, "%u,%u,%u,%u", &a, &b, &c, &e) == 4) { g_desc[0] = a; g_desc[1] = b; g_desc[2] = c; g_desc[3] = e; }
         }
         cudaError_t pa = cudaFuncSetAttribute(gemm_tcgen05_persistent<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmPSmem<256>::TOTAL);
         if (pa == cudaSuccess) pa = cudaFuncSetAttribute(gemm_tcgen05_persistent<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmPSmem<128>::TOTAL);
+        if (pa == cudaSuccess) pa = cudaFuncSetAttribute(gemm_tcgen05_persistent2<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmP2Smem::TOTAL);
         if (pa == cudaSuccess) { cudaDeviceProp prop; int dev = 0; cudaGetDevice(&dev); if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) g_sm_count = prop.multiProcessorCount; }
         if (pa != cudaSuccess) { ctp_set_error("cudaFuncSetAttribute(persistent gemm smem): %s", cudaGetErrorString(pa)); g_init_status = CTP_ERR_CUDA; return; }
         cudaError_t a = set_smem_attr<32>();
@@ -205,6 +208,26 @@ int gemm_launch_maps(const CUtensorMap& tmA, const CUtensorMap& tmB, long long a
     }
 }
 
+// The pair tile pays once the problem holds at least one full wave of 256 x 256 tiles (measured: +4-8 % at M = 131072, 1316 -> 1376 TFLOP/s at
+// 16384 x 4096 x 4096; -7 % at M = 4096, N = 768 where 48 pairs leave a third of the SMs idle)
+static bool pair_wins(long long a_rows, long long n_cols) {
+    if (g_pair == 0) return false;
+    const long long pairs = ((a_rows + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * ((n_cols + 255) / 256);
+    return g_pair == 2 || pairs >= g_sm_count / 2;
+}
+
+// one cta_group::2 pair per 256 x 256 tile; tmB must have been built with 128-row boxes
+static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, long long a_rows, long long n_cols, GemmShape shp, const GemmEpilogue& epi, cudaStream_t stream) {
+    const int tiles_m2 = (int)((a_rows + 2 * GEMM_BM - 1) / (2 * GEMM_BM)), tiles_n = (int)((n_cols + 255) / 256);
+    const int pairs = std::min(tiles_m2 * tiles_n, g_sm_count / 2);
+    cudaError_t e = launch_kc(gemm_tcgen05_persistent2<256>, dim3(2 * pairs), dim3(GEMM_P_THREADS), (size_t)GemmP2Smem::TOTAL, stream, false, 2u, tmA, tmB, shp, epi, tiles_m2,
+                              tiles_n);
+    ctp_count_launch();
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { ctp_set_error("cta-pair gemm launch failed: %s", cudaGetErrorString(e)); return CTP_ERR_CUDA; }
+    return CTP_OK;
+}
+
 int gemm_launch_swiglu(const void* A, long long a_rows, long long lda, const void* Wgu, long long I, long long K, __half* out, long long ldo,
                        cudaStream_t stream) {
     int st = gemm_init();
@@ -222,6 +245,7 @@ int gemm_launch_swiglu(const void* A, long long a_rows, long long lda, const voi
     shp.swiglu_up_row = (int)I;
     GemmEpilogue epi{};
     epi.out = out; epi.ldo = ldo; epi.out_f16 = 1; epi.T = (int)a_rows; epi.F = (int)I;
+    if (pair_wins(a_rows, 2 * I)) return launch_pair(tmA, tmB, a_rows, 2 * I, shp, epi, stream);
     const int tiles_m = (int)((a_rows + GEMM_BM - 1) / GEMM_BM), tiles_n = (int)(I / 128);
     const int grid = std::min(tiles_m * tiles_n, g_sm_count);
     cudaError_t e = launch_k(gemm_tcgen05_persistent<256>, dim3(grid), dim3(GEMM_P_THREADS), (size_t)GemmPSmem<256>::TOTAL, stream, false, tmA, tmB, shp, epi,
@@ -236,8 +260,15 @@ int gemm_launch(const GemmLaunch& g, cudaStream_t stream) {
     CUtensorMap tmA, tmB;
     int st = make_tmap_kmajor(&tmA, g.A, g.a_rows, g.K, g.lda, GEMM_BM);
     if (st) return st;
-    st = make_tmap_kmajor(&tmB, g.B, g.b_rows, g.K, g.ldb, g.block_n);
+    const bool pair = g_persistent && !g.epi.swap && !g.epi.atomic && g.split_k <= 1 && g.a_rows >= 512 && g.block_n == 256 && pair_wins(g.a_rows, g.b_rows);
+    st = make_tmap_kmajor(&tmB, g.B, g.b_rows, g.K, g.ldb, pair ? 128 : g.block_n);
     if (st) return st;
+    if (pair) {
+        GemmShape shp{};
+        shp.k_blocks = (int)((g.K + GEMM_BK - 1) / GEMM_BK);
+        shp.desc_lbo = g_desc[0]; shp.desc_sbo = g_desc[1]; shp.desc_layout = g_desc[2]; shp.desc_kadv = g_desc[3];
+        return launch_pair(tmA, tmB, g.a_rows, g.b_rows, shp, g.epi, stream);
+    }
     return gemm_launch_maps(tmA, tmB, g.a_rows, g.b_rows, g.K, g.block_n, g.split_k, g.epi, stream);
 }
 

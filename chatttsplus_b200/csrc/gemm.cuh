@@ -439,6 +439,116 @@ struct GemmPSmem {
     static constexpr int TOTAL = STAGES * STAGE_BYTES + VEC_BYTES + 256 + 1024;
 };
 
+// Epilogue of one accumulator tile for one of the eight epilogue warps of the persistent kernels: TMEM lane quarter q (tile rows), column
+// half `half`; bias / GELU / layer-scale / residual / row mask / fp16-or-fp32 store, or the SwiGLU form.  The accumulator is handed back
+// to the MMA thread (arrival on the shared::cluster address tempty_addr: the CTA's own barrier, or the pair leader's) right after this
+// warp's last TMEM read.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+
+template <int BN>
+__device__ __forceinline__ void gemm_p_epilogue_tile(const GemmShape& shp, const GemmEpilogue& epi, uint32_t tmem_base, int acc, int m0, int n0, int q,
+                                                     int half, int lane, const float* s_bias, const float* s_gamma, uint32_t tempty_addr) {
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < epi.T;
+    const bool valid = row_ok && (epi.row_valid ? (epi.row_valid[row] != 0) : true);
+    if (shp.swiglu_up_row) {
+        // SwiGLU epilogue: this warp owns features [n0/2 + half * BN/4, + BN/4) of its 32 token rows: gate from columns
+        // [half * BN/4, ...), up from the same columns of the second half of the tile
+#pragma unroll 1
+        for (int c = half * (BN / 4); c < (half + 1) * (BN / 4); c += 32) {
+            float g[32], u[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c), g);
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + BN / 2 + c), u);
+            if (c + 32 >= (half + 1) * (BN / 4)) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(tempty_addr);
+            }
+            const int f0 = n0 / 2 + c;
+            if (row_ok && f0 < epi.F) {
+                __half* o = reinterpret_cast<__half*>(epi.out) + (long long)row * epi.ldo + f0;
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    uint4 pk;
+                    __half2 h0 = __floats2half2_rn(silu(g[i]) * u[i], silu(g[i + 1]) * u[i + 1]);
+                    __half2 h1 = __floats2half2_rn(silu(g[i + 2]) * u[i + 2], silu(g[i + 3]) * u[i + 3]);
+                    __half2 h2 = __floats2half2_rn(silu(g[i + 4]) * u[i + 4], silu(g[i + 5]) * u[i + 5]);
+                    __half2 h3 = __floats2half2_rn(silu(g[i + 6]) * u[i + 6], silu(g[i + 7]) * u[i + 7]);
+                    pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                    pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                    *reinterpret_cast<uint4*>(o + i) = pk;
+                }
+            }
+        }
+        return;
+    }
+    const int c_lo = half * (BN / 2), c_hi = c_lo + BN / 2;
+#pragma unroll 1
+    for (int c = c_lo; c < c_hi; c += 32) {
+        float v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c), v);
+        if (c + 32 >= c_hi) {   // last read of this accumulator by this warp: hand it back to the MMA warp as early as possible
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_addr);
+        }
+        const int f0 = n0 + c;
+        if (row_ok && f0 < epi.F) {   // (a block, not `continue`: the warp reconverges before the next aligned tcgen05.ld)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += s_bias[c + i];
+        if (epi.act_gelu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= s_gamma[c + i];
+        const bool full = (f0 + 32 <= epi.F);
+        if (epi.residual) {
+            const float* rp = epi.residual + (long long)row * epi.ldr + f0;
+            if (full && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 r4 = *reinterpret_cast<const float4*>(rp + i);
+                    v[i] += r4.x; v[i + 1] += r4.y; v[i + 2] += r4.z; v[i + 3] += r4.w;
+                }
+            } else {
+                for (int i = 0; i < 32; ++i) if (f0 + i < epi.F) v[i] += rp[i];
+            }
+        }
+        if (!valid) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+        if (epi.out_f16) {
+            __half* o = reinterpret_cast<__half*>(epi.out) + (long long)row * epi.ldo + f0;
+            if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    __half2 h0 = __floats2half2_rn(v[i], v[i + 1]), h1 = __floats2half2_rn(v[i + 2], v[i + 3]);
+                    __half2 h2 = __floats2half2_rn(v[i + 4], v[i + 5]), h3 = __floats2half2_rn(v[i + 6], v[i + 7]);
+                    uint4 pk;
+                    pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                    pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                    *reinterpret_cast<uint4*>(o + i) = pk;
+                }
+            } else {
+                for (int i = 0; i < 32; ++i) if (f0 + i < epi.F) o[i] = __float2half_rn(v[i]);
+            }
+        } else {
+            float* o = reinterpret_cast<float*>(epi.out) + (long long)row * epi.ldo + f0;
+            if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else {
+                for (int i = 0; i < 32; ++i) if (f0 + i < epi.F) o[i] = v[i];
+            }
+        }
+        }
+    }
+}
+
 // Tile order of the persistent kernel: groups of G = gridDim.x / tiles_n m-tiles, and inside a group all n-tiles of those m-tiles.
 // One wave of CTAs then covers every n-tile of G m-tiles: an activation tile is pulled from HBM once and shared through L2 by the
 // tiles_n CTAs that need it at the same time (n-major order re-read the whole activation matrix from HBM once per n-tile: 800 MB
@@ -558,108 +668,181 @@ gemm_tcgen05_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_co
             asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(&tfull[acc], (j >> 1) & 1);
             tc_fence_after();
-            const int row = m0 + q * 32 + lane;
-            const bool row_ok = row < epi.T;
-            const bool valid = row_ok && (epi.row_valid ? (epi.row_valid[row] != 0) : true);
-            if (shp.swiglu_up_row) {
-                // SwiGLU epilogue: this warp owns features [n0/2 + half * BN/4, + BN/4) of its 32 token rows: gate from columns
-                // [half * BN/4, ...), up from the same columns of the second half of the tile
-#pragma unroll 1
-                for (int c = half * (BN / 4); c < (half + 1) * (BN / 4); c += 32) {
-                    float g[32], u[32];
-                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c), g);
-                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + BN / 2 + c), u);
-                    if (c + 32 >= (half + 1) * (BN / 4)) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tempty[acc]);
-                    }
-                    const int f0 = n0 / 2 + c;
-                    if (row_ok && f0 < epi.F) {
-                        __half* o = reinterpret_cast<__half*>(epi.out) + (long long)row * epi.ldo + f0;
-#pragma unroll
-                        for (int i = 0; i < 32; i += 8) {
-                            uint4 pk;
-                            __half2 h0 = __floats2half2_rn(silu(g[i]) * u[i], silu(g[i + 1]) * u[i + 1]);
-                            __half2 h1 = __floats2half2_rn(silu(g[i + 2]) * u[i + 2], silu(g[i + 3]) * u[i + 3]);
-                            __half2 h2 = __floats2half2_rn(silu(g[i + 4]) * u[i + 4], silu(g[i + 5]) * u[i + 5]);
-                            __half2 h3 = __floats2half2_rn(silu(g[i + 6]) * u[i + 6], silu(g[i + 7]) * u[i + 7]);
-                            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                            *reinterpret_cast<uint4*>(o + i) = pk;
-                        }
-                    }
-                }
-                continue;
-            }
-            const int c_lo = half * (BN / 2), c_hi = c_lo + BN / 2;
-#pragma unroll 1
-            for (int c = c_lo; c < c_hi; c += 32) {
-                float v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c), v);
-                if (c + 32 >= c_hi) {   // last read of this accumulator by this warp: hand it back to the MMA warp as early as possible
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[acc]);
-                }
-                const int f0 = n0 + c;
-                if (row_ok && f0 < epi.F) {   // (a block, not `continue`: the warp reconverges before the next aligned tcgen05.ld)
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] += s_bias[c + i];
-                if (epi.act_gelu) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-                }
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] *= s_gamma[c + i];
-                const bool full = (f0 + 32 <= epi.F);
-                if (epi.residual) {
-                    const float* rp = epi.residual + (long long)row * epi.ldr + f0;
-                    if (full && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            const float4 r4 = *reinterpret_cast<const float4*>(rp + i);
-                            v[i] += r4.x; v[i + 1] += r4.y; v[i + 2] += r4.z; v[i + 3] += r4.w;
-                        }
-                    } else {
-                        for (int i = 0; i < 32; ++i) if (f0 + i < epi.F) v[i] += rp[i];
-                    }
-                }
-                if (!valid) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = 0.f;
-                }
-                if (epi.out_f16) {
-                    __half* o = reinterpret_cast<__half*>(epi.out) + (long long)row * epi.ldo + f0;
-                    if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 8) {
-                            __half2 h0 = __floats2half2_rn(v[i], v[i + 1]), h1 = __floats2half2_rn(v[i + 2], v[i + 3]);
-                            __half2 h2 = __floats2half2_rn(v[i + 4], v[i + 5]), h3 = __floats2half2_rn(v[i + 6], v[i + 7]);
-                            uint4 pk;
-                            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                            *reinterpret_cast<uint4*>(o + i) = pk;
-                        }
-                    } else {
-                        for (int i = 0; i < 32; ++i) if (f0 + i < epi.F) o[i] = __float2half_rn(v[i]);
-                    }
-                } else {
-                    float* o = reinterpret_cast<float*>(epi.out) + (long long)row * epi.ldo + f0;
-                    if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                    } else {
-                        for (int i = 0; i < 32; ++i) if (f0 + i < epi.F) o[i] = v[i];
-                    }
-                }
-                }
-            }
+            gemm_p_epilogue_tile<BN>(shp, epi, tmem_base, acc, m0, n0, q, half, lane, s_bias, s_gamma, smem_u32(&tempty[acc]));
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 5) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): two CTAs of a cluster — two SMs of one TPC — work on ONE 256 x 256 output tile.  Each CTA loads its
+// own 128 rows of the activation tile and HALF of the weight tile (128 of the 256 weight rows) per k-block: 32 KB per SM per k-block
+// instead of 48 KB, which is what bounds the K = 512 pointwise convolutions of the vocoder (94 B/clk per SM demanded by the one-CTA
+// tile against ~64 B/clk an SM can take in).  Protocol (the CUTLASS 2-SM scheme, written out in PTX):
+//   * both CTAs run a TMA producer; every load is cp.async.bulk.tensor...cta_group::2 and completes on the LEADER's (rank 0) full
+//     barrier, for which the leader's producer posts the bytes of both CTAs;
+//   * the leader's MMA thread alone issues tcgen05.mma.cta_group::2 (M = 256: rows 0-127 accumulate in its own TMEM, 128-255 in the
+//     peer's, same column addresses; the 256-row N operand is read half from each CTA's shared memory) and signals stage-free and
+//     accumulator-ready with tcgen05.commit.cta_group::2 ... multicast::cluster to the barriers of BOTH CTAs;
+//   * the eight epilogue warps of each CTA drain their own TMEM and arrive on the leader's accumulator-free barrier (16 arrivals).
+// In SwiGLU mode CTA 0 holds the gate rows of the weight tile and CTA 1 the up rows.
+// ---------------------------------------------------------------------------------------------------------
+struct GemmP2Smem {
+    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;      // this CTA's 128 activation rows
+    static constexpr int B_BYTES = 128 * GEMM_BK * 2;          // this CTA's half of the 256 weight rows
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;      // 32 KB
+    static constexpr int STAGES = 6;
+    static constexpr int VEC_BYTES = 2 * 256 * 4;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + VEC_BYTES + 256 + 1024;
+};
+
+__device__ __forceinline__ void tma_load_2d_2sm(const void* desc, uint32_t bar_cluster_addr, void* smem_dst, int32_t c0, int32_t c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :
+        : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive (once all MMAs issued so far have completed) on the barrier at this shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+
+template <int BN>   // 256
+__global__ void __launch_bounds__(GEMM_P_THREADS, 1)
+gemm_tcgen05_persistent2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape shp,
+                         const GemmEpilogue epi, const int tiles_m2 /* pairs of m-tiles */, const int tiles_n) {
+    using S = GemmP2Smem;
+    static_assert(BN == 256, "the pair tile is 256 x 256");
+    constexpr int STAGES = S::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* ring = smem;
+    float* s_bias = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES);
+    float* s_gamma = s_bias + BN;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES + S::VEC_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull = empty_bar + STAGES;    // [2] accumulator ready (both CTAs, multicast commit)
+    uint64_t* tempty = tfull + 2;            // [2] accumulator drained (leader's: 16 arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const bool leader = rank == 0;
+    const int pair = (int)blockIdx.x >> 1, n_pairs = (int)gridDim.x >> 1;
+    const int n_tiles = tiles_m2 * tiles_n;
+    const int nkb = shp.k_blocks;
+    const int G = n_pairs / tiles_n > 0 ? n_pairs / tiles_n : 1;
+
+    if (warp == 4 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 16); }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    // both CTAs' barriers are initialised and both allocations are done before anything is signalled across the pair
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int t = pair; t < n_tiles; t += n_pairs) {
+                int tm, tn;
+                gemm_p_tile(t, tiles_m2, tiles_n, G, tm, tn);
+                const int m0 = (2 * tm + (int)rank) * GEMM_BM, n0 = tn * BN;
+                const int brow = shp.swiglu_up_row ? (leader ? n0 / 2 : shp.swiglu_up_row + n0 / 2) : n0 + 128 * (int)rank;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+                    uint8_t* a = ring + s * S::STAGE_BYTES;
+                    uint32_t lbar;   // the leader's full barrier of this stage, as a shared::cluster address
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(lbar) : "r"(smem_u32(&full_bar[s])), "r"(0u));
+                    if (leader) mbar_expect_tx(&full_bar[s], 2 * S::STAGE_BYTES);
+                    tma_load_2d_2sm(&tmA, lbar, a, kb * GEMM_BK, m0);
+                    tma_load_2d_2sm(&tmB, lbar, a + S::A_BYTES, kb * GEMM_BK, brow);
+                }
+            }
+        }
+    } else if (warp == 5) {
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(256, 256);
+            uint32_t it = 0;
+            int j = 0;
+            for (int t = pair; t < n_tiles; t += n_pairs, ++j) {
+                const int acc = j & 1;
+                mbar_wait(&tempty[acc], ((j >> 1) & 1) ^ 1);   // both CTAs' epilogues have drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&full_bar[s], (it / STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(ring + s * S::STAGE_BYTES);
+                    const uint64_t da = make_kmajor_desc(a_addr, shp.desc_lbo, shp.desc_sbo, shp.desc_layout);
+                    const uint64_t db = make_kmajor_desc(a_addr + S::A_BYTES, shp.desc_lbo, shp.desc_sbo, shp.desc_layout);
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k)
+                        umma_f16_2sm(d_tmem, da + (uint64_t)(shp.desc_kadv * k), db + (uint64_t)(shp.desc_kadv * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    umma_commit_2sm(&empty_bar[s]);
+                }
+                umma_commit_2sm(&tfull[acc]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int half = warp < 4 ? 0 : 1;
+        const int et = (warp < 4 ? warp : warp - 2) * 32 + lane;   // 0..255
+        uint32_t lte[2];   // the leader's accumulator-drained barriers
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(lte[0]) : "r"(smem_u32(&tempty[0])), "r"(0u));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(lte[1]) : "r"(smem_u32(&tempty[1])), "r"(0u));
+        int j = 0;
+        for (int t = pair; t < n_tiles; t += n_pairs, ++j) {
+            const int acc = j & 1;
+            int tm, tn;
+            gemm_p_tile(t, tiles_m2, tiles_n, G, tm, tn);
+            const int m0 = (2 * tm + (int)rank) * GEMM_BM, n0 = tn * BN;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const bool sw = shp.swiglu_up_row != 0;
+            for (int i = et; i < BN; i += 256) {
+                const int f = n0 + i;
+                s_bias[i] = (!sw && epi.bias && f < epi.F) ? epi.bias[f] : 0.f;
+                s_gamma[i] = (!sw && epi.gamma && f < epi.F) ? epi.gamma[f] : 1.f;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            mbar_wait(&tfull[acc], (j >> 1) & 1);
+            tc_fence_after();
+            gemm_p_epilogue_tile<BN>(shp, epi, tmem_base, acc, m0, n0, q, half, lane, s_bias, s_gamma, lte[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    // neither CTA may release its half of the pair's tensor memory (or exit, while the peer may still signal its barriers) before both are done
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -13,7 +13,7 @@ eng = VocoderEngine(d, v)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 nf = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 hid = [torch.randn(nf, 768, device="cuda") for _ in range(B)]
-for rep in range(2):
+for rep in range(5):
     e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(2))
     e1.record()
     wavs, _ = eng.decode_batch(hid)

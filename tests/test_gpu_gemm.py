@@ -100,3 +100,28 @@ def test_gemm_persistent_epilogue(M, N, K, bn, f16):
     out = gemm(A, B, out_f16=f16, gelu=True, bias=bias, block_n=bn)
     ref = torch.nn.functional.gelu(_ref(A, B) + bias)
     _check(out, ref, tol_rel=3e-3, what=f"persistent bias+gelu {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("M,N,K,f16", [(9000, 2048, 512, True), (700, 1027, 512, True), (5000, 771, 320, False), (1281, 256, 1536, False)])
+def test_gemm_cta_pair_kernel(M, N, K, f16, monkeypatch):
+    """cta_group::2 kernel (two CTAs of a cluster on one 256 x 256 tile, forced for every eligible shape): odd numbers of 128-row tiles (the
+    second CTA of the last pair is all padding), partial and unaligned N tiles, bias + GELU epilogue; fp16 and fp32 outputs."""
+    import subprocess, sys, os, textwrap
+    # the switch is read once per process: run the forced mode in a child
+    code = textwrap.dedent(f"""
+        import sys, torch
+        sys.path.insert(0, {os.path.dirname(os.path.abspath(__file__))!r}); sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})
+        from gpu_util import gemm
+        g = torch.Generator(device="cuda").manual_seed({M + N})
+        A = (torch.randn({M}, {K}, device="cuda", generator=g) * 0.3).half()
+        B = (torch.randn({N}, {K}, device="cuda", generator=g) * 0.05).half()
+        bias = torch.randn({N}, device="cuda", generator=g) * 0.1
+        out = gemm(A, B, out_f16={f16}, gelu=True, bias=bias, block_n=256)
+        ref = torch.nn.functional.gelu(A.float() @ B.float().t() + bias)
+        err = float((out.float() - ref).abs().max()); scale = float(ref.abs().max())
+        print("ERR", err, scale)
+        assert err <= 3e-3 * max(1.0, scale), (err, scale)
+    """)
+    env = dict(os.environ, CTP_GEMM_2CTA="2")
+    r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:]
