@@ -496,14 +496,18 @@ __device__ __forceinline__ void gemm_p_epilogue_tile(const GemmShape& shp, const
         }
         const int f0 = n0 + c;
         if (row_ok && f0 < epi.F) {   // (a block, not `continue`: the warp reconverges before the next aligned tcgen05.ld)
+        if (epi.bias) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += s_bias[c + i];
+            for (int i = 0; i < 32; ++i) v[i] += s_bias[c + i];
+        }
         if (epi.act_gelu) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
         }
+        if (epi.gamma) {   // (the K = 512 GELU tiles are epilogue-bound: 2 warps per scheduler x 128 values x ~17 instructions against 4096 MMA cycles)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] *= s_gamma[c + i];
+            for (int i = 0; i < 32; ++i) v[i] *= s_gamma[c + i];
+        }
         const bool full = (f0 + 32 <= epi.F);
         if (epi.residual) {
             const float* rp = epi.residual + (long long)row * epi.ldr + f0;
