@@ -19,7 +19,7 @@ struct GemmEpilogue {
     int out_f16;             // 1: __half output, 0: float
     int atomic;              // 1: atomicAdd into fp32 out (split-K or residual accumulate)
     int swap;                // 0: tile rows = tokens t, tile cols = features f;  1: rows = f, cols = t
-    int act_gelu;            // exact-erf GELU after bias
+    int act_gelu;            // exact-erf GELU after bias: 1 = Abramowitz-Stegun form (rcp + ex2), 2 = one-MUFU form (ctp_common.cuh)
     const float* bias;       // [F] or null
     const float* gamma;      // [F] or null (applied after activation)
     const float* residual;   // fp32 [T][ldr] or null (added last)
@@ -96,7 +96,7 @@ __device__ __forceinline__ void gemm_epilogue_store(const GemmEpilogue& e, int r
             float x = acc[j];
             if (f < e.F) {
                 if (e.bias && add_bias) x += e.bias[f];
-                if (e.act_gelu) x = gelu_erf(x);
+                if (e.act_gelu) x = e.act_gelu == 2 ? gelu_erf_poly(x) : gelu_erf(x);
                 if (e.gamma) x *= e.gamma[f];
                 if (e.residual && add_bias) x += e.residual[(long long)t * e.ldr + f];
             }
@@ -149,7 +149,7 @@ __device__ __forceinline__ void gemm_epilogue_store(const GemmEpilogue& e, int r
             const int t = col_g0 + j;
             if (t >= e.T) break;
             float x = acc[j] + b;
-            if (e.act_gelu) x = gelu_erf(x);
+            if (e.act_gelu) x = e.act_gelu == 2 ? gelu_erf_poly(x) : gelu_erf(x);
             x *= g;
             if (e.residual && add_bias) x += e.residual[(long long)t * e.ldr + f];
             if (e.row_valid && !e.row_valid[t]) x = 0.0f;
@@ -500,7 +500,10 @@ __device__ __forceinline__ void gemm_p_epilogue_tile(const GemmShape& shp, const
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] += s_bias[c + i];
         }
-        if (epi.act_gelu) {
+        if (epi.act_gelu == 2) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_erf_poly(v[i]);
+        } else if (epi.act_gelu) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
         }

@@ -30,6 +30,8 @@ struct GraphKey {
 
 }  // namespace
 
+static int g_split_target = 296;   // CTAs per decode GEMM: two per SM (83 KB of shared memory each) measured best; CTP_GEMM_CTAS, re-read at every handle creation
+
 struct ctp_gpt {
     ctp_gpt_cfg cfg{};
     ctp_gpt_weights w{};
@@ -67,6 +69,7 @@ struct ctp_gpt {
     std::map<GraphKey, cudaGraphExec_t> graphs;
     std::map<GraphKey, long long> graph_nodes;
     cudaStream_t cap_stream = nullptr;
+    cudaEvent_t poll_ev = nullptr;   // marks the lagged copy of the all_done flag in ctp_gpt_generate
 
     int sm_count = 0;
     bool use_pdl = true;       // programmatic dependent launch between the kernels of the decode step graph (CTP_PDL=0 disables)
@@ -171,6 +174,7 @@ extern "C" ctp_status ctp_gpt_create(ctp_gpt** out, const ctp_gpt_cfg* cfg) {
     CK(cudaMemset(h->st, 0, sizeof(GenState)));
     CK(cudaMallocHost(&h->st_pin, sizeof(GenState)));
     CK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->poll_ev, cudaEventDisableTiming));
     CK(cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     {
         // llama.py:98 — inv_freq = 1 / base^(2i/d), evaluated in fp32 like torch does
@@ -184,6 +188,7 @@ extern "C" ctp_status ctp_gpt_create(ctp_gpt** out, const ctp_gpt_cfg* cfg) {
         h->sm_count = prop.multiProcessorCount;
         const int I = cfg->inter;
         if (const char* e = getenv("CTP_PDL")) h->use_pdl = atoi(e) != 0;
+        g_split_target = getenv("CTP_GEMM_CTAS") ? atoi(getenv("CTP_GEMM_CTAS")) : 296;
         if (const char* e = getenv("CTP_FUSE_NORM")) h->fuse_norm = atoi(e) != 0;
         if (const char* e = getenv("CTP_ATTN_CTAS")) h->attn_cta_target = atoi(e);
         CK(cudaMalloc(&h->dec_gu, sizeof(float) * (128 + (size_t)64 * 2 * I)));
@@ -230,6 +235,7 @@ extern "C" void ctp_gpt_destroy(ctp_gpt* h) {
     cudaFree(h->attn_cnt); cudaFree(h->pad_len); cudaFree(h->inv_freq); cudaFree(h->st);
     if (h->st_pin) cudaFreeHost(h->st_pin);
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+    if (h->poll_ev) cudaEventDestroy(h->poll_ev);
     delete h;
 }
 
@@ -289,8 +295,7 @@ static GemmEpilogue epi_swap_atomic(float* out, long long ldo, int T, int F) {
 }
 
 static int split_for(int k_blocks, int m_tiles, int target_ctas = 0) {
-    static const int env_target = getenv("CTP_GEMM_CTAS") ? atoi(getenv("CTP_GEMM_CTAS")) : 296;   // CTAs per decode GEMM: two per SM (83 KB of shared memory each) measured best
-    if (target_ctas <= 0) target_ctas = env_target;
+    if (target_ctas <= 0) target_ctas = g_split_target;
     int s = target_ctas / m_tiles;
     if (s < 1) s = 1;
     if (s > k_blocks) s = k_blocks;
@@ -682,17 +687,16 @@ extern "C" ctp_status ctp_gpt_generate(ctp_gpt* h, const ctp_sample_cfg* cfg, in
     int iters = max_steps;
     iters = std::min(iters, h->max_new - h->step);
     iters = std::min(iters, h->cfg.max_seq - h->cur_len);
-    cudaEvent_t ev = nullptr;
-    CTP_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    cudaEvent_t ev = h->poll_ev;
     bool pending = false;
     h->st_pin->all_done = 0;
     for (int it = 0; it < iters; ++it) {
         {
             cudaGraphExec_t g;
-            if ((st = get_graph(h, h->B, nsplit_for(h, h->B, h->cur_len + 1), &g))) { cudaEventDestroy(ev); return (ctp_status)st; }
+            if ((st = get_graph(h, h->B, nsplit_for(h, h->B, h->cur_len + 1), &g))) return (ctp_status)st;
             ctp_count_launch((int)h->graph_nodes[GraphKey{h->B, nsplit_for(h, h->B, h->cur_len + 1), h->text_mode}]);
             cudaError_t e = cudaGraphLaunch(g, s);
-            if (e != cudaSuccess) { ctp_set_error("graph launch: %s", cudaGetErrorString(e)); cudaEventDestroy(ev); return CTP_ERR_CUDA; }
+            if (e != cudaSuccess) { ctp_set_error("graph launch: %s", cudaGetErrorString(e)); return CTP_ERR_CUDA; }
         }
         h->cur_len += 1; h->step += 1; done += 1;
         if ((it + 1) % check_every == 0 && it + 1 < iters) {
@@ -707,7 +711,6 @@ extern "C" ctp_status ctp_gpt_generate(ctp_gpt* h, const ctp_sample_cfg* cfg, in
             pending = true;
         }
     }
-    cudaEventDestroy(ev);
     CTP_CUDA_OK(cudaGetLastError());
     if (steps_done) *steps_done = done;
     return CTP_OK;

@@ -489,6 +489,7 @@ struct ctp_voc {
     __half* o1 = nullptr;     // [rows][odim]
     float* mel32 = nullptr;   // [rows][n_mels]
     __half* mel16 = nullptr;  // [rows][MEL_PAD]
+    int gelu_mode = 2;        // GEMM epilogue GELU: 2 = one-MUFU erf (ctp_common.cuh), 1 = Abramowitz-Stegun form (CTP_GELU=as)
     bool dw_tile = true;      // k_dwconv_ln_tile (16 rows per CTA); CTP_DWCONV=row keeps one CTA per row
     float* head = nullptr;    // [rows][n_fft + 2, pitch HEAD_PITCH]
     float* frames = nullptr;  // [rows][n_fft]
@@ -529,6 +530,7 @@ extern "C" ctp_status ctp_voc_create(ctp_voc** out, const ctp_voc_cfg* c) {
     ctp_voc* h = new ctp_voc();
     h->cfg = *c;
     if (const char* e = getenv("CTP_DWCONV")) h->dw_tile = strcmp(e, "row") != 0;
+    if (const char* e = getenv("CTP_GELU")) h->gelu_mode = strcmp(e, "as") == 0 ? 1 : 2;
     const long long R = c->max_frames;
     h->cap_rows = R;
     const int cw = std::max(c->dvae_hidden, c->voc_dim);
@@ -614,7 +616,7 @@ static int convnext_block(ctp_voc* h, const ctp_convnext_w& b, int rows, int int
     else k_dwconv_ln<C><<<rows, 128, 0, s>>>(h->xres, h->y16, h->valid, b.dw_w, b.dw_b, b.ln_w, b.ln_b, dil);
     VLAUNCH_OK();
     GemmEpilogue e1{};
-    e1.out = h->hm; e1.ldo = inter; e1.out_f16 = 1; e1.bias = b.pw1_b; e1.act_gelu = 1; e1.row_valid = h->valid;
+    e1.out = h->hm; e1.ldo = inter; e1.out_f16 = 1; e1.bias = b.pw1_b; e1.act_gelu = h->gelu_mode; e1.row_valid = h->valid;
     int st = voc_gemm(h->y16, C, 1, rows, b.pw1_w, inter, e1, s);
     if (st) return st;
     GemmEpilogue e2{};
@@ -695,7 +697,7 @@ static int voc_run_stack(ctp_voc* h, int rows, cudaStream_t s) {
     int st;
     {   // conv_in[0]: Conv1d(idim -> bn, k3, p1) + GELU   (dvae.py:145-147)
         GemmEpilogue e{};
-        e.out = h->c1; e.ldo = c.dvae_bn; e.out_f16 = 1; e.bias = h->w.conv_in0_b; e.act_gelu = 1; e.row_valid = h->valid;
+        e.out = h->c1; e.ldo = c.dvae_bn; e.out_f16 = 1; e.bias = h->w.conv_in0_b; e.act_gelu = h->gelu_mode; e.row_valid = h->valid;
         if ((st = voc_gemm(h->x0, c.dvae_idim, 3, rows, h->w.conv_in0_w, c.dvae_bn, e, s))) return st;
     }
     {   // conv_in[2]: Conv1d(bn -> hidden, k3, p1) -> fp32 residual stream
@@ -828,7 +830,7 @@ extern "C" ctp_status ctp_voc_encode(ctp_voc* h, int32_t n_samples, const float*
     VLAUNCH_OK();
     {   // downsample_conv.0: Conv1d(100 -> dim, k3, p1) + GELU (dvae.py:227-228) -> hm rows (fp16, pitch dim)
         GemmEpilogue e{};
-        e.out = h->hm; e.ldo = dim; e.out_f16 = 1; e.bias = h->w.ds0_b; e.act_gelu = 1; e.row_valid = h->valid;
+        e.out = h->hm; e.ldo = dim; e.out_f16 = 1; e.bias = h->w.ds0_b; e.act_gelu = h->gelu_mode; e.row_valid = h->valid;
         if ((st = voc_gemm(h->mel16, MEL_PAD, 3, LA.rows, h->w.ds0_w, dim, e, s))) return (ctp_status)st;
     }
     GroupLayout LB;
@@ -840,7 +842,7 @@ extern "C" ctp_status ctp_voc_encode(ctp_voc* h, int32_t n_samples, const float*
         g.A = h->hm + (long long)(row0 - 1) * dim; g.a_rows = T2; g.lda = 2LL * dim;
         g.B = h->w.ds2_w; g.b_rows = dim; g.ldb = 4LL * dim; g.K = 4LL * dim;
         g.block_n = dim >= 256 ? 256 : 128; g.split_k = 1;
-        g.epi.out = h->x0 + (long long)LB.row0[0] * dim; g.epi.ldo = dim; g.epi.out_f16 = 1; g.epi.bias = h->w.ds2_b; g.epi.act_gelu = 1;
+        g.epi.out = h->x0 + (long long)LB.row0[0] * dim; g.epi.ldo = dim; g.epi.out_f16 = 1; g.epi.bias = h->w.ds2_b; g.epi.act_gelu = h->gelu_mode;
         g.epi.T = T2; g.epi.F = dim;
         if ((st = gemm_launch(g, s))) return (ctp_status)st;
     }
