@@ -366,7 +366,10 @@ class Vocos:
 class VocoderEngine:
     """One libctp vocoder handle bound to a DVAE and/or a Vocos weight set."""
 
-    def __init__(self, dvae: Optional[DVAE], vocos: Optional[Vocos], max_frames: int = 1 << 15):
+    # Rows of one workspace group.  74 * 512: the persistent GEMMs then run in whole waves of 128- / 256-row tiles on 148 SMs, and a
+    # configs[1] batch (32 utterances x 512 code frames = 33 000 mel rows with their guard rows) is ONE group — with 32 768 rows it
+    # was 31 utterances plus a second ~190-launch pass for the last one.
+    def __init__(self, dvae: Optional[DVAE], vocos: Optional[Vocos], max_frames: int = 74 * 512):
         assert dvae is not None or vocos is not None
         self.dvae, self.vocos = dvae, vocos
         self.device = (dvae or vocos).device
